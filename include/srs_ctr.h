@@ -1,0 +1,175 @@
+/*
+ * srs_ctr.h - C ABI of the B200-native SparrowRecSys CTR ranking forward path.
+ *
+ * The reference has no FFI: its hot path is `model.predict(feature_dict)` on a
+ * Keras graph (TFRecModel/src/com/sparrowrecsys/offline/tensorflow/*.py) and, at
+ * serve time, the same graph behind TF-Serving's REST `:predict`
+ * (src/main/java/com/sparrowrecsys/online/recprocess/RecForYouProcess.java:113-138).
+ * This header is the boundary a maintainer binds instead (ctypes stub in
+ * sparrowrecsys_b200/_lib.py, JNI sketch in INTEGRATION.md).  Each entry point
+ * cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SRS_OK (0)
+ * or a negative error code and never throws across the ABI; srs_last_error()
+ * gives the message of the last failure on the calling thread.  The caller owns
+ * all input/output buffers; the library owns its device copy of the weights.
+ */
+#ifndef SRS_CTR_H_
+#define SRS_CTR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRS_ABI_VERSION 1
+
+enum srs_status {
+  SRS_OK = 0,
+  SRS_ERR_INVALID = -1,     /* bad argument / unsupported spec                   */
+  SRS_ERR_MISSING = -2,     /* a required weight tensor was not supplied         */
+  SRS_ERR_SHAPE = -3,       /* a weight tensor has the wrong shape               */
+  SRS_ERR_CUDA = -4,        /* CUDA runtime failure (message has the cudaError)  */
+  SRS_ERR_RANGE = -5,       /* an id in the batch is outside its vocabulary:     */
+                            /* mirrors TF's assert_less_than_num_buckets         */
+  SRS_ERR_NOMEM = -6
+};
+
+/* Model families = the reference's model scripts. */
+enum srs_model_kind {
+  SRS_EMBEDDINGMLP = 0,     /* EmbeddingMLP.py:72-77                             */
+  SRS_WIDENDEEP = 1,        /* WideNDeep.py:101-108                              */
+  SRS_NEURALCF = 2,         /* NeuralCF.py:45-53  (neural_cf_model_1)            */
+  SRS_TWOTOWERS = 3,        /* NeuralCF.py:57-70  (neural_cf_model_2)            */
+  SRS_DEEPFM = 4,           /* DeepFM.py:91-113                                  */
+  SRS_DEEPFM_V2 = 5,        /* DeepFM_v2.py:98-155                               */
+  SRS_DIN = 6               /* DIN.py:125-167                                    */
+};
+
+/* Hyper-parameters the reference hard-codes as module constants
+ * (DIN.py:30-31,66,132; EmbeddingMLP.py:50-58; NeuralCF.py:74). */
+typedef struct srs_spec {
+  int32_t kind;             /* enum srs_model_kind                               */
+  int32_t emb_dim;          /* E                                                 */
+  int32_t n_movies;         /* num_buckets of movieId (valid ids 0..n-1)         */
+  int32_t n_users;          /* num_buckets of userId                             */
+  int32_t n_genres;         /* 19                                                */
+  int32_t hist_len;         /* T (DIN); W&D reads history slot 0 only            */
+  int32_t n_hidden;         /* entries used in hidden[]                          */
+  int32_t hidden[4];        /* MLP widths, model dependent                       */
+  int32_t au_hidden;        /* DIN activation-unit width (32)                    */
+  int32_t cross_buckets;    /* W&D hash_bucket_size (10000)                      */
+  int32_t proj_dim;         /* DeepFM_v2 field projection width (64)             */
+  int32_t final_dense;      /* two towers: Dense(1,sigmoid) after the dot        */
+} srs_spec;
+
+enum srs_location { SRS_HOST = 0, SRS_DEVICE_BORROWED = 1 };
+
+/* One weight tensor in the reference's own (Keras variable) shape: Dense kernels
+ * [in,out], tables [buckets,E], vectors [n] as rows=n, cols=1.  Names are the
+ * canonical ones of sparrowrecsys_b200/weights.py.
+ * SRS_DEVICE_BORROWED: `data` is a device pointer on the model's device that the
+ * library uses in place (no copy; must outlive the model; only for embedding
+ * tables whose emb_dim is a multiple of 4) - this is how a 25.6 GB table is
+ * handed over without a host round trip. */
+typedef struct srs_tensor {
+  const char* name;
+  const float* data;
+  int64_t rows;
+  int64_t cols;
+  int32_t location;         /* enum srs_location                                 */
+} srs_tensor;
+
+/* One batch of ranking instances, structure-of-arrays.  Replaces the feature
+ * dict handed to `model.predict` (keys of the Keras `inputs` dicts, e.g.
+ * DIN.py:34-59) / the `instances` array of the TF-Serving request
+ * (RecForYouProcess.java:118-127).  Genre strings are already vocabulary indices
+ * (-1 = missing / out of vocabulary -> zero vector), integer numerics already
+ * cast to float32 (what numeric_column does).  Pointers a model does not read may
+ * be NULL.  All pointers are host pointers for srs_predict_host* and device
+ * pointers (on the model's device) for srs_predict_device. */
+typedef struct srs_batch {
+  int32_t B;                   /* rows                                            */
+  int32_t hist_stride;         /* elements between consecutive rows of `hist`     */
+  const int32_t* movie_id;     /* [B]                                             */
+  const int32_t* user_id;      /* [B]                                             */
+  const int32_t* hist;         /* [B, T] userRatedMovie<k> in graph position order */
+  const int32_t* movie_genre;  /* [B, 3] movieGenre1..3                           */
+  const int32_t* user_genre;   /* [B, 5] userGenre1..5                            */
+  const float* numerics;       /* [B, 7] movieAvgRating, movieRatingCount,
+                                  movieRatingStddev, releaseYear, userAvgRating,
+                                  userRatingCount, userRatingStddev               */
+} srs_batch;
+
+typedef struct srs_model srs_model;
+
+int srs_abi_version(void);
+
+/* Message of the last error raised on this thread ("" if none). */
+const char* srs_last_error(void);
+
+/* Build a model on CUDA device `device`: validates names/shapes against `spec`,
+ * copies (and privately re-lays-out) the weights into HBM.  Replaces building
+ * the module-level Keras `model` and loading its variables (e.g. DIN.py:169,
+ * NeuralCF.py:74 + the SavedModel under webroot/modeldata/). */
+int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors,
+                     int32_t device, srs_model** out);
+
+void srs_model_destroy(srs_model* m);
+
+/* Forward pass with everything resident in HBM; asynchronous on `stream`
+ * (a cudaStream_t; NULL = the default stream).  `probs` [B] receives the model
+ * output (sigmoid probability; raw dot for two towers without final dense);
+ * `logits` [B] (may be NULL) receives the pre-sigmoid value.  Replaces the
+ * compiled forward that `model.predict` runs per batch (e.g. DIN.py:185).
+ * Out-of-range ids are read as id 0 and latch an error flag that
+ * srs_model_status() reports. */
+int srs_predict_device(srs_model* m, const srs_batch* batch, float* probs, float* logits,
+                       void* stream);
+
+/* Forward pass from host buffers: H2D of the batch, kernel, D2H of the scores,
+ * synchronous.  This is the drop-in for `model.predict(dict) -> float32[B,1]`
+ * and for one TF-Serving `:predict` call.  Returns SRS_ERR_RANGE if an id was
+ * out of range (outputs are still written). */
+int srs_predict_host(srs_model* m, const srs_batch* batch, float* probs, float* logits);
+
+/* Pipelined variant: enqueue on one of srs_num_slots() internal slots (each with
+ * its own stream and device staging) and return; srs_wait_slot() blocks until that
+ * slot's scores are in `probs`.  Host buffers must stay valid (and should be
+ * pinned for the copies to overlap) until the wait returns. */
+int srs_num_slots(void);
+int srs_predict_host_async(srs_model* m, int32_t slot, const srs_batch* batch, float* probs,
+                           float* logits);
+int srs_wait_slot(srs_model* m, int32_t slot);
+
+/* Synchronises the device and reports SRS_ERR_RANGE if any kernel since the last
+ * call saw an out-of-range id, SRS_ERR_CUDA on a sticky CUDA error. */
+int srs_model_status(srs_model* m);
+
+/* Algorithmic bytes per inference of this model (SURVEY.md section 8d definition). */
+int64_t srs_model_bytes_per_inference(const srs_model* m);
+
+/* Name of the kernel variant srs_predict_* dispatches to for this model. */
+const char* srs_model_kernel_name(const srs_model* m);
+
+/* Number of kernels this library has launched in this process (all models). */
+int64_t srs_launch_count(void);
+
+/* Deterministic counter-based fill of a device float buffer:
+ * x[i] = lo + (hi-lo) * u(seed, i), u in [0,1) from a splitmix64 hash of (seed, i).
+ * Used to initialise synthetic embedding tables in place (BASELINE cfg 5). */
+int srs_fill_uniform(float* device_ptr, int64_t n, uint64_t seed, float lo, float hi,
+                     int32_t device, void* stream);
+
+/* Batched cosine similarity of one query embedding against n candidates
+ * (online/model/Embedding.java:33-47, used by SimilarMovieProcess.java:121-137
+ * and RecForYouProcess.java:93-105).  Device pointers. */
+int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, int32_t dim,
+                             float* scores, int32_t device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRS_CTR_H_ */

@@ -1,0 +1,113 @@
+"""ctypes binding of include/srs_ctr.h (the whole FFI surface, nothing else).
+
+The library is built in-tree by `sparrowrecsys_b200.build`; loading fails loudly if
+it is missing - there is no CPU or PyTorch fallback for the forward path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+SRS_OK = 0
+SRS_ERR_INVALID, SRS_ERR_MISSING, SRS_ERR_SHAPE = -1, -2, -3
+SRS_ERR_CUDA, SRS_ERR_RANGE, SRS_ERR_NOMEM = -4, -5, -6
+SRS_HOST, SRS_DEVICE_BORROWED = 0, 1
+ABI_VERSION = 1
+
+
+class SrsSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("emb_dim", C.c_int32), ("n_movies", C.c_int32),
+                ("n_users", C.c_int32), ("n_genres", C.c_int32), ("hist_len", C.c_int32),
+                ("n_hidden", C.c_int32), ("hidden", C.c_int32 * 4), ("au_hidden", C.c_int32),
+                ("cross_buckets", C.c_int32), ("proj_dim", C.c_int32), ("final_dense", C.c_int32)]
+
+
+class SrsTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("rows", C.c_int64),
+                ("cols", C.c_int64), ("location", C.c_int32)]
+
+
+class SrsBatch(C.Structure):
+    _fields_ = [("B", C.c_int32), ("hist_stride", C.c_int32), ("movie_id", C.c_void_p),
+                ("user_id", C.c_void_p), ("hist", C.c_void_p), ("movie_genre", C.c_void_p),
+                ("user_genre", C.c_void_p), ("numerics", C.c_void_p)]
+
+
+EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_destroy",
+           "srs_predict_device", "srs_predict_host", "srs_num_slots", "srs_predict_host_async",
+           "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
+           "srs_model_kernel_name", "srs_launch_count", "srs_fill_uniform",
+           "srs_cosine_scores_device")
+
+_lib = None
+
+
+class SrsError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("srs error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """dlopen libsrs_ctr.so (no CUDA call is made here) and declare signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s not found: build it with `python -m sparrowrecsys_b200.build` "
+            "(needs nvcc; there is no CPU fallback for the CTR forward path)" % path)
+    lib = C.CDLL(path)
+    lib.srs_abi_version.restype = C.c_int
+    lib.srs_last_error.restype = C.c_char_p
+    lib.srs_model_create.restype = C.c_int
+    lib.srs_model_create.argtypes = [C.POINTER(SrsSpec), C.POINTER(SrsTensor), C.c_int32,
+                                     C.c_int32, C.POINTER(C.c_void_p)]
+    lib.srs_model_destroy.restype = None
+    lib.srs_model_destroy.argtypes = [C.c_void_p]
+    lib.srs_predict_device.restype = C.c_int
+    lib.srs_predict_device.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    lib.srs_predict_host.restype = C.c_int
+    lib.srs_predict_host.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_void_p, C.c_void_p]
+    lib.srs_num_slots.restype = C.c_int
+    lib.srs_predict_host_async.restype = C.c_int
+    lib.srs_predict_host_async.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SrsBatch), C.c_void_p,
+                                           C.c_void_p]
+    lib.srs_wait_slot.restype = C.c_int
+    lib.srs_wait_slot.argtypes = [C.c_void_p, C.c_int32]
+    lib.srs_model_status.restype = C.c_int
+    lib.srs_model_status.argtypes = [C.c_void_p]
+    lib.srs_model_bytes_per_inference.restype = C.c_int64
+    lib.srs_model_bytes_per_inference.argtypes = [C.c_void_p]
+    lib.srs_model_kernel_name.restype = C.c_char_p
+    lib.srs_model_kernel_name.argtypes = [C.c_void_p]
+    lib.srs_launch_count.restype = C.c_int64
+    lib.srs_fill_uniform.restype = C.c_int
+    lib.srs_fill_uniform.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_float, C.c_float,
+                                     C.c_int32, C.c_void_p]
+    lib.srs_cosine_scores_device.restype = C.c_int
+    lib.srs_cosine_scores_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_int32, C.c_void_p]
+    if lib.srs_abi_version() != ABI_VERSION:
+        raise ImportError("libsrs_ctr.so ABI version %d != %d" % (lib.srs_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc == SRS_OK:
+        return
+    msg = load().srs_last_error().decode("utf-8", "replace")
+    if rc == SRS_ERR_RANGE:
+        raise ValueError(msg)            # mirrors TF's assert on identity columns
+    if rc == SRS_ERR_MISSING:
+        raise KeyError(msg)
+    raise SrsError(rc, msg)

@@ -1,0 +1,138 @@
+// kernels.h - parameter blocks (device pointers into the model's private weight
+// layout) and launch entry points of the fused per-model forward kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace srs {
+
+// ---- NeuralCF / two towers (NeuralCF.py:45-70) ------------------------------------
+// One thread per row.  All Dense weights live in one small blob that each CTA copies
+// to shared memory; offsets are in floats.  Hidden widths are zero-padded to HP.
+struct NcfParams {
+  const float* movie;      // [n_movies][EP]
+  const float* user;       // [n_users][EP]
+  const float* blob;       // dense weights, layout below
+  int blob_floats;
+  int n_movies, n_users;
+  int EP, HP;
+  int n_layers;            // hidden layers (1..3)
+  int two_towers;          // 0: neural_cf_model_1, 1: neural_cf_model_2
+  int final_dense;         // two towers only
+  // neuralcf:  L0 kernel [2EP][HP] @w_off[0], bias @b_off[0]; Ll kernel [HP][HP] @w_off[l]
+  //            out kernel [HP] @out_w, bias @out_b
+  // twotowers: item tower @w_off[l]/b_off[l], user tower @w_off[3+l]/b_off[3+l];
+  //            out kernel [1] @out_w, bias @out_b
+  int w_off[6], b_off[6];
+  int out_w, out_b;
+};
+
+// ---- EmbeddingMLP / Wide&Deep (EmbeddingMLP.py:72-77, WideNDeep.py:101-107) --------
+struct EmbMlpParams {
+  const float* genre[8];   // movieGenre1..3, userGenre1..5 tables [19][EP]
+  const float* movie;      // [n_movies][EP]
+  const float* user;       // [n_users][EP]
+  const float* W1;         // [KP = 10*EP + 8][128] rows in tile order, zero padded
+  const float* b1;         // [128]
+  const float* W2;         // [128][128]
+  const float* b2;         // [128]
+  const float* w3;         // [128] deep rows of dense_2
+  const float* wide;       // [cross_buckets] wide rows of dense_2 (nullptr for EmbeddingMLP)
+  float b3;
+  int n_movies, n_users, n_genres, cross_buckets;
+  int EP;
+};
+
+// ---- DeepFM (DeepFM.py:91-113) -----------------------------------------------------
+struct DeepFmParams {
+  const float* fm_movie;   // [n_movies][EP]
+  const float* fm_user;    // [n_users][EP]
+  const float* fm_mgenre;  // [19][EP]
+  const float* fm_ugenre;  // [19][EP]
+  const float* deep_movie; // [n_movies][EP]
+  const float* deep_user;  // [n_users][EP]
+  const float* W1;         // [KP = 2*EP + 8][64]
+  const float* b1;
+  const float* W2;         // [64][64]
+  const float* b2;
+  const float* first;      // [fm1_width] one-hot rows of dense_2 (movieGenre1|movieId|userGenre1|userId)
+  const float* wdeep;      // [64]
+  float wdot[4];
+  float bout;
+  int n_movies, n_users, n_genres;
+  int EP;
+};
+
+// ---- DeepFM_v2 (DeepFM_v2.py:98-155) -----------------------------------------------
+struct DeepFm2Params {
+  const float* mgenre;     // [19][EP]
+  const float* movie;      // [n_movies][EP]
+  const float* ugenre;     // [19][EP]
+  const float* user;       // [n_users][EP]
+  const float* first;      // [fm1_width] first_cat kernel
+  const float* first_num;  // [8]
+  float first_bias;        // first_cat bias + first_num bias
+  const float* proj[4];    // [EP][64] each, field order movieGenre1, movieId, userGenre1, userId
+  const float* proj_b[4];  // [64]
+  const float* proj_num;   // [8][64]
+  const float* proj_num_b; // [64]
+  const float* Wd;         // [320][32]
+  const float* bd;         // [32]
+  const float* Wd1;        // [32][16]
+  const float* bd1;        // [16]
+  const float* wout;       // [1 + 64 + 16]
+  float bout;
+  int n_movies, n_users, n_genres;
+  int EP;
+};
+
+// ---- DIN (DIN.py:125-167) ------------------------------------------------------------
+struct DinParams {
+  const float* movie;      // shared candidate/history table [n_movies][EP]
+  const float* user;       // [n_users][EP]
+  const float* ugenre;     // [19][EP]
+  const float* mgenre;     // [19][EP]
+  // activation unit, algebraically folded (DESIGN.md "DIN activation unit"):
+  //   Dense32([h-c, h, c, h*c]) = h.(W_sub+W_h) + (h*c).W_prod + c.(W_c-W_sub) + b
+  const float* au_wh;      // [EP][32]  W_sub + W_h
+  const float* au_wp;      // [EP][32]  W_prod
+  const float* au_wc;      // [EP][32]  W_c - W_sub
+  const float* au_b;       // [32]
+  const float* au_alpha;   // [T][32]   per-position PReLU
+  const float* au_wout;    // [32]
+  float au_bout;
+  // top MLP, first kernel permuted to the tile order
+  //   [userGenre1 | userId | pooled | candidate | movieGenre1] x EP, then 7 numerics + pad
+  const float* W1;         // [KP = 5*EP + 8][128]
+  const float* b1;         // [128]
+  const float* a1;         // [128] PReLU alpha
+  const float* W2;         // [128][64]
+  const float* b2;         // [64]
+  const float* a2;         // [64]
+  const float* w3;         // [64]
+  float b3;
+  int n_movies, n_users, n_genres;
+  int T;
+  int EP;
+};
+
+// launchers (defined next to their kernels); return cudaGetLastError()
+cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_embmlp(const EmbMlpParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_deepfm2(const DeepFm2Params& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_din(const DinParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, float hi,
+                                cudaStream_t s);
+cudaError_t launch_cosine(const float* q, const float* c, int n, int dim, float* out,
+                          cudaStream_t s);
+
+// one-time per-device kernel attribute setup (dynamic shared memory opt-in)
+cudaError_t setup_kernel_attributes();
+
+extern int64_t g_launch_count;   // kernels launched by this library
+
+}  // namespace srs

@@ -1,0 +1,789 @@
+// model.cu - the C ABI (include/srs_ctr.h): model construction (validation + the private
+// device re-layout of the reference's weights), and the predict entry points.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/srs_ctr.h"
+#include "kernels.h"
+
+namespace srs {
+cudaError_t setup_embmlp_attributes();
+cudaError_t setup_deepfm_attributes();
+cudaError_t setup_din_attributes();
+}  // namespace srs
+
+using namespace srs;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(SRS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+constexpr int kSlots = 4;           // public pipelining slots; slot kSlots is private to
+                                    // the synchronous srs_predict_host
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  int capacity = 0;                 // rows the device staging can hold
+  int32_t* d_movie = nullptr;
+  int32_t* d_user = nullptr;
+  int32_t* d_hist = nullptr;
+  int32_t* d_mg = nullptr;
+  int32_t* d_ug = nullptr;
+  float* d_num = nullptr;
+  float* d_probs = nullptr;
+  float* d_logits = nullptr;
+  int* h_err = nullptr;             // pinned mirror of the device error flag
+};
+
+}  // namespace
+
+struct srs_model {
+  srs_spec spec{};
+  int device = 0;
+  int EP = 0;
+  int hist_cols = 0;                // history columns the model reads (T for DIN, 1 for W&D)
+  std::vector<void*> owned;
+  int* err_flag = nullptr;
+  NcfParams ncf{};
+  EmbMlpParams emb{};
+  DeepFmParams fm{};
+  DeepFm2Params fm2{};
+  DinParams din{};
+  const char* kernel_name = "";
+  int64_t bytes_per_inf = 0;
+  Slot slots[kSlots + 1];
+  std::mutex mu;
+};
+
+namespace {
+
+int round_ep(int E) {
+  if (E <= 12) return 12;
+  if (E <= 16) return 16;
+  if (E <= 32) return 32;
+  return 64;
+}
+
+struct Builder {
+  srs_model* m;
+  std::map<std::string, const srs_tensor*> by_name;
+  int status = SRS_OK;
+
+  const srs_tensor* need(const char* name, int64_t rows, int64_t cols) {
+    if (status != SRS_OK) return nullptr;
+    auto it = by_name.find(name);
+    if (it == by_name.end()) {
+      status = fail(SRS_ERR_MISSING, "missing weight tensor '%s'", name);
+      return nullptr;
+    }
+    const srs_tensor* t = it->second;
+    if (t->rows != rows || t->cols != cols) {
+      status = fail(SRS_ERR_SHAPE, "weight '%s' has shape [%lld,%lld], expected [%lld,%lld]", name,
+                    (long long)t->rows, (long long)t->cols, (long long)rows, (long long)cols);
+      return nullptr;
+    }
+    if (t->data == nullptr) {
+      status = fail(SRS_ERR_INVALID, "weight '%s' has a null data pointer", name);
+      return nullptr;
+    }
+    return t;
+  }
+
+  // dense host tensor -> float vector (must be SRS_HOST)
+  const float* host(const char* name, int64_t rows, int64_t cols) {
+    const srs_tensor* t = need(name, rows, cols);
+    if (!t) return nullptr;
+    if (t->location != SRS_HOST) {
+      status = fail(SRS_ERR_INVALID, "weight '%s' must be a host tensor", name);
+      return nullptr;
+    }
+    return t->data;
+  }
+
+  float* upload(const std::vector<float>& v) {
+    if (status != SRS_OK) return nullptr;
+    float* d = nullptr;
+    size_t bytes = (v.size() ? v.size() : 1) * sizeof(float);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) {
+      status = fail(SRS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return nullptr;
+    }
+    m->owned.push_back(d);
+    if (!v.empty()) {
+      e = cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        status = fail(SRS_ERR_CUDA, "cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+        return nullptr;
+      }
+    }
+    return d;
+  }
+
+  // embedding table [V][E] -> device [V][EP] (zero padded rows), chunked upload
+  const float* table(const char* name, int64_t V, int E) {
+    const srs_tensor* t = need(name, V, E);
+    if (!t) return nullptr;
+    const int EP = m->EP;
+    if (t->location == SRS_DEVICE_BORROWED) {
+      if (E != EP) {
+        status = fail(SRS_ERR_INVALID,
+                      "borrowed device table '%s' needs emb_dim == padded dim (%d != %d)", name, E, EP);
+        return nullptr;
+      }
+      return t->data;
+    }
+    float* d = nullptr;
+    size_t bytes = (size_t)V * EP * sizeof(float);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) {
+      status = fail(SRS_ERR_NOMEM, "cudaMalloc(%zu) for '%s' failed: %s", bytes, name,
+                    cudaGetErrorString(e));
+      return nullptr;
+    }
+    m->owned.push_back(d);
+    if (E == EP) {
+      e = cudaMemcpy(d, t->data, bytes, cudaMemcpyHostToDevice);
+    } else {
+      const int64_t chunk = 1 << 16;
+      std::vector<float> buf((size_t)std::min<int64_t>(chunk, V) * EP);
+      e = cudaSuccess;
+      for (int64_t v0 = 0; v0 < V && e == cudaSuccess; v0 += chunk) {
+        const int64_t nv = std::min<int64_t>(chunk, V - v0);
+        std::fill(buf.begin(), buf.end(), 0.f);
+        for (int64_t v = 0; v < nv; ++v)
+          memcpy(&buf[(size_t)v * EP], t->data + (size_t)(v0 + v) * E, (size_t)E * sizeof(float));
+        e = cudaMemcpy(d + (size_t)v0 * EP, buf.data(), (size_t)nv * EP * sizeof(float),
+                       cudaMemcpyHostToDevice);
+      }
+    }
+    if (e != cudaSuccess) {
+      status = fail(SRS_ERR_CUDA, "table upload '%s' failed: %s", name, cudaGetErrorString(e));
+      return nullptr;
+    }
+    return d;
+  }
+
+  // Dense kernel [K][N] -> [dev_rows][NP]: device row i takes reference row map[i]
+  // (-1 = zero row); columns zero padded to NP.
+  std::vector<float> permute(const float* ref, int N, const std::vector<int>& map, int NP) {
+    std::vector<float> out(map.size() * (size_t)NP, 0.f);
+    if (!ref) return out;
+    for (size_t i = 0; i < map.size(); ++i)
+      if (map[i] >= 0)
+        for (int j = 0; j < N; ++j) out[i * NP + j] = ref[(size_t)map[i] * N + j];
+    return out;
+  }
+
+  std::vector<float> padvec(const float* ref, int n, int np) {
+    std::vector<float> out(np, 0.f);
+    if (ref)
+      for (int i = 0; i < n; ++i) out[i] = ref[i];
+    return out;
+  }
+};
+
+std::vector<int> iota_map(int start, int n, int padded) {
+  std::vector<int> v(padded, -1);
+  for (int i = 0; i < n; ++i) v[i] = start + i;
+  return v;
+}
+
+void append(std::vector<int>& a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); }
+
+// ------------------------------------------------------------------------------------
+int build_ncf(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP;
+  const bool two = s.kind == SRS_TWOTOWERS;
+  if (s.n_hidden < 1 || s.n_hidden > 3) return fail(SRS_ERR_INVALID, "1..3 hidden layers supported");
+  int hmax = 0;
+  for (int i = 0; i < s.n_hidden; ++i) hmax = std::max(hmax, s.hidden[i]);
+  if (hmax > 32 || hmax < 1) return fail(SRS_ERR_INVALID, "hidden widths must be in 1..32");
+  const int HP = hmax <= 16 ? 16 : 32;
+  NcfParams& p = m->ncf;
+  p.movie = B.table("movieId_embedding", s.n_movies, E);
+  p.user = B.table("userId_embedding", s.n_users, E);
+  p.n_movies = s.n_movies; p.n_users = s.n_users;
+  p.EP = EP; p.HP = HP; p.n_layers = s.n_hidden; p.two_towers = two; p.final_dense = s.final_dense;
+  std::vector<float> blob;
+  auto push = [&](const std::vector<float>& v) {
+    int off = (int)blob.size();
+    blob.insert(blob.end(), v.begin(), v.end());
+    while (blob.size() % 4) blob.push_back(0.f);
+    return off;
+  };
+  char name[64];
+  if (!two) {
+    int in = 2 * E;
+    for (int l = 0; l < s.n_hidden; ++l) {
+      const int out = s.hidden[l];
+      snprintf(name, sizeof(name), "dense_%d/kernel", l);
+      const float* k = B.host(name, in, out);
+      snprintf(name, sizeof(name), "dense_%d/bias", l);
+      const float* bias = B.host(name, out, 1);
+      std::vector<int> map;
+      if (l == 0) { append(map, iota_map(0, E, EP)); append(map, iota_map(E, E, EP)); }
+      else map = iota_map(0, in, HP);
+      p.w_off[l] = push(B.permute(k, out, map, HP));
+      p.b_off[l] = push(B.padvec(bias, out, HP));
+      in = out;
+    }
+    snprintf(name, sizeof(name), "dense_%d/kernel", s.n_hidden);
+    const float* k = B.host(name, in, 1);
+    snprintf(name, sizeof(name), "dense_%d/bias", s.n_hidden);
+    const float* bias = B.host(name, 1, 1);
+    p.out_w = push(B.padvec(k, in, HP));
+    p.out_b = push(B.padvec(bias, 1, 4));
+  } else {
+    const char* sides[2] = {"item", "user"};
+    for (int t = 0; t < 2; ++t) {
+      int in = E;
+      for (int l = 0; l < s.n_hidden; ++l) {
+        const int out = s.hidden[l];
+        snprintf(name, sizeof(name), "%s_dense_%d/kernel", sides[t], l);
+        const float* k = B.host(name, in, out);
+        snprintf(name, sizeof(name), "%s_dense_%d/bias", sides[t], l);
+        const float* bias = B.host(name, out, 1);
+        std::vector<int> map = l == 0 ? iota_map(0, E, EP) : iota_map(0, in, HP);
+        p.w_off[3 * t + l] = push(B.permute(k, out, map, HP));
+        p.b_off[3 * t + l] = push(B.padvec(bias, out, HP));
+        in = out;
+      }
+    }
+    if (s.final_dense) {
+      const float* k = B.host("dense_out/kernel", 1, 1);
+      const float* bias = B.host("dense_out/bias", 1, 1);
+      p.out_w = push(B.padvec(k, 1, 4));
+      p.out_b = push(B.padvec(bias, 1, 4));
+    } else {
+      p.out_w = push(std::vector<float>(4, 1.f));
+      p.out_b = push(std::vector<float>(4, 0.f));
+    }
+  }
+  if (B.status != SRS_OK) return B.status;
+  p.blob = B.upload(blob);
+  p.blob_floats = (int)blob.size();
+  m->kernel_name = two ? "ncf_kernel<two_towers>" : "ncf_kernel<neural_cf_model_1>";
+  return B.status;
+}
+
+int build_embmlp(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP;
+  const bool wide = s.kind == SRS_WIDENDEEP;
+  if (s.n_hidden != 2 || s.hidden[0] > 128 || s.hidden[1] > 128 || s.hidden[0] < 1 || s.hidden[1] < 1)
+    return fail(SRS_ERR_INVALID, "EmbeddingMLP/W&D need two hidden layers of width <= 128");
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  EmbMlpParams& p = m->emb;
+  char name[64];
+  for (int k = 0; k < 3; ++k) {
+    snprintf(name, sizeof(name), "movieGenre%d_embedding", k + 1);
+    p.genre[k] = B.table(name, s.n_genres, E);
+  }
+  for (int k = 0; k < 5; ++k) {
+    snprintf(name, sizeof(name), "userGenre%d_embedding", k + 1);
+    p.genre[3 + k] = B.table(name, s.n_genres, E);
+  }
+  p.movie = B.table("movieId_embedding", s.n_movies, E);
+  p.user = B.table("userId_embedding", s.n_users, E);
+  // reference row order of dense/kernel: DenseFeatures sorted concat
+  std::vector<int> map;
+  for (int k = 0; k < 3; ++k) append(map, iota_map(1 + k * E, E, EP));         // movieGenre1..3
+  append(map, iota_map(1 + 3 * E, E, EP));                                        // movieId
+  for (int k = 0; k < 5; ++k) append(map, iota_map(5 + 4 * E + k * E, E, EP));   // userGenre1..5
+  append(map, iota_map(5 + 9 * E, E, EP));                                        // userId
+  const int nums[8] = {0, 1 + 4 * E, 2 + 4 * E, 3 + 4 * E, 4 + 4 * E, 5 + 10 * E, 6 + 10 * E, -1};
+  for (int j = 0; j < 8; ++j) map.push_back(nums[j]);
+  const float* k1 = B.host("dense/kernel", 7 + 10 * E, h0);
+  const float* b1 = B.host("dense/bias", h0, 1);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  const float* b2 = B.host("dense_1/bias", h1, 1);
+  const int last_in = h1 + (wide ? s.cross_buckets : 0);
+  const float* k3 = B.host("dense_2/kernel", last_in, 1);
+  const float* b3 = B.host("dense_2/bias", 1, 1);
+  if (B.status != SRS_OK) return B.status;
+  p.W1 = B.upload(B.permute(k1, h0, map, 128));
+  p.b1 = B.upload(B.padvec(b1, h0, 128));
+  p.W2 = B.upload(B.permute(k2, h1, iota_map(0, h0, 128), 128));
+  p.b2 = B.upload(B.padvec(b2, h1, 128));
+  p.w3 = B.upload(B.padvec(k3, h1, 128));
+  p.wide = nullptr;
+  if (wide) p.wide = B.upload(std::vector<float>(k3 + h1, k3 + h1 + s.cross_buckets));
+  p.b3 = b3[0];
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.cross_buckets = s.cross_buckets; p.EP = EP;
+  m->kernel_name = wide ? "embmlp_kernel<wide&deep>" : "embmlp_kernel";
+  return B.status;
+}
+
+int build_deepfm(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP;
+  if (s.n_hidden != 2 || s.hidden[0] > 64 || s.hidden[1] > 64 || s.hidden[0] < 1 || s.hidden[1] < 1)
+    return fail(SRS_ERR_INVALID, "DeepFM needs two hidden layers of width <= 64");
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  const int64_t fm1 = (int64_t)2 * s.n_genres + s.n_movies + s.n_users;
+  DeepFmParams& p = m->fm;
+  p.fm_movie = B.table("fm_movieId_embedding", s.n_movies, E);
+  p.fm_user = B.table("fm_userId_embedding", s.n_users, E);
+  p.fm_mgenre = B.table("fm_movieGenre1_embedding", s.n_genres, E);
+  p.fm_ugenre = B.table("fm_userGenre1_embedding", s.n_genres, E);
+  p.deep_movie = B.table("deep_movieId_embedding", s.n_movies, E);
+  p.deep_user = B.table("deep_userId_embedding", s.n_users, E);
+  std::vector<int> map;
+  append(map, iota_map(1, E, EP));            // deep movieId emb
+  append(map, iota_map(5 + E, E, EP));        // deep userId emb
+  const int nums[8] = {0, 1 + E, 2 + E, 3 + E, 4 + E, 5 + 2 * E, 6 + 2 * E, -1};
+  for (int j = 0; j < 8; ++j) map.push_back(nums[j]);
+  const float* k1 = B.host("dense/kernel", 7 + 2 * E, h0);
+  const float* b1 = B.host("dense/bias", h0, 1);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  const float* b2 = B.host("dense_1/bias", h1, 1);
+  const float* k3 = B.host("dense_2/kernel", fm1 + 4 + h1, 1);
+  const float* b3 = B.host("dense_2/bias", 1, 1);
+  if (B.status != SRS_OK) return B.status;
+  p.W1 = B.upload(B.permute(k1, h0, map, 64));
+  p.b1 = B.upload(B.padvec(b1, h0, 64));
+  p.W2 = B.upload(B.permute(k2, h1, iota_map(0, h0, 64), 64));
+  p.b2 = B.upload(B.padvec(b2, h1, 64));
+  p.first = B.upload(std::vector<float>(k3, k3 + fm1));
+  for (int d = 0; d < 4; ++d) p.wdot[d] = k3[fm1 + d];
+  p.wdeep = B.upload(B.padvec(k3 + fm1 + 4, h1, 64));
+  p.bout = b3[0];
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres; p.EP = EP;
+  m->kernel_name = "deepfm_kernel";
+  return B.status;
+}
+
+int build_deepfm2(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP, P = 64;
+  if (s.proj_dim != P) return fail(SRS_ERR_INVALID, "DeepFM_v2 projection width must be 64");
+  if (s.n_hidden != 2 || s.hidden[0] > 32 || s.hidden[1] > 16 || s.hidden[0] < 1 || s.hidden[1] < 1)
+    return fail(SRS_ERR_INVALID, "DeepFM_v2 needs hidden widths <= (32, 16)");
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  const int64_t fm1 = (int64_t)2 * s.n_genres + s.n_movies + s.n_users;
+  DeepFm2Params& p = m->fm2;
+  p.mgenre = B.table("movieGenre1_embedding", s.n_genres, E);
+  p.movie = B.table("movieId_embedding", s.n_movies, E);
+  p.ugenre = B.table("userGenre1_embedding", s.n_genres, E);
+  p.user = B.table("userId_embedding", s.n_users, E);
+  const float* fc = B.host("first_cat/kernel", fm1, 1);
+  const float* fcb = B.host("first_cat/bias", 1, 1);
+  const float* fn = B.host("first_num/kernel", 7, 1);
+  const float* fnb = B.host("first_num/bias", 1, 1);
+  const char* fields[4] = {"movieGenre1", "movieId", "userGenre1", "userId"};
+  const float* pk[4]; const float* pb[4];
+  char name[64];
+  for (int f = 0; f < 4; ++f) {
+    snprintf(name, sizeof(name), "proj_%s/kernel", fields[f]);
+    pk[f] = B.host(name, E, P);
+    snprintf(name, sizeof(name), "proj_%s/bias", fields[f]);
+    pb[f] = B.host(name, P, 1);
+  }
+  const float* pnk = B.host("proj_num/kernel", 7, P);
+  const float* pnb = B.host("proj_num/bias", P, 1);
+  const float* dk = B.host("deep/kernel", 5 * P, h0);
+  const float* db = B.host("deep/bias", h0, 1);
+  const float* d1k = B.host("deep_1/kernel", h0, h1);
+  const float* d1b = B.host("deep_1/bias", h1, 1);
+  const float* ok = B.host("out/kernel", 1 + P + h1, 1);
+  const float* ob = B.host("out/bias", 1, 1);
+  if (B.status != SRS_OK) return B.status;
+  p.first = B.upload(std::vector<float>(fc, fc + fm1));
+  p.first_num = B.upload(B.padvec(fn, 7, 8));
+  p.first_bias = fcb[0] + fnb[0];
+  for (int f = 0; f < 4; ++f) {
+    p.proj[f] = B.upload(B.permute(pk[f], P, iota_map(0, E, EP), P));
+    p.proj_b[f] = B.upload(B.padvec(pb[f], P, P));
+  }
+  p.proj_num = B.upload(B.permute(pnk, P, iota_map(0, 7, 8), P));
+  p.proj_num_b = B.upload(B.padvec(pnb, P, P));
+  p.Wd = B.upload(B.permute(dk, h0, iota_map(0, 5 * P, 5 * P), 32));
+  p.bd = B.upload(B.padvec(db, h0, 32));
+  p.Wd1 = B.upload(B.permute(d1k, h1, iota_map(0, h0, 32), 16));
+  p.bd1 = B.upload(B.padvec(d1b, h1, 16));
+  p.wout = B.upload(B.padvec(ok, 1 + P + h1, 1 + P + 16));
+  p.bout = ob[0];
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres; p.EP = EP;
+  m->kernel_name = "deepfm2_kernel";
+  return B.status;
+}
+
+int build_din(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP, T = s.hist_len, A = 32;
+  if (s.au_hidden != A) return fail(SRS_ERR_INVALID, "DIN activation-unit width must be 32");
+  if (s.n_hidden != 2 || s.hidden[0] > 128 || s.hidden[1] > 64 || s.hidden[0] < 1 || s.hidden[1] < 1)
+    return fail(SRS_ERR_INVALID, "DIN needs hidden widths <= (128, 64)");
+  if (T < 1) return fail(SRS_ERR_INVALID, "hist_len must be >= 1");
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  DinParams& p = m->din;
+  p.movie = B.table("embedding", s.n_movies, E);
+  p.user = B.table("userId_embedding", s.n_users, E);
+  p.ugenre = B.table("userGenre1_embedding", s.n_genres, E);
+  p.mgenre = B.table("movieGenre1_embedding", s.n_genres, E);
+  const float* au = B.host("au_dense/kernel", 4 * E, A);
+  const float* aub = B.host("au_dense/bias", A, 1);
+  const float* alpha = B.host("au_prelu/alpha", T, A);
+  const float* auo = B.host("au_out/kernel", A, 1);
+  const float* auob = B.host("au_out/bias", 1, 1);
+  const float* k1 = B.host("dense/kernel", 5 * E + 7, h0);
+  const float* b1 = B.host("dense/bias", h0, 1);
+  const float* a1 = B.host("prelu/alpha", h0, 1);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  const float* b2 = B.host("dense_1/bias", h1, 1);
+  const float* a2 = B.host("prelu_1/alpha", h1, 1);
+  const float* k3 = B.host("dense_2/kernel", h1, 1);
+  const float* b3 = B.host("dense_2/bias", 1, 1);
+  if (B.status != SRS_OK) return B.status;
+  // activation-unit fold: rows of au_dense/kernel are [h-c | h | c | h*c] blocks of E
+  std::vector<float> wh((size_t)EP * A, 0.f), wp((size_t)EP * A, 0.f), wc((size_t)EP * A, 0.f);
+  for (int e = 0; e < E; ++e)
+    for (int j = 0; j < A; ++j) {
+      const float w_sub = au[(size_t)e * A + j], w_h = au[(size_t)(E + e) * A + j];
+      const float w_c = au[(size_t)(2 * E + e) * A + j], w_p = au[(size_t)(3 * E + e) * A + j];
+      wh[(size_t)e * A + j] = w_sub + w_h;
+      wp[(size_t)e * A + j] = w_p;
+      wc[(size_t)e * A + j] = w_c - w_sub;
+    }
+  p.au_wh = B.upload(wh); p.au_wp = B.upload(wp); p.au_wc = B.upload(wc);
+  p.au_b = B.upload(std::vector<float>(aub, aub + A));
+  p.au_alpha = B.upload(std::vector<float>(alpha, alpha + (size_t)T * A));
+  p.au_wout = B.upload(std::vector<float>(auo, auo + A));
+  p.au_bout = auob[0];
+  // top kernel rows: [user_profile | pooled | candidate | context] (DIN.py:161-162)
+  const int base = 3 + 4 * E;
+  std::vector<int> map;
+  append(map, iota_map(1, E, EP));               // userGenre1 emb
+  append(map, iota_map(1 + E, E, EP));           // userId emb
+  append(map, iota_map(3 + 2 * E, E, EP));       // pooled behaviours
+  append(map, iota_map(3 + 3 * E, E, EP));       // candidate emb
+  append(map, iota_map(base + 1, E, EP));        // movieGenre1 emb
+  const int nums[8] = {base, base + 1 + E, base + 2 + E, base + 3 + E, 0, 1 + 2 * E, 2 + 2 * E, -1};
+  for (int j = 0; j < 8; ++j) map.push_back(nums[j]);
+  p.W1 = B.upload(B.permute(k1, h0, map, 128));
+  p.b1 = B.upload(B.padvec(b1, h0, 128));
+  p.a1 = B.upload(B.padvec(a1, h0, 128));
+  p.W2 = B.upload(B.permute(k2, h1, iota_map(0, h0, 128), 64));
+  p.b2 = B.upload(B.padvec(b2, h1, 64));
+  p.a2 = B.upload(B.padvec(a2, h1, 64));
+  p.w3 = B.upload(B.padvec(k3, h1, 64));
+  p.b3 = b3[0];
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.T = T; p.EP = EP;
+  m->kernel_name = "din_kernel";
+  return B.status;
+}
+
+int64_t bytes_per_inference(const srs_spec& s) {
+  const int64_t E = s.emb_dim, T = s.hist_len;
+  switch (s.kind) {
+    case SRS_EMBEDDINGMLP: return 10 * 4 * E + 10 * 4 + 7 * 4 + 4;
+    case SRS_WIDENDEEP: return 10 * 4 * E + 11 * 4 + 7 * 4 + 4 + 4;
+    case SRS_NEURALCF:
+    case SRS_TWOTOWERS: return 2 * 4 * E + 2 * 4 + 4;
+    case SRS_DEEPFM: return 6 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4;
+    case SRS_DEEPFM_V2: return 4 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4;
+    case SRS_DIN: return (T + 1) * 4 * E + 3 * 4 * E + 28 + 4 * (T + 4) + 4;
+  }
+  return 0;
+}
+
+int check_batch(const srs_model* m, const srs_batch* b) {
+  if (!m || !b) return fail(SRS_ERR_INVALID, "null model or batch");
+  if (b->B < 0) return fail(SRS_ERR_INVALID, "negative batch size");
+  if (b->B == 0) return SRS_OK;
+  if (!b->movie_id || !b->user_id) return fail(SRS_ERR_INVALID, "movie_id / user_id are required");
+  const int k = m->spec.kind;
+  const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
+  if (dense_feats && (!b->movie_genre || !b->user_genre || !b->numerics))
+    return fail(SRS_ERR_INVALID, "movie_genre / user_genre / numerics are required for this model");
+  if (m->hist_cols > 0) {
+    if (!b->hist) return fail(SRS_ERR_INVALID, "hist is required for this model");
+    if (b->hist_stride < m->hist_cols)
+      return fail(SRS_ERR_INVALID, "hist_stride %d < history columns %d", b->hist_stride, m->hist_cols);
+  }
+  return SRS_OK;
+}
+
+int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  switch (m->spec.kind) {
+    case SRS_NEURALCF:
+    case SRS_TWOTOWERS: e = launch_ncf(m->ncf, v, stream); break;
+    case SRS_EMBEDDINGMLP:
+    case SRS_WIDENDEEP: e = launch_embmlp(m->emb, v, stream); break;
+    case SRS_DEEPFM: e = launch_deepfm(m->fm, v, stream); break;
+    case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
+    case SRS_DIN: e = launch_din(m->din, v, stream); break;
+    default: return fail(SRS_ERR_INVALID, "unknown model kind");
+  }
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return SRS_OK;
+}
+
+int ensure_slot(srs_model* m, Slot& s, int B) {
+  if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  if (!s.h_err) {
+    CUDA_TRY(cudaMallocHost(&s.h_err, sizeof(int)));
+    *s.h_err = 0;
+  }
+  if (B <= s.capacity) return SRS_OK;
+  int cap = std::max(B, 1024);
+  cudaFree(s.d_movie); cudaFree(s.d_user); cudaFree(s.d_hist); cudaFree(s.d_mg); cudaFree(s.d_ug);
+  cudaFree(s.d_num); cudaFree(s.d_probs); cudaFree(s.d_logits);
+  s.capacity = 0;
+  const int hc = std::max(m->hist_cols, 1);
+  CUDA_TRY(cudaMalloc(&s.d_movie, (size_t)cap * 4));
+  CUDA_TRY(cudaMalloc(&s.d_user, (size_t)cap * 4));
+  CUDA_TRY(cudaMalloc(&s.d_hist, (size_t)cap * hc * 4));
+  CUDA_TRY(cudaMalloc(&s.d_mg, (size_t)cap * 3 * 4));
+  CUDA_TRY(cudaMalloc(&s.d_ug, (size_t)cap * 5 * 4));
+  CUDA_TRY(cudaMalloc(&s.d_num, (size_t)cap * 7 * 4));
+  CUDA_TRY(cudaMalloc(&s.d_probs, (size_t)cap * 4));
+  CUDA_TRY(cudaMalloc(&s.d_logits, (size_t)cap * 4));
+  s.capacity = cap;
+  return SRS_OK;
+}
+
+int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits) {
+  int rc = check_batch(m, b);
+  if (rc != SRS_OK) return rc;
+  if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
+  CUDA_TRY(cudaSetDevice(m->device));
+  rc = ensure_slot(m, s, b->B);
+  if (rc != SRS_OK) return rc;
+  if (b->B == 0) return SRS_OK;
+  const size_t B = (size_t)b->B;
+  const int k = m->spec.kind;
+  const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
+  CUDA_TRY(cudaMemcpyAsync(s.d_movie, b->movie_id, B * 4, cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.d_user, b->user_id, B * 4, cudaMemcpyHostToDevice, s.stream));
+  if (m->hist_cols > 0) {
+    if (b->hist_stride == m->hist_cols) {
+      CUDA_TRY(cudaMemcpyAsync(s.d_hist, b->hist, B * m->hist_cols * 4, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      CUDA_TRY(cudaMemcpy2DAsync(s.d_hist, (size_t)m->hist_cols * 4, b->hist, (size_t)b->hist_stride * 4,
+                                 (size_t)m->hist_cols * 4, B, cudaMemcpyHostToDevice, s.stream));
+    }
+  }
+  if (dense_feats) {
+    CUDA_TRY(cudaMemcpyAsync(s.d_mg, b->movie_genre, B * 3 * 4, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.d_ug, b->user_genre, B * 5 * 4, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.d_num, b->numerics, B * 7 * 4, cudaMemcpyHostToDevice, s.stream));
+  }
+  BatchView v{};
+  v.B = b->B; v.hist_stride = m->hist_cols;
+  v.movie_id = s.d_movie; v.user_id = s.d_user; v.hist = s.d_hist;
+  v.movie_genre = s.d_mg; v.user_genre = s.d_ug; v.numerics = s.d_num;
+  v.probs = s.d_probs; v.logits = logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
+  rc = launch(m, v, s.stream);
+  if (rc != SRS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (logits) CUDA_TRY(cudaMemcpyAsync(logits, s.d_logits, B * 4, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  return SRS_OK;
+}
+
+int wait_slot(srs_model* m, Slot& s) {
+  if (!s.stream) return SRS_OK;
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  if (s.h_err && *s.h_err) {
+    *s.h_err = 0;
+    CUDA_TRY(cudaMemsetAsync(m->err_flag, 0, sizeof(int), s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return fail(SRS_ERR_RANGE, "an id in the batch is outside its vocabulary");
+  }
+  return SRS_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+extern "C" {
+
+int srs_abi_version(void) { return SRS_ABI_VERSION; }
+
+const char* srs_last_error(void) { return g_err.c_str(); }
+
+int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors,
+                     int32_t device, srs_model** out) {
+  if (!spec || !out || (n_tensors > 0 && !tensors)) return fail(SRS_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (spec->kind < SRS_EMBEDDINGMLP || spec->kind > SRS_DIN)
+    return fail(SRS_ERR_INVALID, "unknown model kind %d", spec->kind);
+  if (spec->emb_dim < 1 || spec->emb_dim > 64) return fail(SRS_ERR_INVALID, "emb_dim must be in 1..64");
+  if (spec->n_movies < 1 || spec->n_users < 1 || spec->n_genres < 1)
+    return fail(SRS_ERR_INVALID, "vocabulary sizes must be positive");
+  if (spec->n_hidden < 0 || spec->n_hidden > 4) return fail(SRS_ERR_INVALID, "n_hidden must be in 0..4");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SRS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(SRS_ERR_INVALID, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(setup_embmlp_attributes());
+  CUDA_TRY(setup_deepfm_attributes());
+  CUDA_TRY(setup_din_attributes());
+
+  srs_model* m = new srs_model();
+  m->spec = *spec;
+  m->device = device;
+  m->EP = round_ep(spec->emb_dim);
+  m->hist_cols = spec->kind == SRS_DIN ? spec->hist_len : spec->kind == SRS_WIDENDEEP ? 1 : 0;
+  m->bytes_per_inf = bytes_per_inference(*spec);
+  Builder B{m};
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].name) B.by_name[tensors[i].name] = &tensors[i];
+  int rc;
+  switch (spec->kind) {
+    case SRS_NEURALCF:
+    case SRS_TWOTOWERS: rc = build_ncf(B); break;
+    case SRS_EMBEDDINGMLP:
+    case SRS_WIDENDEEP: rc = build_embmlp(B); break;
+    case SRS_DEEPFM: rc = build_deepfm(B); break;
+    case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
+    default: rc = build_din(B); break;
+  }
+  if (rc == SRS_OK) {
+    e = cudaMalloc(&m->err_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->err_flag, 0, sizeof(int));
+    if (e != cudaSuccess) rc = fail(SRS_ERR_CUDA, "error-flag allocation failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == SRS_OK) {
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(SRS_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc != SRS_OK) {
+    std::string keep = g_err;
+    srs_model_destroy(m);
+    g_err = keep;
+    return rc;
+  }
+  *out = m;
+  return SRS_OK;
+}
+
+void srs_model_destroy(srs_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (Slot& s : m->slots) {
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    cudaFree(s.d_movie); cudaFree(s.d_user); cudaFree(s.d_hist); cudaFree(s.d_mg); cudaFree(s.d_ug);
+    cudaFree(s.d_num); cudaFree(s.d_probs); cudaFree(s.d_logits);
+    if (s.h_err) cudaFreeHost(s.h_err);
+  }
+  for (void* p : m->owned) cudaFree(p);
+  if (m->err_flag) cudaFree(m->err_flag);
+  delete m;
+}
+
+int srs_predict_device(srs_model* m, const srs_batch* b, float* probs, float* logits, void* stream) {
+  int rc = check_batch(m, b);
+  if (rc != SRS_OK) return rc;
+  if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
+  if (b->B == 0) return SRS_OK;
+  CUDA_TRY(cudaSetDevice(m->device));
+  BatchView v{};
+  v.B = b->B; v.hist_stride = b->hist_stride;
+  v.movie_id = b->movie_id; v.user_id = b->user_id; v.hist = b->hist;
+  v.movie_genre = b->movie_genre; v.user_genre = b->user_genre; v.numerics = b->numerics;
+  v.probs = probs; v.logits = logits; v.err_flag = m->err_flag;
+  return launch(m, v, static_cast<cudaStream_t>(stream));
+}
+
+int srs_predict_host(srs_model* m, const srs_batch* b, float* probs, float* logits) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  std::lock_guard<std::mutex> lock(m->mu);
+  Slot& s = m->slots[kSlots];
+  int rc = enqueue_host(m, s, b, probs, logits);
+  if (rc != SRS_OK) return rc;
+  return wait_slot(m, s);
+}
+
+int srs_num_slots(void) { return kSlots; }
+
+int srs_predict_host_async(srs_model* m, int32_t slot, const srs_batch* b, float* probs,
+                           float* logits) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (slot < 0 || slot >= kSlots) return fail(SRS_ERR_INVALID, "slot %d out of range", slot);
+  return enqueue_host(m, m->slots[slot], b, probs, logits);
+}
+
+int srs_wait_slot(srs_model* m, int32_t slot) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (slot < 0 || slot >= kSlots) return fail(SRS_ERR_INVALID, "slot %d out of range", slot);
+  return wait_slot(m, m->slots[slot]);
+}
+
+int srs_model_status(srs_model* m) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  int flag = 0;
+  CUDA_TRY(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+    return fail(SRS_ERR_RANGE, "an id in a batch was outside its vocabulary");
+  }
+  return SRS_OK;
+}
+
+int64_t srs_model_bytes_per_inference(const srs_model* m) { return m ? m->bytes_per_inf : 0; }
+
+const char* srs_model_kernel_name(const srs_model* m) { return m ? m->kernel_name : ""; }
+
+int64_t srs_launch_count(void) { return g_launch_count; }
+
+int srs_fill_uniform(float* device_ptr, int64_t n, uint64_t seed, float lo, float hi,
+                     int32_t device, void* stream) {
+  if (!device_ptr && n > 0) return fail(SRS_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_fill_uniform(device_ptr, n, seed, lo, hi, static_cast<cudaStream_t>(stream)));
+  return SRS_OK;
+}
+
+int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, int32_t dim,
+                             float* scores, int32_t device, void* stream) {
+  if ((!query || !cands || !scores) && n > 0) return fail(SRS_ERR_INVALID, "null pointer");
+  if (dim < 1) return fail(SRS_ERR_INVALID, "dim must be positive");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_cosine(query, cands, n, dim, scores, static_cast<cudaStream_t>(stream)));
+  return SRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Host-side mirror of the reference's model-call surface over the C ABI.
+
+The reference's callable is a module-level Keras `model` and the call is
+`model.predict(feature_dict) -> float32[N,1]` (e.g.
+`TFRecModel/src/com/sparrowrecsys/offline/tensorflow/DIN.py:169,185`); at serve
+time the same graph answers TF-Serving's `:predict`
+(`online/recprocess/RecForYouProcess.java:113-138`).  `CTRModel` keeps that
+surface - same key names, same dtypes, unknown keys ignored, `KeyError` for a
+missing key, `ValueError` for an out-of-range id (TF's identity-column assert) -
+and forwards to `libsrs_ctr.so` through ctypes.  There is no fallback: without the
+CUDA library or a GPU, construction raises.
+
+PyTorch appears only in the `*_device` helpers, as the on-device container.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+
+from . import _lib
+from .features import EncodedBatch, encode_batch
+from .spec import ModelSpec, default_spec
+from .weights import check_weights, init_weights, weight_shapes
+
+
+def _spec_struct(spec: ModelSpec) -> _lib.SrsSpec:
+    s = _lib.SrsSpec()
+    s.kind = spec.kind
+    s.emb_dim = spec.emb_dim
+    s.n_movies = spec.n_movies
+    s.n_users = spec.n_users
+    s.n_genres = spec.n_genres
+    s.hist_len = spec.hist_len
+    s.n_hidden = len(spec.hidden)
+    for i, h in enumerate(spec.hidden):
+        s.hidden[i] = h
+    s.au_hidden = spec.au_hidden
+    s.cross_buckets = spec.cross_buckets
+    s.proj_dim = spec.proj_dim
+    s.final_dense = 1 if spec.final_dense else 0
+    return s
+
+
+class DeviceBatch:
+    """An encoded batch resident in HBM (torch tensors as containers)."""
+
+    def __init__(self, enc: EncodedBatch, device, hist_cols: int):
+        import torch
+        dev = torch.device(device)
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.B = enc.B
+        self.movie_id = t(enc.movie_id)
+        self.user_id = t(enc.user_id)
+        self.hist = t(enc.hist)
+        self.movie_genre = t(enc.movie_genre)
+        self.user_genre = t(enc.user_genre)
+        self.numerics = t(enc.numerics)
+        self.hist_stride = 0 if enc.hist is None else enc.hist.shape[1]
+
+    def struct(self) -> _lib.SrsBatch:
+        p = lambda x: None if x is None else x.data_ptr()
+        return _lib.SrsBatch(self.B, self.hist_stride, p(self.movie_id), p(self.user_id),
+                             p(self.hist), p(self.movie_genre), p(self.user_genre),
+                             p(self.numerics))
+
+
+def _host_struct(enc: EncodedBatch, keep: list) -> _lib.SrsBatch:
+    def p(a, dtype):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data
+    hs = 0 if enc.hist is None else enc.hist.shape[1]
+    return _lib.SrsBatch(enc.B, hs, p(enc.movie_id, np.int32), p(enc.user_id, np.int32),
+                         p(enc.hist, np.int32), p(enc.movie_genre, np.int32),
+                         p(enc.user_genre, np.int32), p(enc.numerics, np.float32))
+
+
+class CTRModel:
+    """One CTR ranking model resident on one GPU."""
+
+    def __init__(self, spec: ModelSpec, weights: Mapping[str, object], device: int = 0):
+        """`weights`: canonical name -> float32 numpy array (reference shapes), or a
+        torch CUDA tensor for an embedding table that is already in HBM (used in
+        place, see SRS_DEVICE_BORROWED in include/srs_ctr.h)."""
+        self.spec = spec
+        self.device = int(device)
+        self._h = None
+        lib = _lib.load()
+        self._lib = lib
+        borrowed = {k for k, v in weights.items() if not isinstance(v, np.ndarray)}
+        check_weights(spec, {k: v for k, v in weights.items() if k not in borrowed},
+                      skip=tuple(borrowed))
+        shapes = dict(weight_shapes(spec))
+        tensors = (_lib.SrsTensor * len(shapes))()
+        self._keep = []
+        for i, (name, shape) in enumerate(shapes.items()):
+            if name not in weights:
+                raise KeyError("missing weight tensor %r" % name)
+            w = weights[name]
+            rows = shape[0]
+            cols = shape[1] if len(shape) > 1 else 1
+            if name in borrowed:
+                if tuple(w.shape) != tuple(shape) or str(w.dtype) != "torch.float32" or not w.is_contiguous():
+                    raise ValueError("device tensor %r must be contiguous float32 %s" % (name, shape))
+                self._keep.append(w)
+                tensors[i] = _lib.SrsTensor(name.encode(), w.data_ptr(), rows, cols,
+                                            _lib.SRS_DEVICE_BORROWED)
+            else:
+                a = np.ascontiguousarray(w, dtype=np.float32)
+                self._keep.append(a)
+                tensors[i] = _lib.SrsTensor(name.encode(), a.ctypes.data, rows, cols, _lib.SRS_HOST)
+        handle = C.c_void_p()
+        sp = _spec_struct(spec)
+        _lib.check(lib.srs_model_create(C.byref(sp), tensors, len(shapes), self.device,
+                                        C.byref(handle)))
+        self._h = handle
+        self._keep = [w for w in self._keep if not isinstance(w, np.ndarray)]  # host copies done
+        self.hist_cols = spec.hist_len if spec.model == "din" else (1 if spec.model == "widendeep" else 0)
+
+    # ---- constructors ------------------------------------------------------------
+    @classmethod
+    def from_spec(cls, spec: ModelSpec, seed: int = 0, device: int = 0, for_test: bool = True):
+        return cls(spec, init_weights(spec, seed, for_test=for_test), device)
+
+    @classmethod
+    def from_savedmodel(cls, savedmodel_dir: str, model: str = "neuralcf", device: int = 0):
+        """Load one of the reference's shipped exports (`webroot/modeldata/neuralcf/<v>`,
+        `webroot/modeldata/MLPRec/005`) without TensorFlow."""
+        from . import bundle
+        if model == "neuralcf":
+            return cls(default_spec("neuralcf"), bundle.load_neuralcf(savedmodel_dir), device)
+        if model == "twotowers":
+            return cls(default_spec("twotowers", hidden=(10,), final_dense=False),
+                       bundle.load_twotowers(savedmodel_dir), device)
+        raise ValueError("no shipped SavedModel layout known for %r" % model)
+
+    # ---- lifetime ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.srs_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def kernel_name(self) -> str:
+        return self._lib.srs_model_kernel_name(self._h).decode()
+
+    @property
+    def bytes_per_inference(self) -> int:
+        return int(self._lib.srs_model_bytes_per_inference(self._h))
+
+    # ---- the reference's call surface -----------------------------------------------
+    def predict(self, features: Mapping[str, object], batch_size: Optional[int] = None) -> np.ndarray:
+        """`model.predict(x)`: feature dict of 1-D columns -> float32 [N,1]."""
+        return self._predict(features, batch_size, want_logits=False)[0]
+
+    def predict_with_logits(self, features, batch_size: Optional[int] = None):
+        return self._predict(features, batch_size, want_logits=True)
+
+    def _predict(self, features, batch_size, want_logits):
+        enc = encode_batch(self.spec, features)
+        n = enc.B
+        probs = np.empty(n, np.float32)
+        logits = np.empty(n, np.float32) if want_logits else None
+        step = n if not batch_size else int(batch_size)
+        for lo in range(0, n, max(step, 1)):
+            hi = min(n, lo + step)
+            self.predict_encoded(enc.slice(lo, hi), probs[lo:hi],
+                                 None if logits is None else logits[lo:hi])
+        return probs.reshape(n, 1), (None if logits is None else logits.reshape(n, 1))
+
+    def predict_encoded(self, enc: EncodedBatch, probs: np.ndarray,
+                        logits: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host arrays in, host scores out (`srs_predict_host`)."""
+        if enc.B == 0:
+            return probs
+        keep = []
+        b = _host_struct(enc, keep)
+        assert probs.dtype == np.float32 and probs.flags.c_contiguous and probs.shape[0] == enc.B
+        lp = None
+        if logits is not None:
+            assert logits.dtype == np.float32 and logits.flags.c_contiguous
+            lp = logits.ctypes.data
+        _lib.check(self._lib.srs_predict_host(self._h, C.byref(b), probs.ctypes.data, lp))
+        return probs
+
+    # ---- pipelined host path -----------------------------------------------------------
+    def num_slots(self) -> int:
+        return int(self._lib.srs_num_slots())
+
+    def submit_host(self, slot: int, batch_struct: _lib.SrsBatch, probs_ptr: int,
+                    logits_ptr: Optional[int] = None):
+        _lib.check(self._lib.srs_predict_host_async(self._h, slot, C.byref(batch_struct),
+                                                    probs_ptr, logits_ptr))
+
+    def wait(self, slot: int):
+        _lib.check(self._lib.srs_wait_slot(self._h, slot))
+
+    # ---- device-resident path -----------------------------------------------------------
+    def to_device(self, features_or_enc) -> DeviceBatch:
+        enc = features_or_enc if isinstance(features_or_enc, EncodedBatch) \
+            else encode_batch(self.spec, features_or_enc)
+        return DeviceBatch(enc, "cuda:%d" % self.device, self.hist_cols)
+
+    def predict_device(self, batch: DeviceBatch, probs, logits=None, stream=None):
+        """Everything in HBM: `probs` / `logits` are float32 CUDA tensors [B]; asynchronous
+        on `stream` (a torch stream; default: torch's current stream)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        b = batch.struct()
+        _lib.check(self._lib.srs_predict_device(
+            self._h, C.byref(b), probs.data_ptr(), None if logits is None else logits.data_ptr(),
+            stream.cuda_stream))
+        return probs
+
+    def status(self):
+        """Synchronise; raises ValueError if a device batch carried an out-of-range id."""
+        _lib.check(self._lib.srs_model_status(self._h))
+
+
+def launch_count() -> int:
+    return int(_lib.load().srs_launch_count())

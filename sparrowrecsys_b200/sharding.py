@@ -1,0 +1,63 @@
+"""Multi-GPU: shard ranking instances by row, replicate the model, gather scores.
+
+Rows of every reference graph are independent (no batch statistics, no cross-row
+op), so the path shards by user-batch with no data-path
+collective: rank r scores the contiguous slice [r*B/N, (r+1)*B/N).  The only
+exchange is an all-gather of float32 scores, and only when one ranking call needs
+the whole vector on every rank (`gather_scores`).  One process per GPU,
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Mapping, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous near-equal split; the first `n_rows % world_size` ranks get one
+    extra row."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank/world_size")
+    base, extra = divmod(n_rows, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_features(features: Mapping[str, object], world_size: int, rank: int) -> Dict[str, np.ndarray]:
+    n = len(np.asarray(features["movieId"]))
+    lo, hi = shard_bounds(n, world_size, rank)
+    return {k: np.asarray(v)[lo:hi] for k, v in features.items()}
+
+
+def gather_scores(local_scores, n_rows: int, group=None):
+    """All-gather per-rank score slices (torch tensor [n_local] on the rank's device)
+    into the full [n_rows] vector on every rank.  Slices may differ by one row, so each
+    rank pads to the largest slice; the kernel's output can be written straight into
+    the rank's slot of the gather buffer."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(n_rows, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros(world * width, dtype=local_scores.dtype, device=local_scores.device)
+    mine = buf[rank * width: rank * width + local_scores.numel()]
+    mine.copy_(local_scores.reshape(-1))
+    dist.all_gather_into_tensor(buf, buf[rank * width:(rank + 1) * width].clone(), group=group)
+    out = torch.cat([buf[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+    return out
+
+
+def predict_sharded(score_fn: Callable[[Dict[str, np.ndarray]], object], features, group=None,
+                    gather: bool = True):
+    """Score this rank's row shard with `score_fn(shard_features) -> torch tensor [n_local]`
+    and (optionally) all-gather the full score vector."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = len(np.asarray(features["movieId"]))
+    local = score_fn(shard_features(features, world, rank))
+    if not gather:
+        return local
+    return gather_scores(local, n, group)

@@ -1,0 +1,90 @@
+"""Pin the oracle: shipped trained weights of the reference on the bundled test rows
+must reproduce the known answers recorded in SURVEY.md section 8c (computed there by
+an independent numpy restatement of the graph; TensorFlow itself cannot run here)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REFERENCE_WEBROOT, load_golden_weights
+from oracle import ctr_oracle as O
+from sparrowrecsys_b200.spec import default_spec
+
+FIRST8 = [(1, 14887), (10, 11888), (10, 27990), (135, 27108), (15, 23843), (150, 21259),
+          (150, 26112), (162, 23843)]
+KNOWN = {
+    "neuralcf_002": [0.8525178, 0.51808727, 0.35965464, 0.02063905, 0.03719175, 0.80573314,
+                     0.5643234, 0.78833336],
+    "neuralcf_001": [0.6695241, 0.5660429, 0.08600407, 0.6025467, 0.1260225, 0.9618024,
+                     0.59564346, 0.8093899],
+    "mlprec_005": [0.5534312, 0.21570465, 0.09113927, 0.37527242, 0.22620608, 0.5138782,
+                   0.43187657, 0.9393208],
+}
+
+
+def test_head_rows_are_the_surveyed_rows(head_rows):
+    assert list(zip(head_rows["movieId"][:8].tolist(), head_rows["userId"][:8].tolist())) == FIRST8
+    assert len(head_rows["movieId"]) == 512
+
+
+@pytest.mark.parametrize("name", ["neuralcf_002", "neuralcf_001"])
+def test_neuralcf_known_answers(head_rows, name):
+    W = load_golden_weights(name)
+    sub = {k: v[:8] for k, v in head_rows.items()}
+    p, _ = O.neuralcf_forward(default_spec("neuralcf"), W, sub)
+    np.testing.assert_allclose(p[:, 0], KNOWN[name], rtol=0, atol=2e-7)
+    p64, _ = O.neuralcf_forward(default_spec("neuralcf"), W, sub, dtype=np.float64)
+    np.testing.assert_allclose(p64[:, 0], KNOWN[name], rtol=0, atol=2e-7)
+
+
+def test_twotowers_known_answers(head_rows):
+    W = load_golden_weights("mlprec_005")
+    sub = {k: v[:8] for k, v in head_rows.items()}
+    spec = default_spec("twotowers", hidden=(10,), final_dense=False)
+    p, z = O.twotowers_forward(spec, W, sub)
+    np.testing.assert_allclose(p[:, 0], KNOWN["mlprec_005"], rtol=0, atol=2e-7)
+    assert np.array_equal(p, z)          # raw dot, no sigmoid
+
+
+def test_httpclient_main_pair():
+    """online/util/HttpClient.java:110-147 posts (userId 10351; movieId 52, 53)."""
+    W = load_golden_weights("neuralcf_002")
+    f = {"movieId": np.array([52, 53], np.int32), "userId": np.array([10351, 10351], np.int32)}
+    p, _ = O.neuralcf_forward(default_spec("neuralcf"), W, f)
+    np.testing.assert_allclose(p[:, 0], [0.68536943, 0.17321654], rtol=0, atol=2e-7)
+
+
+def test_full_file_stats_recorded():
+    with open(os.path.join(GOLDEN, "full_file_stats.json")) as f:
+        s = json.load(f)
+    assert s["rows"] == 22440
+    assert abs(s["accuracy"] - 0.67879) < 1e-5
+    assert abs(s["roc_auc"] - 0.73208) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
+def test_bundle_reader_matches_fixture():
+    """The TF-free bundle reader on the real SavedModel dirs equals the committed fixture."""
+    from sparrowrecsys_b200 import bundle
+    W = bundle.load_neuralcf(REFERENCE_WEBROOT + "modeldata/neuralcf/002")
+    G = load_golden_weights("neuralcf_002")
+    for k in ("movieId_embedding", "dense_0/kernel", "dense_0/bias", "dense_1/kernel",
+              "dense_2/kernel", "dense_2/bias"):
+        assert np.array_equal(W[k], G[k]), k
+    nz = np.flatnonzero(np.abs(G["userId_embedding"]).sum(axis=1))
+    assert np.array_equal(W["userId_embedding"][nz], G["userId_embedding"][nz])
+    idx = bundle.read_index(REFERENCE_WEBROOT + "modeldata/neuralcf/002/variables/variables.index")
+    e = idx["layer_with_weights-2/kernel/.ATTRIBUTES/VARIABLE_VALUE"]
+    assert (e["shape"], e["offset"]) == ((20, 10), 1240080)       # SURVEY.md 8c offsets
+    W5 = bundle.load_twotowers(REFERENCE_WEBROOT + "modeldata/MLPRec/005")
+    assert W5["item_dense_0/kernel"].shape == (10, 10)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
+def test_head_fixture_is_prefix_of_reference_file():
+    with open(REFERENCE_WEBROOT + "sampledata/testSamples.csv", "rb") as f:
+        ref = f.read(200000)
+    with open(os.path.join(GOLDEN, "samples_head.csv"), "rb") as f:
+        head = f.read()
+    assert ref.startswith(head)
