@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py - CTR inferences/s of the DIN forward path (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch: one fused-kernel launch scoring
+`--batch` (4096) DIN ranking instances (T=50, E=32, MovieLens-20M-shaped vocabularies,
+synthetic Zipf inputs, seeded random-init weights of the reference architecture).
+
+* `value`  : rows scored per second with the batch already resident in HBM, device-timed
+             with CUDA events around exactly K launches, max over ranks.  Inputs cycle
+             through a ring of distinct batches whose footprint exceeds the 126 MB L2, so
+             every step's ids/numerics come from HBM; the 21 MB of embedding tables stay
+             L2 resident by size (that is the workload's nature, see `config.l2`).
+* `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
+             (`srs_predict_host_async`: H2D of the batch from pinned memory, kernel, D2H of
+             the scores, pipelined over the library's slots), wall-clock, max over ranks.
+* `roofline`: algorithmic bytes per launch (7160 B/row) / average launch
+             duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* `cpu_baseline`: the oracle (numpy restatement of the Keras graph; TensorFlow is not
+             installable here) timed on this box's host cores on a bounded sample.
+
+`--impl reference` times that CPU restatement as the reference arm (rank 0 only).
+Multi-GPU (`torchrun`, one rank per GPU): rows shard by rank, weights replicate, no
+data-path collective (weak scaling: 4096 rows per GPU per step); `--gather` adds the
+all-gather of scores that a ranking call spanning GPUs would need.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CTR inferences/sec (DIN, batch=4096, hist_len=50)"
+WORKLOAD = "cfg3_din"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="rows per GPU per step")
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--gather", action="store_true", help="all-gather scores every step (N>1)")
+    ap.add_argument("--no-graph", action="store_true", help="launch directly instead of CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def workload_desc(spec, batch):
+    return ("%s: DIN forward, hist_len=%d, emb_dim=%d, batch=%d per GPU, V_movie=%d, V_user=%d, "
+            "activation unit 4E->32->1 sigmoid-gated sum pooling, top MLP %d->128->64->1"
+            % (WORKLOAD, spec.hist_len, spec.emb_dim, batch, spec.n_movies, spec.n_users,
+               5 * spec.emb_dim + 7))
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed
+    region runs (nvidia-smi reads the same counters)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.ok = False
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                index = int(visible.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                                   # pragma: no cover
+            self.err = repr(e)
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            nv = self.nv
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def start(self, period=0.05):
+        def run():
+            while not self._stop.is_set():
+                self.sample()
+                self._stop.wait(period)
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu
+    summary (profiles/ncu_din_summary.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_din_summary.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_oracle_throughput(spec, W, feats, seconds, max_reps=50):
+    """Rows/s of the numpy oracle on `feats` (one bounded sample), all BLAS threads."""
+    from oracle import ctr_oracle as O
+    O.forward(spec, W, feats)                                     # warm-up
+    n = len(feats["movieId"])
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        O.forward(spec, W, feats)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or reps >= max_reps:
+            break
+    return n * reps / dt, reps, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  TensorFlow is
+    not installed / installable on this image, so this is the oracle port (numpy + OpenBLAS
+    threads) of the Keras graph, same workload, each step a bounded sample of the batch."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import ctr_oracle as O
+    from sparrowrecsys_b200.features import synthetic_features
+    from sparrowrecsys_b200.spec import baseline_spec
+    from sparrowrecsys_b200.weights import init_weights
+    spec = baseline_spec(args.workload)
+    W = init_weights(spec, 2)
+    feats = synthetic_features(spec, args.batch, seed=2)
+    cores = os.cpu_count() or 1
+    # size the per-step sample so that steps+warmup stay within ~2 minutes
+    t0 = time.perf_counter()
+    O.forward(spec, W, feats)
+    O.forward(spec, W, feats)
+    t_batch = (time.perf_counter() - t0) / 2
+    budget = 120.0
+    rows = args.batch
+    total = args.steps + args.warmup
+    if t_batch * total > budget:
+        rows = int(max(16, min(args.batch, args.batch * budget / (t_batch * total))))
+    sample = {k: np.asarray(v)[:rows] for k, v in feats.items()}
+    for _ in range(args.warmup):
+        O.forward(spec, W, sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.forward(spec, W, sample)
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "inferences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_desc(spec, args.batch), "rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": "inferences/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d rows per step, numpy float32 oracle (OpenBLAS, %d threads); "
+                                   "TF2 itself is not installable here" % (rows, args.batch, cores)},
+        "e2e": {"value": value, "unit": "inferences/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sparrowrecsys_b200 import _lib
+    from sparrowrecsys_b200.features import encode_batch, synthetic_features
+    from sparrowrecsys_b200.model import CTRModel
+    from sparrowrecsys_b200.spec import baseline_spec
+    from sparrowrecsys_b200.weights import init_weights
+
+    lib = _lib.load()
+    spec = baseline_spec(args.workload)
+    B = args.batch
+    W = init_weights(spec, 2)                       # same weights on every rank (replicated)
+    model = CTRModel(spec, W, device=local_rank)
+    T = spec.hist_len
+
+    # ---- input ring: distinct batches, footprint > L2 ------------------------------
+    bytes_per_batch = B * (4 * (T + 2) + 4 * 8 + 4 * 7 + 4)
+    ring = int(np.ceil(1.25 * L2_BYTES / bytes_per_batch))
+    feats = synthetic_features(spec, ring * B, seed=1000 + rank)   # each rank its own user-batches
+    enc = encode_batch(spec, feats)
+    d = model.to_device(enc)                          # one big device allocation per column
+    out = torch.empty(ring, B, dtype=torch.float32, device=dev)
+    structs = []
+    for i in range(ring):
+        lo = i * B
+        structs.append(_lib.SrsBatch(
+            B, T, d.movie_id.data_ptr() + 4 * lo, d.user_id.data_ptr() + 4 * lo,
+            d.hist.data_ptr() + 4 * lo * T, d.movie_genre.data_ptr() + 4 * lo * 3,
+            d.user_genre.data_ptr() + 4 * lo * 5, d.numerics.data_ptr() + 4 * lo * 7))
+    out_ptrs = [out[i].data_ptr() for i in range(ring)]
+    handle = model._h
+
+    def launch(i, stream_ptr):
+        rc = lib.srs_predict_device(handle, C.byref(structs[i % ring]), out_ptrs[i % ring], None,
+                                    stream_ptr)
+        if rc != 0:
+            _lib.check(rc)
+
+    gather_buf = None
+    if distributed and args.gather:
+        gather_buf = torch.empty(world * B, dtype=torch.float32, device=dev)
+
+    stream = torch.cuda.Stream(device=dev)
+    graph = None
+    launch_mode = "direct"
+    with torch.cuda.stream(stream):
+        for i in range(min(args.warmup, ring)):       # first touches / module load
+            launch(i, stream.cuda_stream)
+        stream.synchronize()
+        if not args.no_graph and not (distributed and args.gather):
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for i in range(ring):
+                        launch(i, torch.cuda.current_stream().cuda_stream)
+                graph = g
+                launch_mode = "cuda-graph of %d launches (one pass over the ring)" % ring
+            except Exception as e:                    # pragma: no cover
+                sys.stderr.write("graph capture failed (%r); launching directly\n" % (e,))
+                torch.cuda.synchronize()
+
+        def run_steps(n):
+            i = 0
+            if graph is not None:
+                while n - i >= ring:
+                    graph.replay()
+                    i += ring
+            while i < n:
+                launch(i, stream.cuda_stream)
+                if gather_buf is not None:
+                    dist.all_gather_into_tensor(gather_buf, out[i % ring])
+                i += 1
+
+        run_steps(args.warmup)
+        stream.synchronize()
+
+        sampler = ClockSampler(local_rank)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        ev0.record(stream)
+        run_steps(args.steps)
+        ev1.record(stream)
+        sampler.sample()                               # GPU still draining the queue
+        stream.synchronize()
+        sampler.sample()
+        sampler.stop()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+    model.status()                                     # no id was out of range
+
+    # ---- e2e through the C ABI with host buffers ----------------------------------
+    n_slots = model.num_slots()
+    host_ring = 8
+    hfe = encode_batch(spec, {k: np.asarray(v)[:host_ring * B] for k, v in feats.items()})
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hp = dict(movie=pin(hfe.movie_id), user=pin(hfe.user_id), hist=pin(hfe.hist),
+              mg=pin(hfe.movie_genre), ug=pin(hfe.user_genre), num=pin(hfe.numerics))
+    hout = torch.empty(host_ring, B, dtype=torch.float32).pin_memory()
+    hstructs = []
+    for i in range(host_ring):
+        lo = i * B
+        hstructs.append(_lib.SrsBatch(
+            B, T, hp["movie"].data_ptr() + 4 * lo, hp["user"].data_ptr() + 4 * lo,
+            hp["hist"].data_ptr() + 4 * lo * T, hp["mg"].data_ptr() + 4 * lo * 3,
+            hp["ug"].data_ptr() + 4 * lo * 5, hp["num"].data_ptr() + 4 * lo * 7))
+    h2d = B * (4 * (T + 2) + 4 * 3 + 4 * 5 + 4 * 7)
+    d2h = B * 4 + 4
+
+    def e2e_steps(n):
+        for i in range(n):
+            slot = i % n_slots
+            if i >= n_slots:
+                model.wait(slot)
+            model.submit_host(slot, hstructs[i % host_ring], hout[i % host_ring].data_ptr())
+        for s in range(n_slots):
+            model.wait(s)
+
+    e2e_n = args.steps
+    e2e_steps(min(args.warmup, 64))
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps(e2e_n)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # scores that came back over PCIe equal the device-path scores of the same rows
+    chk = torch.empty(B, dtype=torch.float32, device=dev)
+    lib.srs_predict_device(handle, C.byref(structs[0]), chk.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    if e2e_n >= 1 and not np.array_equal(chk.cpu().numpy(), hout[0].numpy()):
+        raise SystemExit("e2e scores differ from device-path scores")
+
+    # ---- reduce over ranks ------------------------------------------------------------
+    if distributed:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    total_rows = world * B * args.steps
+    value = total_rows / (ms * 1e-3)
+    e2e_value = world * B * e2e_n / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bpi = model.bytes_per_inference
+        launch_us = 1e3 * ms / max(args.steps, 1)
+        achieved = bpi * B / (launch_us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "inferences/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": workload_desc(spec, B), "batch_per_gpu": B, "global_batch": world * B,
+                "parallelism": "dp%d: rows sharded by user-batch, weights replicated, no data-path "
+                               "collective%s" % (world, " + all-gather of scores" if gather_buf is not None else ""),
+                "kernel": model.kernel_name, "launch": launch_mode,
+                "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB > 126 MB L2): ids/"
+                      "numerics are read from HBM every step; embedding tables (%.1f MB) are L2-resident "
+                      "by size" % (ring, ring * bytes_per_batch / 1e6,
+                                   4 * spec.emb_dim * (spec.n_movies + spec.n_users) / 1e6),
+                "weights": "random init of the reference architecture (seed 2), Zipf(1.05) movie ids, "
+                           "history length U[1,50] zero-padded (padding included, as in the reference)",
+            },
+            "e2e": {"value": e2e_value, "unit": "inferences/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_n,
+                    "how": "srs_predict_host_async over %d slots, pinned host buffers, wall clock" % n_slots},
+            "gpu_launches": args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "algorithmic_bytes_per_launch": bpi * B, "launch_us": launch_us,
+                         "peak_source": peak_src},
+        }
+        if not args.no_cpu_baseline:
+            n_cpu = min(B, 4096)
+            cpu_feats = {k: np.asarray(v)[:n_cpu] for k, v in feats.items()}
+            v, reps, dt = cpu_oracle_throughput(spec, W, cpu_feats, args.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "inferences/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": "%d x %d-row batch of the same workload in %.1f s, numpy float32 oracle "
+                          "(OpenBLAS threads = cores); TF2 is not installable here" % (reps, n_cpu, dt)}
+        print(json.dumps(line))
+    model.close()
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
