@@ -169,6 +169,13 @@ int srs_fill_uniform(float* device_ptr, int64_t n, uint64_t seed, float lo, floa
 int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, int32_t dim,
                              float* scores, int32_t device, void* stream);
 
+/* Known-answer self test of the tcgen05 / TMEM plumbing the DIN kernel is built on:
+ * D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T (inputs truncated to bf16, fp32 accumulate),
+ * K = 64 * k_blocks (1..3), N = 16 or 32, A staged through shared memory (a_in_tmem = 0)
+ * or written to tensor memory (a_in_tmem = 1).  Device pointers; synchronous. */
+int srs_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t k_blocks,
+                      int32_t a_in_tmem, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif

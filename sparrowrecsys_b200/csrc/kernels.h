@@ -127,6 +127,8 @@ cudaError_t launch_deepfm2(const DeepFm2Params& p, const BatchView& b, cudaStrea
 cudaError_t launch_din(const DinParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, float hi,
                                 cudaStream_t s);
+cudaError_t launch_umma_selftest(const float* A, const float* B, float* D, int N, int KB,
+                                 int a_in_tmem, cudaStream_t s);
 cudaError_t launch_cosine(const float* q, const float* c, int n, int dim, float* out,
                           cudaStream_t s);
 

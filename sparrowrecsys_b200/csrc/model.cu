@@ -786,4 +786,13 @@ int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, 
   return SRS_OK;
 }
 
+int srs_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t k_blocks,
+                      int32_t a_in_tmem, int32_t device) {
+  if (!A || !B || !D) return fail(SRS_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_umma_selftest(A, B, D, N, k_blocks, a_in_tmem, nullptr));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return SRS_OK;
+}
+
 }  // extern "C"
