@@ -119,7 +119,32 @@ struct DinParams {
   int EP;
 };
 
+// ---- DIN on tensor cores (din_tc.cu): E padded to 32, T <= 128 -----------------------------
+struct DinTcParams {
+  const float* movie;      // [n_movies][32]
+  const float* user;       // [n_users][32]
+  const float* ugenre;     // [19][32]
+  const float* mgenre;     // [19][32]
+  const uint8_t* image;    // shared-memory image: bf16 hi/lo SW128 operand tiles + alpha*wout table
+  const float* au_wc;      // [32][32]  W_c - W_sub
+  const float* au_b;       // [32]
+  const float* b1;         // [128]
+  const float* a1;         // [128]
+  const float* w1num;      // [8][128] rows of dense/kernel that multiply the 7 numerics
+  const float* b2;         // [64]
+  const float* a2;         // [64]
+  const float* w3;         // [64]
+  float au_wout[32];
+  float au_bout;
+  float b3;
+  int n_movies, n_users, n_genres;
+  int T;
+  int CPR;                 // 32-position chunks per row = ceil(T / 32)
+  int num_sms;
+};
+
 // launchers (defined next to their kernels); return cudaGetLastError()
+cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_embmlp(const EmbMlpParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_t s);

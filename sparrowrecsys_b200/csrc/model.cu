@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -17,6 +18,7 @@ namespace srs {
 cudaError_t setup_embmlp_attributes();
 cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
+cudaError_t setup_din_tc_attributes();
 }  // namespace srs
 
 using namespace srs;
@@ -74,6 +76,8 @@ struct srs_model {
   DeepFmParams fm{};
   DeepFm2Params fm2{};
   DinParams din{};
+  DinTcParams din_tc{};
+  bool use_din_tc = false;
   const char* kernel_name = "";
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
@@ -507,6 +511,116 @@ int build_din(Builder& B) {
   return B.status;
 }
 
+// ---- tensor-core DIN: shared-memory image ------------------------------------------------
+inline uint32_t f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+inline float u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
+inline uint16_t bf16_trunc_bits(float x) { return (uint16_t)(f2u(x) >> 16); }
+inline float bf16_trunc_val(float x) { return u2f(f2u(x) & 0xFFFF0000u); }
+inline uint16_t bf16_rn_bits(float x) {
+  const uint32_t u = f2u(x);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+inline uint32_t sw128_off(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
+
+// Write logical matrix M[rows][64*kblocks] (via getter) as K-major SW128 bf16 tiles; `part`
+// selects the hi half (x rounded to bf16) or the lo half (x - hi rounded to bf16).
+template <class F>
+void write_sw128(uint8_t* dst, int rows, int kblocks, bool lo_part, F get) {
+  for (int kb = 0; kb < kblocks; ++kb)
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < 8; ++c)
+        for (int i = 0; i < 8; ++i) {
+          const float x = get(r, kb * 64 + c * 8 + i);
+          const uint16_t hb = bf16_rn_bits(x);
+          const uint16_t v = lo_part ? bf16_rn_bits(x - u2f((uint32_t)hb << 16)) : hb;
+          memcpy(dst + (size_t)kb * rows * 128 + sw128_off(r, c) + i * 2, &v, 2);
+        }
+}
+
+// Fills m->din_tc from the same reference tensors build_din validated.
+int build_din_tc(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, T = s.hist_len, A = 32;
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  const int CPR = (T + 31) / 32, TP = CPR * 32;
+  const float* au = B.host("au_dense/kernel", 4 * E, A);
+  const float* alpha = B.host("au_prelu/alpha", T, A);
+  const float* auo = B.host("au_out/kernel", A, 1);
+  const float* k1 = B.host("dense/kernel", 5 * E + 7, h0);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  if (B.status != SRS_OK) return B.status;
+  // image offsets mirror the constants in din_tc.cu
+  const uint32_t IMG_AUB_HI = 0, IMG_AUB_LO = 4096, IMG_W1_HI = 8192, IMG_W1_LO = IMG_W1_HI + 3 * 16384,
+                 IMG_W2 = IMG_W1_LO + 3 * 16384, IMG_ALPHAW = IMG_W2 + 2 * 16384;
+  const uint32_t bytes = IMG_ALPHAW + 32u * TP * 4u;
+  std::vector<uint8_t> img(bytes, 0);
+  // activation unit B operand: row j = [ (Wsub+Wh)[e][j], e<32 | Wp[e][j], e<32 ]
+  auto au_get = [&](int j, int k) -> float {
+    const int e = k & 31;
+    if (e >= E) return 0.f;
+    if (k < 32) return au[(size_t)e * A + j] + au[(size_t)(E + e) * A + j];
+    return au[(size_t)(3 * E + e) * A + j];
+  };
+  write_sw128(img.data() + IMG_AUB_HI, 32, 1, false, au_get);
+  write_sw128(img.data() + IMG_AUB_LO, 32, 1, true, au_get);
+  // layer 1 A operand: row = unit j, K = [userGenre1 | userId | pooled | candidate | movieGenre1 | 0] x 32
+  const int base = 3 + 4 * E;
+  const int slot_start[6] = {1, 1 + E, 3 + 2 * E, 3 + 3 * E, base + 1, -1};
+  auto w1_get = [&](int j, int k) -> float {
+    const int slot = k >> 5, e = k & 31;
+    if (j >= h0 || slot >= 5 || e >= E) return 0.f;
+    return k1[(size_t)(slot_start[slot] + e) * h0 + j];
+  };
+  write_sw128(img.data() + IMG_W1_HI, 128, 3, false, w1_get);
+  write_sw128(img.data() + IMG_W1_LO, 128, 3, true, w1_get);
+  // layer 2 A operand: rows 0..63 = hi halves of W2^T, rows 64..127 = lo halves
+  auto w2_raw = [&](int i, int k) -> float { return (i < h1 && k < h0) ? k2[(size_t)k * h1 + i] : 0.f; };
+  {
+    std::vector<uint8_t> hi(2 * 64 * 128), lo(2 * 64 * 128);
+    // build as two 64-row matrices, then interleave into 128-row tiles
+    for (int kb = 0; kb < 2; ++kb)
+      for (int r = 0; r < 128; ++r)
+        for (int c = 0; c < 8; ++c)
+          for (int i = 0; i < 8; ++i) {
+            const float x = w2_raw(r & 63, kb * 64 + c * 8 + i);
+            const uint16_t hb = bf16_rn_bits(x);
+            const uint16_t v = (r < 64) ? hb : bf16_rn_bits(x - u2f((uint32_t)hb << 16));
+            memcpy(img.data() + IMG_W2 + (size_t)kb * 16384 + sw128_off(r, c) + i * 2, &v, 2);
+          }
+  }
+  // alpha * wout, transposed [unit j][position t], zero beyond T
+  float* aw = reinterpret_cast<float*>(img.data() + IMG_ALPHAW);
+  for (int j = 0; j < A; ++j)
+    for (int t = 0; t < T; ++t) aw[(size_t)j * TP + t] = alpha[(size_t)t * A + j] * auo[j];
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, bytes);
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc(%u) failed: %s", bytes, cudaGetErrorString(e));
+  m->owned.push_back(d_img);
+  e = cudaMemcpy(d_img, img.data(), bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+  // numerics rows of dense/kernel in NUMERIC_KEYS order
+  const int nrows[7] = {base, base + 1 + E, base + 2 + E, base + 3 + E, 0, 1 + 2 * E, 2 + 2 * E};
+  std::vector<float> w1num(8 * 128, 0.f);
+  for (int n = 0; n < 7; ++n)
+    for (int j = 0; j < h0; ++j) w1num[(size_t)n * 128 + j] = k1[(size_t)nrows[n] * h0 + j];
+  DinTcParams& p = m->din_tc;
+  const DinParams& v1 = m->din;                 // reuse tables / vectors uploaded by build_din
+  p.movie = v1.movie; p.user = v1.user; p.ugenre = v1.ugenre; p.mgenre = v1.mgenre;
+  p.image = d_img;
+  p.au_wc = v1.au_wc; p.au_b = v1.au_b;
+  p.b1 = v1.b1; p.a1 = v1.a1; p.w1num = B.upload(w1num);
+  p.b2 = v1.b2; p.a2 = v1.a2; p.w3 = v1.w3;
+  for (int j = 0; j < A; ++j) p.au_wout[j] = auo[j];
+  p.au_bout = v1.au_bout; p.b3 = v1.b3;
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.T = T; p.CPR = CPR;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  p.num_sms = sms > 0 ? sms : 148;
+  return B.status;
+}
+
 int64_t bytes_per_inference(const srs_spec& s) {
   const int64_t E = s.emb_dim, T = s.hist_len;
   switch (s.kind) {
@@ -547,7 +661,9 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_WIDENDEEP: e = launch_embmlp(m->emb, v, stream); break;
     case SRS_DEEPFM: e = launch_deepfm(m->fm, v, stream); break;
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
-    case SRS_DIN: e = launch_din(m->din, v, stream); break;
+    case SRS_DIN:
+      e = m->use_din_tc ? launch_din_tc(m->din_tc, v, stream) : launch_din(m->din, v, stream);
+      break;
     default: return fail(SRS_ERR_INVALID, "unknown model kind");
   }
   if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -659,6 +775,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_embmlp_attributes());
   CUDA_TRY(setup_deepfm_attributes());
   CUDA_TRY(setup_din_attributes());
+  CUDA_TRY(setup_din_tc_attributes());
 
   srs_model* m = new srs_model();
   m->spec = *spec;
@@ -677,7 +794,24 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     case SRS_WIDENDEEP: rc = build_embmlp(B); break;
     case SRS_DEEPFM: rc = build_deepfm(B); break;
     case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
-    default: rc = build_din(B); break;
+    default: {
+      rc = build_din(B);
+      // kernel selection: tensor-core path when the shape fits it (E padded to 32, T in 9..128);
+      // SRS_DIN_IMPL=cudacore|tc overrides (tc fails loudly if the shape is unsupported)
+      const char* impl = getenv("SRS_DIN_IMPL");
+      const bool fits = m->EP == 32 && spec->hist_len <= 128;
+      bool want = fits && spec->hist_len > 8;
+      if (impl && !strcmp(impl, "cudacore")) want = false;
+      if (impl && !strcmp(impl, "tc")) {
+        if (!fits && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=tc needs 16 < emb_dim <= 32 and hist_len <= 128");
+        want = true;
+      }
+      if (rc == SRS_OK && want) {
+        rc = build_din_tc(B);
+        if (rc == SRS_OK) { m->use_din_tc = true; m->kernel_name = "din_tc_kernel"; }
+      }
+      break;
+    }
   }
   if (rc == SRS_OK) {
     e = cudaMalloc(&m->err_flag, sizeof(int));

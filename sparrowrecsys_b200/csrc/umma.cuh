@@ -183,18 +183,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-// ---- bf16 hi/lo split ("bf16x3": x = hi + lo + O(2^-17 x); x*w ~ hi*whi + lo*whi + hi*wlo) ------
-// hi is x truncated to bf16 (so x - hi is exact in fp32), lo is x - hi rounded to bf16.
+// ---- bf16 hi/lo split ("bf16x3": x*w ~ hi*whi + lo*whi + hi*wlo) ------------------------------
+// hi = x rounded to bf16 (round-to-nearest-even), lo = (x - hi) rounded to bf16; x - hi is
+// exact in fp32 and |x - hi - lo| <= 2^-17 |x|.
+struct Split2 {
+  uint32_t hi, lo;      // packed pairs: first value in the low half
+};
+__device__ __forceinline__ Split2 split_pack(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+  const float ha = __uint_as_float(hb << 16), hbv = __uint_as_float(hb & 0xFFFF0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hbv);
+  Split2 r;
+  r.hi = hb;
+  r.lo = *reinterpret_cast<uint32_t*>(&l);
+  return r;
+}
+// truncating variant used by the self test (exactly representable operands)
 __device__ __forceinline__ uint32_t pack_hi(float a, float b) {   // (a -> low half, b -> high half)
   return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
-}
-__device__ __forceinline__ float trunc_bf16(float a) {
-  return __uint_as_float(__float_as_uint(a) & 0xFFFF0000u);
-}
-__device__ __forceinline__ uint32_t pack_lo(float a, float b) {
-  const float la = a - trunc_bf16(a), lb = b - trunc_bf16(b);
-  __nv_bfloat162 v = __floats2bfloat162_rn(la, lb);   // .x = la (low half), .y = lb
-  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 }  // namespace umma

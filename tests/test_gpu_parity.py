@@ -326,3 +326,68 @@ def test_launch_counter_counts_kernels():
         before = launch_count()
         m.predict({"movieId": np.array([1, 2, 3]), "userId": np.array([1, 2, 3])})
         assert launch_count() == before + 1
+
+
+# ---- DIN tensor-core kernel (csrc/din_tc.cu) vs CUDA-core kernel vs oracle ----------------
+@pytest.fixture
+def din_impl(monkeypatch):
+    def set_impl(name):
+        monkeypatch.setenv("SRS_DIN_IMPL", name)
+    return set_impl
+
+
+@pytest.mark.parametrize("E,T,B", [(32, 50, 4096), (32, 9, 100), (32, 31, 17), (32, 32, 16),
+                                   (32, 33, 15), (20, 64, 333), (32, 65, 129), (32, 128, 257),
+                                   (24, 100, 1), (32, 50, 4097)])
+def test_din_tensor_core_kernel(E, T, B, din_impl):
+    spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=27279, n_users=5000)
+    W = init_weights(spec, E * 1000 + T)
+    feats = synthetic_features(spec, B, seed=T)
+    din_impl("tc")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_tc_kernel"
+        p_tc, z_tc = m.predict_with_logits(feats)
+        p_tc2 = m.predict(feats)
+    assert np.array_equal(p_tc, p_tc2)                       # deterministic
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(z_tc - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z_tc - zo).max()
+    assert np.abs(p_tc - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p_tc - po).max()
+    din_impl("cudacore")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_kernel"
+        p_cc = m.predict(feats)
+    assert np.abs(p_cc - po).max() <= PROB_ATOL
+    assert np.abs(p_cc - p_tc).max() <= 2 * PROB_ATOL
+
+
+def test_din_tensor_core_row_independence(din_impl):
+    din_impl("tc")
+    spec = baseline_spec("cfg3_din")
+    W = init_weights(spec, 3)
+    B = 8192 + 5
+    feats = synthetic_features(spec, B, seed=3)
+    perm = np.random.default_rng(1).permutation(B)
+    with _model(spec, W) as m:
+        p = m.predict(feats)[:, 0]
+        pp = m.predict({k: v[perm] for k, v in feats.items()})[:, 0]
+        assert np.array_equal(pp, p[perm])                   # bit-exact under row permutation
+        lo = m.predict({k: v[:4099] for k, v in feats.items()})[:, 0]
+        hi = m.predict({k: v[4099:] for k, v in feats.items()})[:, 0]
+        assert np.array_equal(np.concatenate([lo, hi]), p)   # sharding invariant
+
+
+def test_din_tensor_core_large_magnitudes(din_impl):
+    """Trained-scale weights: embeddings O(0.5), logits up to ~10 - the bf16x3 split must hold
+    the 1e-4 target with margin where plain TF32/bf16 would not."""
+    din_impl("tc")
+    spec = baseline_spec("cfg3_din")
+    W = init_weights(spec, 5)
+    W["embedding"] = (W["embedding"] * 10).astype(np.float32)
+    W["dense_2/kernel"] = (W["dense_2/kernel"] * 4).astype(np.float32)
+    feats = synthetic_features(spec, 2048, seed=5)
+    with _model(spec, W) as m:
+        p, z = m.predict_with_logits(feats)
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(zo).max() > 2.0
+    assert np.abs(p - po).max() <= 1e-4, np.abs(p - po).max()     # the north_star target
+    assert np.abs(z - zo).max() <= 1e-3 * max(1.0, np.abs(zo).max())
