@@ -26,6 +26,8 @@
 //            MMA (12 instr), read back 32 accumulators, PReLU / gate, butterfly-pool
 //   phase 2  pooled -> X tile, layer-1 MMA (36), epilogue (bias, numerics, PReLU) -> H1
 //            operand tile, layer-2 MMA (16), epilogue, sigmoid, store 16 scores.
+#include <climits>
+
 #include "kernels.h"
 #include "umma.cuh"
 
@@ -35,6 +37,13 @@ using namespace umma;
 constexpr int kTcRows = 16;              // rows per group (N of the top-MLP MMAs)
 constexpr int kTcWG = 2;                 // warpgroups (workers) per CTA
 constexpr int kTcMaxCPR = 4;             // chunks (of 32 positions) per row: T <= 128
+constexpr int kNoPair = INT_MIN;         // sentinel: this thread has no (row, position) pair
+
+// tensor-memory map of one worker: 2 buffers x 128 columns
+constexpr uint32_t TM_A_HI = 0;          // 32 cols: bf16 pairs of [h | h*c], hi halves
+constexpr uint32_t TM_A_LO = 32;         // 32 cols: lo halves
+constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators (fp32)
+constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling
 
 // shared-memory image (bulk-copied from global; built by build_din_tc_image in model.cu)
 constexpr uint32_t IMG_AUB_HI = 0;                       // [32 units][64 k] bf16, SW128
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
                                                                  BatchView b) {
   extern __shared__ uint8_t raw[];
   __shared__ uint64_t wbar;                 // weight image landed
-  __shared__ uint64_t mbar[kTcWG];          // per-worker "MMAs complete"
+  __shared__ uint64_t mbar[kTcWG][2];       // per-worker "MMAs complete", one per TMEM buffer
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
@@ -94,10 +103,10 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   float* nums = reinterpret_cast<float*>(ws + WS_NUMS);
 
   // ---- prologue ---------------------------------------------------------------------
-  if (tid < 32) tmem_alloc(&tmem_slot, 256);
+  if (tid < 32) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&wbar, 1);
-    for (int i = 0; i < kTcWG; ++i) mbar_init(&mbar[i], 1);
+    for (int i = 0; i < kTcWG; ++i) { mbar_init(&mbar[i][0], 1); mbar_init(&mbar[i][1], 1); }
     fence_mbar_init();
     mbar_arrive_expect_tx(&wbar, img_bytes);
     for (uint32_t off = 0; off < img_bytes; off += 32768u) {
@@ -121,12 +130,11 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = tmem_slot + wg * 128;          // this worker's 128 TMEM columns
+  const uint32_t tbase = tmem_slot + wg * 256;          // this worker's 256 TMEM columns
   const uint32_t lane_base = (uint32_t)(warp_w * 32) << 16;
-  const uint32_t tA_hi = tbase + 0, tA_lo = tbase + 32, tD = tbase + 64, tD1 = tbase + 96,
-                 tD2 = tbase + 112;
-  uint64_t* my_bar = &mbar[wg];
-  uint32_t phase = 0;
+  const uint32_t tD1 = tbase + TM_D, tD2 = tbase + 128 + TM_D;   // top MLP reuses the AU accumulators
+  uint64_t* my_bar = mbar[wg];
+  uint32_t phase = 0;                                   // bit i = parity to wait for on my_bar[i]
   bool weights_ready = false;
 
   const uint32_t idesc_au = idesc_bf16(128, 32), idesc_top = idesc_bf16(128, 16);
@@ -139,21 +147,56 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
 
   for (int g = blockIdx.x * kTcWG + wg; g < n_groups; g += n_workers) {
     const int row0 = g * kTcRows;
+    // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
+    auto pair_of = [&](int tile, int& rs, int& cq, int& t) {
+      const int ch = 4 * tile + warp_w;
+      rs = ch / CPR;
+      cq = ch - rs * CPR;
+      t = cq * 32 + lane;
+    };
+    // raw history id of this thread's pair in `tile` (kNoPair if none); the value is not
+    // touched here so the load stays in flight until fix_id() one or two tiles later
+    auto raw_id = [&](int tile) -> int {
+      if (tile >= n_tiles) return kNoPair;
+      int rs, cq, t;
+      pair_of(tile, rs, cq, t);
+      const int row = row0 + rs;
+      if (row >= b.B || t >= T) return kNoPair;
+      return __ldg(b.hist + (size_t)row * b.hist_stride + t);
+    };
+    auto fix_id = [&](int raw) -> int {
+      if (raw == kNoPair) return -1;
+      return checked_id(f32_roundtrip_id(raw), p.n_movies, b.err_flag);
+    };
+    auto load_row = [&](int id, float4 (&h)[8]) {
+      if (id >= 0) {
+        const float* src = p.movie + (size_t)id * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = ldg4(src + 4 * q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int raw0 = raw_id(0), raw1 = raw_id(1), raw2 = raw_id(2);   // ids come from HBM: start now
+
     // ================= phase 0: side gathers -> X operand, candidate rows, cst ==========
     {
       const int rs = tw >> 3, q = tw & 7;
       const int row = row0 + rs;
       const bool vr = row < b.B;
       float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = c4, ug4 = c4, mg4 = c4;
+      float nv = 0.f;
       if (vr) {
-        const int cid = checked_id(f32_roundtrip_id(__ldg(b.movie_id + row)), p.n_movies, b.err_flag);
+        const int cid_raw = __ldg(b.movie_id + row), uid_raw = __ldg(b.user_id + row);
+        int ug = __ldg(b.user_genre + row * 5), mg = __ldg(b.movie_genre + row * 3);
+        if (q < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + q);
+        const int cid = checked_id(f32_roundtrip_id(cid_raw), p.n_movies, b.err_flag);
+        const int uid = checked_id(uid_raw, p.n_users, b.err_flag);
         c4 = ldg4(p.movie + (size_t)cid * 32 + 4 * q);
-        const int uid = checked_id(__ldg(b.user_id + row), p.n_users, b.err_flag);
         u4 = ldg4(p.user + (size_t)uid * 32 + 4 * q);
-        int ug = __ldg(b.user_genre + row * 5);
         if (ug >= p.n_genres) { atomicExch(b.err_flag, 1); ug = -1; }
         if (ug >= 0) ug4 = ldg4(p.ugenre + ug * 32 + 4 * q);
-        int mg = __ldg(b.movie_genre + row * 3);
         if (mg >= p.n_genres) { atomicExch(b.err_flag, 1); mg = -1; }
         if (mg >= 0) mg4 = ldg4(p.mgenre + mg * 32 + 4 * q);
       }
@@ -164,9 +207,14 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       store_x4(xh, xl, 0, rs, 32 + 4 * q, u4);
       store_x4(xh, xl, 1, rs, 32 + 4 * q, c4);        // K block 1: [pooled | candidate]
       store_x4(xh, xl, 2, rs, 4 * q, mg4);            // K block 2: [movieGenre1 | 0]
-      float nv = 0.f;
-      if (vr && q < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + q);
       nums[rs * 8 + q] = nv;
+    }
+    float4 hn[8];                                        // history row of the next tile to build
+    bool valid_nxt;
+    {
+      const int id0 = fix_id(raw0);
+      valid_nxt = id0 >= 0;
+      load_row(id0, hn);
     }
     wg_sync(wg);
     {  // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]
@@ -187,68 +235,42 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
 
     // ================= phase 1: activation unit + pooling ================================
-    // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
-    float4 hn[8];                                        // prefetched history row (tile k+1)
-    int id_next;                                         // history id two tiles ahead
-    auto pair_of = [&](int tile, int& rs, int& cq, int& t) {
-      const int ch = 4 * tile + warp_w;
-      rs = ch / CPR;
-      cq = ch - rs * CPR;
-      t = cq * 32 + lane;
-    };
-    auto load_id = [&](int tile) -> int {
-      if (tile >= n_tiles) return -1;
+    // Two TMEM buffers: the MMAs of tile k+1 run while tile k is read back and pooled.
+    // build(k): hn (history row of this thread's pair) -> A operand [h | h*c] hi/lo + fp32
+    // stash of h in TMEM buffer k&1, then one thread issues the 12 MMAs.
+    auto build_and_issue = [&](int tile) {
       int rs, cq, t;
       pair_of(tile, rs, cq, t);
-      const int row = row0 + rs;
-      if (row >= b.B || t >= T) return -1;
-      const int id = f32_roundtrip_id(__ldg(b.hist + (size_t)row * b.hist_stride + t));
-      return checked_id(id, p.n_movies, b.err_flag);
-    };
-    auto load_row = [&](int id, float4 (&h)[8]) {
-      if (id >= 0) {
-        const float* src = p.movie + (size_t)id * 32;
+      const uint32_t buf = tbase + (tile & 1) * 128;
+      const float* c = cand + rs * 32;
+      uint32_t ahi[16], alo[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = ldg4(src + 4 * q);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < 4; ++q) {
+        ahi[4 * q] = __float_as_uint(hn[q].x); ahi[4 * q + 1] = __float_as_uint(hn[q].y);
+        ahi[4 * q + 2] = __float_as_uint(hn[q].z); ahi[4 * q + 3] = __float_as_uint(hn[q].w);
+        alo[4 * q] = __float_as_uint(hn[q + 4].x); alo[4 * q + 1] = __float_as_uint(hn[q + 4].y);
+        alo[4 * q + 2] = __float_as_uint(hn[q + 4].z); alo[4 * q + 3] = __float_as_uint(hn[q + 4].w);
       }
-    };
-    int id_cur = load_id(0);
-    id_next = load_id(1);
-    load_row(id_cur, hn);
-
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      int rs, cq, t;
-      pair_of(tile, rs, cq, t);
-      const bool valid = id_cur >= 0;
-      float h[32];
+      tmem_st16(buf + TM_HS + lane_base, ahi);           // fp32 stash of h for the pooling step
+      tmem_st16(buf + TM_HS + 16 + lane_base, alo);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { h[4 * q] = hn[q].x; h[4 * q + 1] = hn[q].y; h[4 * q + 2] = hn[q].z; h[4 * q + 3] = hn[q].w; }
-      // ---- A operand: [h | h*c] as bf16 hi / lo, packed two K elements per column
-      {
-        const float* c = cand + rs * 32;
-        uint32_t ahi[16], alo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const Split2 sp = split_pack(h[2 * i], h[2 * i + 1]);
-          ahi[i] = sp.hi; alo[i] = sp.lo;
-        }
-        tmem_st16(tA_hi + lane_base, ahi);
-        tmem_st16(tA_lo + lane_base, alo);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * q);
-          const float g0 = h[4 * q] * c4.x, g1 = h[4 * q + 1] * c4.y, g2 = h[4 * q + 2] * c4.z,
-                      g3 = h[4 * q + 3] * c4.w;
-          const Split2 s0 = split_pack(g0, g1), s1 = split_pack(g2, g3);
-          ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
-          alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
-        }
-        tmem_st16(tA_hi + 16 + lane_base, ahi);
-        tmem_st16(tA_lo + 16 + lane_base, alo);
+      for (int q = 0; q < 8; ++q) {
+        const Split2 s0 = split_pack(hn[q].x, hn[q].y), s1 = split_pack(hn[q].z, hn[q].w);
+        ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
+        alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
       }
+      tmem_st16(buf + TM_A_HI + lane_base, ahi);
+      tmem_st16(buf + TM_A_LO + lane_base, alo);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * q);
+        const Split2 s0 = split_pack(hn[q].x * c4.x, hn[q].y * c4.y);
+        const Split2 s1 = split_pack(hn[q].z * c4.z, hn[q].w * c4.w);
+        ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
+        alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
+      }
+      tmem_st16(buf + TM_A_HI + 16 + lane_base, ahi);
+      tmem_st16(buf + TM_A_LO + 16 + lane_base, alo);
       tmem_st_wait();
       tc_fence_before();
       wg_sync(wg);
@@ -257,23 +279,43 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const uint64_t bh = smem_desc_sw128(s_img + IMG_AUB_HI), bl = smem_desc_sw128(s_img + IMG_AUB_LO);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ts(tD, tA_hi + 8 * ks, bh + 2 * ks, idesc_au, ks > 0);
-          mma_ts(tD, tA_lo + 8 * ks, bh + 2 * ks, idesc_au, 1);
-          mma_ts(tD, tA_hi + 8 * ks, bl + 2 * ks, idesc_au, 1);
+          mma_ts(buf + TM_D, buf + TM_A_HI + 8 * ks, bh + 2 * ks, idesc_au, ks > 0);
+          mma_ts(buf + TM_D, buf + TM_A_LO + 8 * ks, bh + 2 * ks, idesc_au, 1);
+          mma_ts(buf + TM_D, buf + TM_A_HI + 8 * ks, bl + 2 * ks, idesc_au, 1);
         }
-        mma_commit(my_bar);
+        mma_commit(&my_bar[tile & 1]);
       }
-      // ---- prefetch the next tile's history rows while the MMAs run
-      id_cur = id_next;
-      id_next = load_id(tile + 2);
-      load_row(tile + 1 < n_tiles ? id_cur : -1, hn);
+      __syncwarp();
+    };
 
-      mbar_wait(my_bar, phase);
-      phase ^= 1;
+    bool valid_cur = valid_nxt;
+    build_and_issue(0);
+    {
+      const int id1 = fix_id(raw1);
+      valid_nxt = id1 >= 0;
+      load_row(n_tiles > 1 ? id1 : -1, hn);
+      raw1 = raw2;                                       // raw1 := id of tile k+2, raw2 := tile k+3
+      raw2 = raw_id(3);
+    }
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const bool valid_next_tile = valid_nxt;
+      if (tile + 1 < n_tiles) {
+        build_and_issue(tile + 1);
+        const int idn = fix_id(raw1);
+        valid_nxt = idn >= 0;
+        load_row(tile + 2 < n_tiles ? idn : -1, hn);
+        raw1 = raw2;
+        raw2 = raw_id(tile + 4);
+      }
+      int rs, cq, t;
+      pair_of(tile, rs, cq, t);
+      const uint32_t buf = tbase + (tile & 1) * 128;
+      mbar_wait(&my_bar[tile & 1], (phase >> (tile & 1)) & 1);
+      phase ^= 1u << (tile & 1);
       __syncwarp();
       tc_fence_after();
       uint32_t d[32];
-      tmem_ld32(tD + lane_base, d);
+      tmem_ld32(buf + TM_D + lane_base, d);
       tmem_ld_wait();
       // ---- epilogue: + cst, PReLU (alpha per position), Dense(1), sigmoid gate
       float s = p.au_bout;
@@ -287,10 +329,14 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
           s = fmaf(fminf(v, 0.f), aw[j * TP], s);
         }
       }
-      const float w = valid ? 1.f / (1.f + __expf(-s)) : 0.f;
+      const float w = valid_cur ? 1.f / (1.f + __expf(-s)) : 0.f;
+      valid_cur = valid_next_tile;
       // ---- pooling: out[e = lane] = sum over the chunk's 32 positions of w_t * h_t[e]
+      tmem_ld32(buf + TM_HS + lane_base, d);
+      tmem_ld_wait();
+      float h[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) h[e] *= w;
+      for (int e = 0; e < 32; ++e) h[e] = __uint_as_float(d[e]) * w;
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         const bool up = (lane & o) != 0;
@@ -303,6 +349,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       }
       part[(rs * kTcMaxCPR + cq) * 32 + lane] = h[0];
     }
+    tc_fence_before();
     wg_sync(wg);
 
     // ================= phase 2: top MLP on the group's 16 rows ============================
@@ -335,9 +382,9 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
           mma_ss(tD1, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(my_bar);
+      mma_commit(&my_bar[0]);
     }
-    mbar_wait(my_bar, phase);
+    mbar_wait(&my_bar[0], phase & 1);
     phase ^= 1;
     __syncwarp();
     tc_fence_after();
@@ -381,10 +428,10 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
           mma_ss(tD2, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(my_bar);
+      mma_commit(&my_bar[1]);
     }
-    mbar_wait(my_bar, phase);
-    phase ^= 1;
+    mbar_wait(&my_bar[1], (phase >> 1) & 1);
+    phase ^= 2;
     __syncwarp();
     tc_fence_after();
     {
@@ -432,7 +479,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   if (!weights_ready) mbar_wait(&wbar, 0);               // never exit with the bulk copy in flight
   tc_fence_before();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem_slot, 256);
+  if (tid < 32) tmem_dealloc(tmem_slot, 512);
 }
 
 size_t din_tc_smem_bytes(int cpr) {
