@@ -169,6 +169,11 @@ int srs_fill_uniform(float* device_ptr, int64_t n, uint64_t seed, float lo, floa
 int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, int32_t dim,
                              float* scores, int32_t device, void* stream);
 
+/* Debug aid for kernel tuning: enable/disable recording of per-phase SM-clock timestamps
+ * in the tensor-core DIN kernel (worker 0 of CTA 0) and, if out40 != NULL, synchronise and
+ * copy the 40 recorded values out.  No effect on results. */
+int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40);
+
 /* Known-answer self test of the tcgen05 / TMEM plumbing the DIN kernel is built on:
  * D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T (inputs truncated to bf16, fp32 accumulate),
  * K = 64 * k_blocks (1..3), N = 16 or 32, A staged through shared memory (a_in_tmem = 0)

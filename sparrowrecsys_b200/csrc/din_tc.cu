@@ -9,23 +9,28 @@
 //                    (tcgen05.st) - the history rows go global -> registers -> TMEM and
 //                    never touch shared memory; Bau = [Wsub+Wh ; Wp]^T resident in smem.
 //   top layer 1      D1[128 units x 16 rows] = W1^T[128 x 192] * X[16 x 192]^T  (transposed
-//                    so that the 16 rows of a group are the MMA's N and the weights its M)
+//                    so that the rows of a group are the MMA's N and the weights its M)
 //   top layer 2      D2[(64 units hi | 64 units lo) x 16 rows] = W2stack[128 x 128] * H1^T
 //
 // Precision: every operand is split x = hi + lo into two bf16 halves and each product is
 // evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation ("bf16x3", relative error
-// ~2^-16 per product); numerics (raw releaseYear, rating counts) never enter an MMA - their
+// ~2^-17 per product); numerics (raw releaseYear, rating counts) never enter an MMA - their
 // rank-7 contribution is added in fp32 in the layer-1 epilogue.  Measured against the
 // oracle in tests/test_gpu_parity.py.
 //
-// Work decomposition: a CTA is two independent warpgroups ("workers") sharing the weight
-// images in shared memory; a worker owns groups of 16 consecutive rows.  Per group:
-//   phase 0  gather candidate/user/genre rows -> X operand tile (bf16 hi/lo, SW128) + cst
-//   phase 1  for each tile of 4 chunks x 32 positions: thread = (row, position) pair:
-//            gather its history row (8 x 128-bit loads, prefetched one tile ahead), build A,
-//            MMA (12 instr), read back 32 accumulators, PReLU / gate, butterfly-pool
-//   phase 2  pooled -> X tile, layer-1 MMA (36), epilogue (bias, numerics, PReLU) -> H1
-//            operand tile, layer-2 MMA (16), epilogue, sigmoid, store 16 scores.
+// Work decomposition: one persistent CTA per SM holds the weight images in shared memory
+// (bulk-copied once per launch) and runs four independent warpgroups ("workers"), each
+// with 128 tensor-memory columns and 13 KB of scratch.  A worker owns groups of G (8 or 16)
+// consecutive rows; the four workers interleave on the SM, which is what hides the
+// latencies of the serial per-group chain:
+//   phase 0  candidate/user/genre row gathers (kept in registers), cst_b
+//   phase 1  per tile of 4 chunks x 32 positions, thread = (row, position) pair: its
+//            history row arrives by 8 x 128-bit loads prefetched one tile ahead, A operand
+//            -> TMEM, 12 MMAs, read back 32 accumulators, PReLU / sigmoid gate,
+//            butterfly-pool w_t * h_t over the chunk
+//   phase 2  X operand tile (bf16 hi/lo, SW128) <- pooled + side rows, layer-1 MMAs (36),
+//            epilogue (bias, numerics, PReLU) -> H1 operand tile, layer-2 MMAs (16),
+//            epilogue, sigmoid, scores out.
 #include <climits>
 
 #include "kernels.h"
@@ -34,34 +39,44 @@
 namespace srs {
 using namespace umma;
 
-constexpr int kTcRows = 16;              // rows per group (N of the top-MLP MMAs)
-constexpr int kTcWG = 2;                 // warpgroups (workers) per CTA
+constexpr int kTcWG = 4;                 // warpgroups (workers) per CTA
 constexpr int kTcMaxCPR = 4;             // chunks (of 32 positions) per row: T <= 128
 constexpr int kNoPair = INT_MIN;         // sentinel: this thread has no (row, position) pair
 
-// tensor-memory map of one worker: 2 buffers x 128 columns
+// tensor-memory map of one worker (128 columns)
 constexpr uint32_t TM_A_HI = 0;          // 32 cols: bf16 pairs of [h | h*c], hi halves
 constexpr uint32_t TM_A_LO = 32;         // 32 cols: lo halves
-constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators (fp32)
-constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling
+constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators; top layer 1 (16 cols)
+constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling; top layer 2 (16 cols)
 
-// shared-memory image (bulk-copied from global; built by build_din_tc_image in model.cu)
+// shared-memory image (bulk-copied from global; built by build_din_tc in model.cu)
 constexpr uint32_t IMG_AUB_HI = 0;                       // [32 units][64 k] bf16, SW128
 constexpr uint32_t IMG_AUB_LO = 4096;
 constexpr uint32_t IMG_W1_HI = 8192;                     // 3 K blocks x [128 units][64 k]
 constexpr uint32_t IMG_W1_LO = IMG_W1_HI + 3 * 16384;
 constexpr uint32_t IMG_W2 = IMG_W1_LO + 3 * 16384;       // 2 K blocks x [64 hi | 64 lo units][64 k]
 constexpr uint32_t IMG_ALPHAW = IMG_W2 + 2 * 16384;      // f32 [32 units][TP] alpha*wout, TP = CPR*32
-// per-worker scratch
-constexpr uint32_t WS_XB_HI = 0;                         // 3 K blocks x [16 rows][64 k] bf16
+// per-worker scratch: phases 0/1 and phase 2 overlay the same 12 KB
+constexpr uint32_t WS_CAND = 0;                          // f32 [16][32]              (phase 0/1)
+constexpr uint32_t WS_CST = 2048;                        // f32 [16][32]              (phase 0/1)
+constexpr uint32_t WS_PART = 4096;                       // f32 [16][4][32] partials  (phase 1)
+constexpr uint32_t WS_XB_HI = 0;                         // 3 K blocks x [16 rows][64 k] bf16 (phase 2)
 constexpr uint32_t WS_XB_LO = 6144;
-constexpr uint32_t WS_H1_HI = 12288;                     // 2 K blocks x [16 rows][64 k]
-constexpr uint32_t WS_H1_LO = 16384;
-constexpr uint32_t WS_CAND = 20480;                      // f32 [16][32]
-constexpr uint32_t WS_CST = 22528;                       // f32 [16][32]
-constexpr uint32_t WS_PART = 24576;                      // f32 [16][4][32] pooled partials / reduce scratch
-constexpr uint32_t WS_NUMS = 32768;                      // f32 [16][8]
-constexpr uint32_t WS_BYTES = 33792;
+constexpr uint32_t WS_H1_HI = 0;                         // 2 K blocks x [16 rows][64 k]; after layer 1
+constexpr uint32_t WS_H1_LO = 4096;
+constexpr uint32_t WS_RED = 8192;                        // f32 [64][16]; after layer 1
+constexpr uint32_t WS_NUMS = 12288;                      // f32 [16][8]
+constexpr uint32_t WS_ZP = 12800;                        // f32 [8][16] final partial sums
+constexpr uint32_t WS_BYTES = 13312;
+
+// Phase timestamps (SM clock) of worker 0 of CTA 0, written when DinTcParams::trace != 0:
+// [0] kernel entry, [1] prologue done, [2] phase 0 done, [3] weight image landed,
+// [4 + k] tile k read back and pooled, [30] top layer 1 done, [31] group done, [32] exit.
+__device__ unsigned long long g_din_tc_trace[40];
+#define TC_TRACE(slot)                                                             \
+  do {                                                                             \
+    if (p.trace && blockIdx.x == 0 && tid == 0) g_din_tc_trace[slot] = clock64();  \
+  } while (0)
 
 __host__ __device__ inline uint32_t din_tc_image_bytes(int cpr) { return IMG_ALPHAW + 32u * cpr * 32u * 4u; }
 
@@ -86,10 +101,11 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
                                                                  BatchView b) {
   extern __shared__ uint8_t raw[];
   __shared__ uint64_t wbar;                 // weight image landed
-  __shared__ uint64_t mbar[kTcWG][2];       // per-worker "MMAs complete", one per TMEM buffer
+  __shared__ uint64_t mbar[kTcWG];          // per-worker "MMAs complete"
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
+  TC_TRACE(0);
   const int wg = tid >> 7, tw = tid & 127, warp_w = tw >> 5, lane = tw & 31;
   uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* img = base;
@@ -106,47 +122,36 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   if (tid < 32) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&wbar, 1);
-    for (int i = 0; i < kTcWG; ++i) { mbar_init(&mbar[i][0], 1); mbar_init(&mbar[i][1], 1); }
+    for (int i = 0; i < kTcWG; ++i) mbar_init(&mbar[i], 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(&wbar, img_bytes);
-    for (uint32_t off = 0; off < img_bytes; off += 32768u) {
-      const uint32_t n = min(32768u, img_bytes - off);
-      bulk_g2s(img + off, p.image + off, n, &wbar);
-    }
+    // activation-unit operand + alpha table first (needed first), then the top-MLP images
+    bulk_g2s(img, p.image, 8192, &wbar);
+    bulk_g2s(img + IMG_ALPHAW, p.image + IMG_ALPHAW, img_bytes - IMG_ALPHAW, &wbar);
+    for (uint32_t off = 8192; off < IMG_ALPHAW; off += 32768u)
+      bulk_g2s(img + off, p.image + off, min(32768u, IMG_ALPHAW - off), &wbar);
   }
-  // zero the K padding of the X operand (K block 2, columns 32..63): never rewritten
-  for (int i = tw; i < 16 * 4; i += 128) {
-    const int rs = i >> 2, ch = 4 + (i & 3);
-    const uint32_t off = 2 * 2048u + sw128_offset(rs, ch);
-    *reinterpret_cast<uint4*>(ws + WS_XB_HI + off) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(ws + WS_XB_LO + off) = make_uint4(0, 0, 0, 0);
-  }
-  // per-thread constants: this thread is unit `tw` of layer 1 and unit `tw & 63` of layer 2
-  const float b1 = __ldg(p.b1 + tw), a1 = __ldg(p.a1 + tw);
-  float w1n[kNumNumerics];
-#pragma unroll
-  for (int n = 0; n < kNumNumerics; ++n) w1n[n] = __ldg(p.w1num + n * 128 + tw);
-  const float b2 = __ldg(p.b2 + (tw & 63)), a2 = __ldg(p.a2 + (tw & 63)), w3 = __ldg(p.w3 + (tw & 63));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = tmem_slot + wg * 256;          // this worker's 256 TMEM columns
+  TC_TRACE(1);
+  const uint32_t tbase = tmem_slot + wg * 128;          // this worker's 128 TMEM columns
   const uint32_t lane_base = (uint32_t)(warp_w * 32) << 16;
-  const uint32_t tD1 = tbase + TM_D, tD2 = tbase + 128 + TM_D;   // top MLP reuses the AU accumulators
-  uint64_t* my_bar = mbar[wg];
-  uint32_t phase = 0;                                   // bit i = parity to wait for on my_bar[i]
+  uint64_t* my_bar = &mbar[wg];
+  uint32_t phase = 0;
   bool weights_ready = false;
 
   const uint32_t idesc_au = idesc_bf16(128, 32), idesc_top = idesc_bf16(128, 16);
   const uint32_t s_img = smem_u32(img), s_ws = smem_u32(ws);
 
-  const int n_groups = (b.B + kTcRows - 1) / kTcRows;
+  const int G = p.G;                                    // rows per group: 8 or 16
+  const int n_groups = (b.B + G - 1) / G;
   const int n_workers = gridDim.x * kTcWG;
   const int CPR = p.CPR, T = p.T;
-  const int n_tiles = 4 * CPR;                          // 16 rows * CPR chunks / 4 chunks per tile
+  const int n_tiles = (G * CPR) >> 2;                   // G rows * CPR chunks / 4 chunks per tile
 
   for (int g = blockIdx.x * kTcWG + wg; g < n_groups; g += n_workers) {
-    const int row0 = g * kTcRows;
+    const int row0 = g * G;
     // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
     auto pair_of = [&](int tile, int& rs, int& cq, int& t) {
       const int ch = 4 * tile + warp_w;
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       t = cq * 32 + lane;
     };
     // raw history id of this thread's pair in `tile` (kNoPair if none); the value is not
-    // touched here so the load stays in flight until fix_id() one or two tiles later
+    // touched here so the load stays in flight until fix_id() a tile later
     auto raw_id = [&](int tile) -> int {
       if (tile >= n_tiles) return kNoPair;
       int rs, cq, t;
@@ -178,36 +183,32 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int raw0 = raw_id(0), raw1 = raw_id(1), raw2 = raw_id(2);   // ids come from HBM: start now
+    int raw0 = raw_id(0), raw1 = raw_id(1);             // ids come from HBM: start them now
 
-    // ================= phase 0: side gathers -> X operand, candidate rows, cst ==========
+    // ================= phase 0: side gathers (registers), candidate rows, cst ============
+    // thread (rs = tw / 8, q = tw % 8) owns floats [4q, 4q+4) of the side rows of row rs
+    const int srs = tw >> 3, sq = tw & 7;
+    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), ug4 = u4, mg4 = u4;
     {
-      const int rs = tw >> 3, q = tw & 7;
-      const int row = row0 + rs;
-      const bool vr = row < b.B;
-      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = c4, ug4 = c4, mg4 = c4;
+      const int row = row0 + srs;
+      const bool vr = srs < G && row < b.B;
+      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float nv = 0.f;
       if (vr) {
         const int cid_raw = __ldg(b.movie_id + row), uid_raw = __ldg(b.user_id + row);
         int ug = __ldg(b.user_genre + row * 5), mg = __ldg(b.movie_genre + row * 3);
-        if (q < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + q);
+        if (sq < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + sq);
         const int cid = checked_id(f32_roundtrip_id(cid_raw), p.n_movies, b.err_flag);
         const int uid = checked_id(uid_raw, p.n_users, b.err_flag);
-        c4 = ldg4(p.movie + (size_t)cid * 32 + 4 * q);
-        u4 = ldg4(p.user + (size_t)uid * 32 + 4 * q);
+        c4 = ldg4(p.movie + (size_t)cid * 32 + 4 * sq);
+        u4 = ldg4(p.user + (size_t)uid * 32 + 4 * sq);
         if (ug >= p.n_genres) { atomicExch(b.err_flag, 1); ug = -1; }
-        if (ug >= 0) ug4 = ldg4(p.ugenre + ug * 32 + 4 * q);
+        if (ug >= 0) ug4 = ldg4(p.ugenre + ug * 32 + 4 * sq);
         if (mg >= p.n_genres) { atomicExch(b.err_flag, 1); mg = -1; }
-        if (mg >= 0) mg4 = ldg4(p.mgenre + mg * 32 + 4 * q);
+        if (mg >= 0) mg4 = ldg4(p.mgenre + mg * 32 + 4 * sq);
       }
-      *reinterpret_cast<float4*>(cand + rs * 32 + 4 * q) = c4;
-      uint8_t* xh = ws + WS_XB_HI;
-      uint8_t* xl = ws + WS_XB_LO;
-      store_x4(xh, xl, 0, rs, 4 * q, ug4);            // K block 0: [userGenre1 | userId]
-      store_x4(xh, xl, 0, rs, 32 + 4 * q, u4);
-      store_x4(xh, xl, 1, rs, 32 + 4 * q, c4);        // K block 1: [pooled | candidate]
-      store_x4(xh, xl, 2, rs, 4 * q, mg4);            // K block 2: [movieGenre1 | 0]
-      nums[rs * 8 + q] = nv;
+      *reinterpret_cast<float4*>(cand + srs * 32 + 4 * sq) = c4;
+      nums[srs * 8 + sq] = nv;
     }
     float4 hn[8];                                        // history row of the next tile to build
     bool valid_nxt;
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       const int id0 = fix_id(raw0);
       valid_nxt = id0 >= 0;
       load_row(id0, hn);
+      raw0 = raw_id(2);                                  // raw1 = tile 1, raw0 = tile 2
     }
     wg_sync(wg);
     {  // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]
@@ -232,45 +234,47 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       for (int i = 0; i < 4; ++i) cst[(warp_w + 4 * i) * 32 + lane] = acc[i];
     }
     wg_sync(wg);
+    TC_TRACE(2);
     if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
+    TC_TRACE(3);
 
     // ================= phase 1: activation unit + pooling ================================
-    // Two TMEM buffers: the MMAs of tile k+1 run while tile k is read back and pooled.
-    // build(k): hn (history row of this thread's pair) -> A operand [h | h*c] hi/lo + fp32
-    // stash of h in TMEM buffer k&1, then one thread issues the 12 MMAs.
-    auto build_and_issue = [&](int tile) {
+    for (int tile = 0; tile < n_tiles; ++tile) {
       int rs, cq, t;
       pair_of(tile, rs, cq, t);
-      const uint32_t buf = tbase + (tile & 1) * 128;
-      const float* c = cand + rs * 32;
-      uint32_t ahi[16], alo[16];
+      const bool valid = valid_nxt;
+      // ---- A operand [h | h*c] as bf16 hi / lo (two K elements per column) + fp32 stash of h
+      {
+        const float* c = cand + rs * 32;
+        uint32_t ahi[16], alo[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        ahi[4 * q] = __float_as_uint(hn[q].x); ahi[4 * q + 1] = __float_as_uint(hn[q].y);
-        ahi[4 * q + 2] = __float_as_uint(hn[q].z); ahi[4 * q + 3] = __float_as_uint(hn[q].w);
-        alo[4 * q] = __float_as_uint(hn[q + 4].x); alo[4 * q + 1] = __float_as_uint(hn[q + 4].y);
-        alo[4 * q + 2] = __float_as_uint(hn[q + 4].z); alo[4 * q + 3] = __float_as_uint(hn[q + 4].w);
-      }
-      tmem_st16(buf + TM_HS + lane_base, ahi);           // fp32 stash of h for the pooling step
-      tmem_st16(buf + TM_HS + 16 + lane_base, alo);
+        for (int q = 0; q < 4; ++q) {
+          ahi[4 * q] = __float_as_uint(hn[q].x); ahi[4 * q + 1] = __float_as_uint(hn[q].y);
+          ahi[4 * q + 2] = __float_as_uint(hn[q].z); ahi[4 * q + 3] = __float_as_uint(hn[q].w);
+          alo[4 * q] = __float_as_uint(hn[q + 4].x); alo[4 * q + 1] = __float_as_uint(hn[q + 4].y);
+          alo[4 * q + 2] = __float_as_uint(hn[q + 4].z); alo[4 * q + 3] = __float_as_uint(hn[q + 4].w);
+        }
+        tmem_st16(tbase + TM_HS + lane_base, ahi);
+        tmem_st16(tbase + TM_HS + 16 + lane_base, alo);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const Split2 s0 = split_pack(hn[q].x, hn[q].y), s1 = split_pack(hn[q].z, hn[q].w);
-        ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
-        alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
-      }
-      tmem_st16(buf + TM_A_HI + lane_base, ahi);
-      tmem_st16(buf + TM_A_LO + lane_base, alo);
+        for (int q = 0; q < 8; ++q) {
+          const Split2 s0 = split_pack(hn[q].x, hn[q].y), s1 = split_pack(hn[q].z, hn[q].w);
+          ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
+          alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
+        }
+        tmem_st16(tbase + TM_A_HI + lane_base, ahi);
+        tmem_st16(tbase + TM_A_LO + lane_base, alo);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * q);
-        const Split2 s0 = split_pack(hn[q].x * c4.x, hn[q].y * c4.y);
-        const Split2 s1 = split_pack(hn[q].z * c4.z, hn[q].w * c4.w);
-        ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
-        alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
+        for (int q = 0; q < 8; ++q) {
+          const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * q);
+          const Split2 s0 = split_pack(hn[q].x * c4.x, hn[q].y * c4.y);
+          const Split2 s1 = split_pack(hn[q].z * c4.z, hn[q].w * c4.w);
+          ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
+          alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
+        }
+        tmem_st16(tbase + TM_A_HI + 16 + lane_base, ahi);
+        tmem_st16(tbase + TM_A_LO + 16 + lane_base, alo);
       }
-      tmem_st16(buf + TM_A_HI + 16 + lane_base, ahi);
-      tmem_st16(buf + TM_A_LO + 16 + lane_base, alo);
       tmem_st_wait();
       tc_fence_before();
       wg_sync(wg);
@@ -279,60 +283,52 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const uint64_t bh = smem_desc_sw128(s_img + IMG_AUB_HI), bl = smem_desc_sw128(s_img + IMG_AUB_LO);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ts(buf + TM_D, buf + TM_A_HI + 8 * ks, bh + 2 * ks, idesc_au, ks > 0);
-          mma_ts(buf + TM_D, buf + TM_A_LO + 8 * ks, bh + 2 * ks, idesc_au, 1);
-          mma_ts(buf + TM_D, buf + TM_A_HI + 8 * ks, bl + 2 * ks, idesc_au, 1);
+          mma_ts(tbase + TM_D, tbase + TM_A_HI + 8 * ks, bh + 2 * ks, idesc_au, ks > 0);
+          mma_ts(tbase + TM_D, tbase + TM_A_LO + 8 * ks, bh + 2 * ks, idesc_au, 1);
+          mma_ts(tbase + TM_D, tbase + TM_A_HI + 8 * ks, bl + 2 * ks, idesc_au, 1);
         }
-        mma_commit(&my_bar[tile & 1]);
+        mma_commit(my_bar);
       }
       __syncwarp();
-    };
-
-    bool valid_cur = valid_nxt;
-    build_and_issue(0);
-    {
-      const int id1 = fix_id(raw1);
-      valid_nxt = id1 >= 0;
-      load_row(n_tiles > 1 ? id1 : -1, hn);
-      raw1 = raw2;                                       // raw1 := id of tile k+2, raw2 := tile k+3
-      raw2 = raw_id(3);
-    }
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      const bool valid_next_tile = valid_nxt;
-      if (tile + 1 < n_tiles) {
-        build_and_issue(tile + 1);
+      // ---- prefetch the next tile's history rows while the MMAs run
+      {
         const int idn = fix_id(raw1);
         valid_nxt = idn >= 0;
-        load_row(tile + 2 < n_tiles ? idn : -1, hn);
-        raw1 = raw2;
-        raw2 = raw_id(tile + 4);
+        load_row(tile + 1 < n_tiles ? idn : -1, hn);
+        raw1 = raw0;
+        raw0 = raw_id(tile + 3);
       }
-      int rs, cq, t;
-      pair_of(tile, rs, cq, t);
-      const uint32_t buf = tbase + (tile & 1) * 128;
-      mbar_wait(&my_bar[tile & 1], (phase >> (tile & 1)) & 1);
-      phase ^= 1u << (tile & 1);
+      mbar_wait(my_bar, phase);
+      phase ^= 1;
       __syncwarp();
       tc_fence_after();
       uint32_t d[32];
-      tmem_ld32(buf + TM_D + lane_base, d);
+      tmem_ld32(tbase + TM_D + lane_base, d);
       tmem_ld_wait();
       // ---- epilogue: + cst, PReLU (alpha per position), Dense(1), sigmoid gate
-      float s = p.au_bout;
+      float s0 = p.au_bout, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       {
         const float* cs = cst + rs * 32;
         const float* aw = alphaw + t;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(d[j]) + cs[j];
-          s = fmaf(fmaxf(v, 0.f), p.au_wout[j], s);
-          s = fmaf(fminf(v, 0.f), aw[j * TP], s);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
+          const float v0 = __uint_as_float(d[j]) + c4.x, v1 = __uint_as_float(d[j + 1]) + c4.y;
+          const float v2 = __uint_as_float(d[j + 2]) + c4.z, v3 = __uint_as_float(d[j + 3]) + c4.w;
+          s0 = fmaf(fmaxf(v0, 0.f), p.au_wout[j], s0);
+          s1 = fmaf(fmaxf(v1, 0.f), p.au_wout[j + 1], s1);
+          s2 = fmaf(fmaxf(v2, 0.f), p.au_wout[j + 2], s2);
+          s3 = fmaf(fmaxf(v3, 0.f), p.au_wout[j + 3], s3);
+          s0 = fmaf(fminf(v0, 0.f), aw[j * TP], s0);
+          s1 = fmaf(fminf(v1, 0.f), aw[(j + 1) * TP], s1);
+          s2 = fmaf(fminf(v2, 0.f), aw[(j + 2) * TP], s2);
+          s3 = fmaf(fminf(v3, 0.f), aw[(j + 3) * TP], s3);
         }
       }
-      const float w = valid_cur ? 1.f / (1.f + __expf(-s)) : 0.f;
-      valid_cur = valid_next_tile;
+      const float s = (s0 + s1) + (s2 + s3);
+      const float w = valid ? 1.f / (1.f + __expf(-s)) : 0.f;
       // ---- pooling: out[e = lane] = sum over the chunk's 32 positions of w_t * h_t[e]
-      tmem_ld32(buf + TM_HS + lane_base, d);
+      tmem_ld32(tbase + TM_HS + lane_base, d);
       tmem_ld_wait();
       float h[32];
 #pragma unroll
@@ -348,19 +344,29 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         }
       }
       part[(rs * kTcMaxCPR + cq) * 32 + lane] = h[0];
+      if (tile < 24) TC_TRACE(4 + tile);
     }
-    tc_fence_before();
     wg_sync(wg);
 
-    // ================= phase 2: top MLP on the group's 16 rows ============================
-    {
-      const int rs = tw >> 3, q = tw & 7;
+    // ================= phase 2: top MLP on the group's rows ================================
+    {  // pooled and candidate leave the phase-1 scratch before the X operand overlays it
       float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = 0; c < CPR; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (rs * kTcMaxCPR + c) * 32 + 4 * q);
+      for (int c = 0; c < (srs < G ? CPR : 0); ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (srs * kTcMaxCPR + c) * 32 + 4 * sq);
         pl.x += v.x; pl.y += v.y; pl.z += v.z; pl.w += v.w;
       }
-      store_x4(ws + WS_XB_HI, ws + WS_XB_LO, 1, rs, 4 * q, pl);
+      const float4 c4 = *reinterpret_cast<const float4*>(cand + srs * 32 + 4 * sq);
+      wg_sync(wg);
+      uint8_t* xh = ws + WS_XB_HI;
+      uint8_t* xl = ws + WS_XB_LO;
+      store_x4(xh, xl, 0, srs, 4 * sq, ug4);           // K block 0: [userGenre1 | userId]
+      store_x4(xh, xl, 0, srs, 32 + 4 * sq, u4);
+      store_x4(xh, xl, 1, srs, 4 * sq, pl);            // K block 1: [pooled | candidate]
+      store_x4(xh, xl, 1, srs, 32 + 4 * sq, c4);
+      store_x4(xh, xl, 2, srs, 4 * sq, mg4);           // K block 2: [movieGenre1 | 0]
+      const uint32_t zoff = 2 * 2048u + sw128_offset(srs, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
+      *reinterpret_cast<uint2*>(xh + zoff) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(xl + zoff) = make_uint2(0u, 0u);
     }
     fence_async_smem();
     tc_fence_before();
@@ -376,23 +382,31 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const uint64_t xl = smem_desc_sw128(s_ws + WS_XB_LO + kb * 2048);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tD1, ah + 2 * ks, xh + 2 * ks, idesc_top, acc);
+          mma_ss(tbase + TM_D, ah + 2 * ks, xh + 2 * ks, idesc_top, acc);
           acc = 1;
-          mma_ss(tD1, al + 2 * ks, xh + 2 * ks, idesc_top, 1);
-          mma_ss(tD1, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
+          mma_ss(tbase + TM_D, al + 2 * ks, xh + 2 * ks, idesc_top, 1);
+          mma_ss(tbase + TM_D, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(&my_bar[0]);
+      mma_commit(my_bar);
     }
-    mbar_wait(&my_bar[0], phase & 1);
+    __syncwarp();
+    // this thread is unit `tw` of layer 1: its constants arrive while the MMAs run
+    const float b1 = __ldg(p.b1 + tw), a1 = __ldg(p.a1 + tw);
+    float w1n[kNumNumerics];
+#pragma unroll
+    for (int n = 0; n < kNumNumerics; ++n) w1n[n] = __ldg(p.w1num + n * 128 + tw);
+    mbar_wait(my_bar, phase);
     phase ^= 1;
     __syncwarp();
     tc_fence_after();
+    TC_TRACE(30);
     {
       uint32_t d[16];
-      tmem_ld16(tD1 + lane_base, d);
+      tmem_ld16(tbase + TM_D + lane_base, d);
       tmem_ld_wait();
-      // layer-1 epilogue for unit tw: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo)
+      // layer-1 epilogue for unit tw: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo),
+      // which overlays the X operand (its MMAs have completed)
       const uint32_t koff = (uint32_t)(tw >> 6) * 2048u;
       const uint32_t chunk = (tw & 63) >> 3, within = (tw & 7) * 2;
 #pragma unroll
@@ -423,22 +437,25 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const uint64_t hl = smem_desc_sw128(s_ws + WS_H1_LO + kb * 2048);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tD2, a + 2 * ks, hh + 2 * ks, idesc_top, acc);
+          mma_ss(tbase + TM_HS, a + 2 * ks, hh + 2 * ks, idesc_top, acc);
           acc = 1;
-          mma_ss(tD2, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
+          mma_ss(tbase + TM_HS, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(&my_bar[1]);
+      mma_commit(my_bar);
     }
-    mbar_wait(&my_bar[1], (phase >> 1) & 1);
-    phase ^= 2;
+    __syncwarp();
+    const float b2 = __ldg(p.b2 + (tw & 63)), a2 = __ldg(p.a2 + (tw & 63)), w3 = __ldg(p.w3 + (tw & 63));
+    mbar_wait(my_bar, phase);
+    phase ^= 1;
     __syncwarp();
     tc_fence_after();
     {
       uint32_t d[16];
-      tmem_ld16(tD2 + lane_base, d);
+      tmem_ld16(tbase + TM_HS + lane_base, d);
       tmem_ld_wait();
-      float* red = part;                                  // [64 units][16 rows]
+      float* red = reinterpret_cast<float*>(ws + WS_RED);     // [64 units][16 rows]
+      float* zp = reinterpret_cast<float*>(ws + WS_ZP);       // [8][16]
       if (tw >= 64) {
 #pragma unroll
         for (int r = 0; r < 16; r += 4)
@@ -461,13 +478,13 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         float s = 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) s += red[(pt * 8 + u) * 16 + r];
-        cst[pt * 16 + r] = s;
+        zp[pt * 16 + r] = s;
       }
       wg_sync(wg);
-      if (tw < 16) {
+      if (tw < G) {
         float z = p.b3;
 #pragma unroll
-        for (int pt = 0; pt < 8; ++pt) z += cst[pt * 16 + tw];
+        for (int pt = 0; pt < 8; ++pt) z += zp[pt * 16 + tw];
         const int row = row0 + tw;
         if (row < b.B) {
           b.probs[row] = sigmoidf_acc(z);
@@ -475,20 +492,32 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         }
       }
     }
+    tc_fence_before();
+    wg_sync(wg);                                         // scratch is reused by the next group
+    TC_TRACE(31);
   }
   if (!weights_ready) mbar_wait(&wbar, 0);               // never exit with the bulk copy in flight
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_slot, 512);
+  TC_TRACE(32);
+}
+
+cudaError_t read_din_tc_trace(unsigned long long* out40) {
+  return cudaMemcpyFromSymbol(out40, g_din_tc_trace, sizeof(unsigned long long) * 40);
 }
 
 size_t din_tc_smem_bytes(int cpr) {
   return 1024 + ((din_tc_image_bytes(cpr) + 1023u) & ~1023u) + (size_t)kTcWG * WS_BYTES;
 }
 
-cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
+cudaError_t launch_din_tc(const DinTcParams& p0, const BatchView& b, cudaStream_t s) {
   if (b.B <= 0) return cudaSuccess;
-  const int n_groups = (b.B + kTcRows - 1) / kTcRows;
+  DinTcParams p = p0;
+  // rows per group: 16 when there is enough work to keep every worker busy, else 8
+  const int workers = p.num_sms * kTcWG;
+  p.G = (b.B >= 16 * workers) ? 16 : 8;
+  const int n_groups = (b.B + p.G - 1) / p.G;
   int grid = (n_groups + kTcWG - 1) / kTcWG;
   if (grid > p.num_sms) grid = p.num_sms;
   din_tc_kernel<<<grid, kTcWG * 128, din_tc_smem_bytes(p.CPR), s>>>(p, b);

@@ -141,10 +141,13 @@ struct DinTcParams {
   int T;
   int CPR;                 // 32-position chunks per row = ceil(T / 32)
   int num_sms;
+  int G;                   // rows per group (8 or 16), chosen per launch
+  int trace;               // debug: record phase timestamps of worker 0 (srs_debug_din_trace)
 };
 
 // launchers (defined next to their kernels); return cudaGetLastError()
 cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t read_din_tc_trace(unsigned long long* out40);
 cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_embmlp(const EmbMlpParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_t s);

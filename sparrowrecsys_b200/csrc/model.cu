@@ -920,6 +920,17 @@ int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, 
   return SRS_OK;
 }
 
+int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  CUDA_TRY(cudaSetDevice(m->device));
+  m->din_tc.trace = enable;
+  if (out40) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
+  }
+  return SRS_OK;
+}
+
 int srs_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t k_blocks,
                       int32_t a_in_tmem, int32_t device) {
   if (!A || !B || !D) return fail(SRS_ERR_INVALID, "null pointer");
