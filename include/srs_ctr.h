@@ -89,7 +89,11 @@ typedef struct srs_tensor {
  * (-1 = missing / out of vocabulary -> zero vector), integer numerics already
  * cast to float32 (what numeric_column does).  Pointers a model does not read may
  * be NULL.  All pointers are host pointers for srs_predict_host* and device
- * pointers (on the model's device) for srs_predict_device. */
+ * pointers (on the model's device) for srs_predict_device.
+ * Fast path for host batches: when the arrays lie back to back in memory in the order
+ * movie_id, user_id, hist (hist_stride == T), movie_genre, user_genre, numerics (arrays the
+ * model does not read left out), srs_predict_host* moves the whole batch with ONE
+ * host-to-device copy instead of one per array. */
 typedef struct srs_batch {
   int32_t B;                   /* rows                                            */
   int32_t hist_stride;         /* elements between consecutive rows of `hist`     */
@@ -134,6 +138,15 @@ int srs_predict_device(srs_model* m, const srs_batch* batch, float* probs, float
  * and for one TF-Serving `:predict` call.  Returns SRS_ERR_RANGE if an id was
  * out of range (outputs are still written). */
 int srs_predict_host(srs_model* m, const srs_batch* batch, float* probs, float* logits);
+
+/* A whole dataset in batches, the way `model.predict(dataset)` iterates it (e.g.
+ * DIN.py:185 over make_csv_dataset batches): batch i is copied in, scored and copied out
+ * on internal slot i % srs_num_slots(), so the PCIe copies of one batch overlap the kernel
+ * of another.  Synchronous; probs[i] (and logits[i] if `logits` != NULL) receive batch i.
+ * Host buffers should be pinned for the copies to overlap.  Not to be mixed concurrently
+ * with srs_predict_host_async on the same model. */
+int srs_predict_host_batches(srs_model* m, int32_t n_batches, const srs_batch* batches,
+                             float* const* probs, float* const* logits);
 
 /* Pipelined variant: enqueue on one of srs_num_slots() internal slots (each with
  * its own stream and device staging) and return; srs_wait_slot() blocks until that

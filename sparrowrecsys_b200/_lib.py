@@ -36,7 +36,7 @@ class SrsBatch(C.Structure):
 
 
 EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_destroy",
-           "srs_predict_device", "srs_predict_host", "srs_num_slots", "srs_predict_host_async",
+           "srs_predict_device", "srs_predict_host", "srs_predict_host_batches", "srs_num_slots", "srs_predict_host_async",
            "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
            "srs_model_kernel_name", "srs_launch_count", "srs_fill_uniform",
            "srs_cosine_scores_device", "srs_selftest_umma", "srs_debug_din_trace")
@@ -77,6 +77,9 @@ def load():
                                        C.c_void_p]
     lib.srs_predict_host.restype = C.c_int
     lib.srs_predict_host.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_void_p, C.c_void_p]
+    lib.srs_predict_host_batches.restype = C.c_int
+    lib.srs_predict_host_batches.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SrsBatch),
+                                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.srs_num_slots.restype = C.c_int
     lib.srs_predict_host_async.restype = C.c_int
     lib.srs_predict_host_async.argtypes = [C.c_void_p, C.c_int32, C.POINTER(SrsBatch), C.c_void_p,

@@ -51,12 +51,7 @@ constexpr int kSlots = 4;           // public pipelining slots; slot kSlots is p
 struct Slot {
   cudaStream_t stream = nullptr;
   int capacity = 0;                 // rows the device staging can hold
-  int32_t* d_movie = nullptr;
-  int32_t* d_user = nullptr;
-  int32_t* d_hist = nullptr;
-  int32_t* d_mg = nullptr;
-  int32_t* d_ug = nullptr;
-  float* d_num = nullptr;
+  uint8_t* d_block = nullptr;       // one allocation: [movie|user|hist|movie_genre|user_genre|numerics]
   float* d_probs = nullptr;
   float* d_logits = nullptr;
   int* h_err = nullptr;             // pinned mirror of the device error flag
@@ -670,6 +665,27 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
   return SRS_OK;
 }
 
+// Device staging of one batch is a single block in the canonical packed order
+//   [movie_id B | user_id B | hist B*hc | movie_genre B*3 | user_genre B*5 | numerics B*7] x 4 bytes;
+// a host batch laid out the same way (arrays back to back) goes over PCIe as ONE copy.
+struct PackedLayout {
+  size_t movie, user, hist, mg, ug, num, total;
+};
+PackedLayout packed_layout(const srs_model* m, size_t B) {
+  const int k = m->spec.kind;
+  const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
+  PackedLayout L{};
+  size_t off = 0;
+  L.movie = off; off += B * 4;
+  L.user = off; off += B * 4;
+  L.hist = off; off += B * (size_t)m->hist_cols * 4;
+  L.mg = off; off += dense_feats ? B * 3 * 4 : 0;
+  L.ug = off; off += dense_feats ? B * 5 * 4 : 0;
+  L.num = off; off += dense_feats ? B * 7 * 4 : 0;
+  L.total = off;
+  return L;
+}
+
 int ensure_slot(srs_model* m, Slot& s, int B) {
   if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   if (!s.h_err) {
@@ -678,23 +694,18 @@ int ensure_slot(srs_model* m, Slot& s, int B) {
   }
   if (B <= s.capacity) return SRS_OK;
   int cap = std::max(B, 1024);
-  cudaFree(s.d_movie); cudaFree(s.d_user); cudaFree(s.d_hist); cudaFree(s.d_mg); cudaFree(s.d_ug);
-  cudaFree(s.d_num); cudaFree(s.d_probs); cudaFree(s.d_logits);
+  cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits);
+  s.d_block = nullptr; s.d_probs = nullptr; s.d_logits = nullptr;
   s.capacity = 0;
-  const int hc = std::max(m->hist_cols, 1);
-  CUDA_TRY(cudaMalloc(&s.d_movie, (size_t)cap * 4));
-  CUDA_TRY(cudaMalloc(&s.d_user, (size_t)cap * 4));
-  CUDA_TRY(cudaMalloc(&s.d_hist, (size_t)cap * hc * 4));
-  CUDA_TRY(cudaMalloc(&s.d_mg, (size_t)cap * 3 * 4));
-  CUDA_TRY(cudaMalloc(&s.d_ug, (size_t)cap * 5 * 4));
-  CUDA_TRY(cudaMalloc(&s.d_num, (size_t)cap * 7 * 4));
+  CUDA_TRY(cudaMalloc(&s.d_block, packed_layout(m, (size_t)cap).total + 256));
   CUDA_TRY(cudaMalloc(&s.d_probs, (size_t)cap * 4));
   CUDA_TRY(cudaMalloc(&s.d_logits, (size_t)cap * 4));
   s.capacity = cap;
   return SRS_OK;
 }
 
-int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits) {
+int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits,
+                 bool copy_err = true) {
   int rc = check_batch(m, b);
   if (rc != SRS_OK) return rc;
   if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
@@ -705,31 +716,51 @@ int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float*
   const size_t B = (size_t)b->B;
   const int k = m->spec.kind;
   const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
-  CUDA_TRY(cudaMemcpyAsync(s.d_movie, b->movie_id, B * 4, cudaMemcpyHostToDevice, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.d_user, b->user_id, B * 4, cudaMemcpyHostToDevice, s.stream));
-  if (m->hist_cols > 0) {
-    if (b->hist_stride == m->hist_cols) {
-      CUDA_TRY(cudaMemcpyAsync(s.d_hist, b->hist, B * m->hist_cols * 4, cudaMemcpyHostToDevice, s.stream));
-    } else {
-      CUDA_TRY(cudaMemcpy2DAsync(s.d_hist, (size_t)m->hist_cols * 4, b->hist, (size_t)b->hist_stride * 4,
-                                 (size_t)m->hist_cols * 4, B, cudaMemcpyHostToDevice, s.stream));
+  const PackedLayout L = packed_layout(m, B);
+  uint8_t* d = s.d_block;
+  const uint8_t* h0 = reinterpret_cast<const uint8_t*>(b->movie_id);
+  bool packed = reinterpret_cast<const uint8_t*>(b->user_id) == h0 + L.user;
+  if (m->hist_cols > 0)
+    packed = packed && b->hist_stride == m->hist_cols &&
+             reinterpret_cast<const uint8_t*>(b->hist) == h0 + L.hist;
+  if (dense_feats)
+    packed = packed && reinterpret_cast<const uint8_t*>(b->movie_genre) == h0 + L.mg &&
+             reinterpret_cast<const uint8_t*>(b->user_genre) == h0 + L.ug &&
+             reinterpret_cast<const uint8_t*>(b->numerics) == h0 + L.num;
+  if (packed) {
+    CUDA_TRY(cudaMemcpyAsync(d, h0, L.total, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(d + L.movie, b->movie_id, B * 4, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(d + L.user, b->user_id, B * 4, cudaMemcpyHostToDevice, s.stream));
+    if (m->hist_cols > 0) {
+      if (b->hist_stride == m->hist_cols) {
+        CUDA_TRY(cudaMemcpyAsync(d + L.hist, b->hist, B * m->hist_cols * 4, cudaMemcpyHostToDevice, s.stream));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(d + L.hist, (size_t)m->hist_cols * 4, b->hist, (size_t)b->hist_stride * 4,
+                                   (size_t)m->hist_cols * 4, B, cudaMemcpyHostToDevice, s.stream));
+      }
     }
-  }
-  if (dense_feats) {
-    CUDA_TRY(cudaMemcpyAsync(s.d_mg, b->movie_genre, B * 3 * 4, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.d_ug, b->user_genre, B * 5 * 4, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.d_num, b->numerics, B * 7 * 4, cudaMemcpyHostToDevice, s.stream));
+    if (dense_feats) {
+      CUDA_TRY(cudaMemcpyAsync(d + L.mg, b->movie_genre, B * 3 * 4, cudaMemcpyHostToDevice, s.stream));
+      CUDA_TRY(cudaMemcpyAsync(d + L.ug, b->user_genre, B * 5 * 4, cudaMemcpyHostToDevice, s.stream));
+      CUDA_TRY(cudaMemcpyAsync(d + L.num, b->numerics, B * 7 * 4, cudaMemcpyHostToDevice, s.stream));
+    }
   }
   BatchView v{};
   v.B = b->B; v.hist_stride = m->hist_cols;
-  v.movie_id = s.d_movie; v.user_id = s.d_user; v.hist = s.d_hist;
-  v.movie_genre = s.d_mg; v.user_genre = s.d_ug; v.numerics = s.d_num;
+  v.movie_id = reinterpret_cast<const int32_t*>(d + L.movie);
+  v.user_id = reinterpret_cast<const int32_t*>(d + L.user);
+  v.hist = reinterpret_cast<const int32_t*>(d + L.hist);
+  v.movie_genre = reinterpret_cast<const int32_t*>(d + L.mg);
+  v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
+  v.numerics = reinterpret_cast<const float*>(d + L.num);
   v.probs = s.d_probs; v.logits = logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
   rc = launch(m, v, s.stream);
   if (rc != SRS_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (logits) CUDA_TRY(cudaMemcpyAsync(logits, s.d_logits, B * 4, cudaMemcpyDeviceToHost, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  if (copy_err)
+    CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   return SRS_OK;
 }
 
@@ -837,8 +868,7 @@ void srs_model_destroy(srs_model* m) {
   cudaSetDevice(m->device);
   for (Slot& s : m->slots) {
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-    cudaFree(s.d_movie); cudaFree(s.d_user); cudaFree(s.d_hist); cudaFree(s.d_mg); cudaFree(s.d_ug);
-    cudaFree(s.d_num); cudaFree(s.d_probs); cudaFree(s.d_logits);
+    cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits);
     if (s.h_err) cudaFreeHost(s.h_err);
   }
   for (void* p : m->owned) cudaFree(p);
@@ -867,6 +897,34 @@ int srs_predict_host(srs_model* m, const srs_batch* b, float* probs, float* logi
   int rc = enqueue_host(m, s, b, probs, logits);
   if (rc != SRS_OK) return rc;
   return wait_slot(m, s);
+}
+
+int srs_predict_host_batches(srs_model* m, int32_t n, const srs_batch* batches,
+                             float* const* probs, float* const* logits) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (n < 0 || (n > 0 && (!batches || !probs))) return fail(SRS_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  CUDA_TRY(cudaSetDevice(m->device));
+  int rc = SRS_OK;
+  for (int i = 0; i < n && rc == SRS_OK; ++i) {
+    Slot& s = m->slots[i % kSlots];
+    if (i >= kSlots) CUDA_TRY(cudaStreamSynchronize(s.stream));     // slot's previous batch is out
+    rc = enqueue_host(m, s, &batches[i], probs[i], logits ? logits[i] : nullptr, false);
+  }
+  for (int k = 0; k < kSlots; ++k)
+    if (m->slots[k].stream) {
+      cudaError_t e = cudaStreamSynchronize(m->slots[k].stream);
+      if (e != cudaSuccess && rc == SRS_OK)
+        rc = fail(SRS_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+    }
+  if (rc != SRS_OK) return rc;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+    return fail(SRS_ERR_RANGE, "an id in a batch was outside its vocabulary");
+  }
+  return SRS_OK;
 }
 
 int srs_num_slots(void) { return kSlots; }

@@ -117,32 +117,52 @@ class EncodedBatch:
                             s(self.movie_genre), s(self.user_genre), s(self.numerics))
 
 
-def encode_batch(spec: ModelSpec, features: Mapping[str, object]) -> EncodedBatch:
+def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=None) -> EncodedBatch:
     """Feature dict (keys as in the Keras `inputs` dicts, e.g. DIN.py:34-59) ->
     `EncodedBatch`.  Unknown keys are ignored (the reference datasets carry
     `rating`, `timestamp`, ... which no model reads); a missing required key raises
-    `KeyError`; an out-of-range id raises `ValueError`."""
+    `KeyError`; an out-of-range id raises `ValueError`.  `arena_alloc(nbytes)` may supply
+    the backing uint8 buffer (e.g. pinned memory); the arrays are views into it, back to
+    back in the packed order the library recognises."""
     m = spec.model
-    movie_id = _as_ids(features, "movieId", spec.n_movies, "movie id")
-    user_id = _as_ids(features, "userId", spec.n_users, "user id")
-    B = movie_id.shape[0]
-    if user_id.shape[0] != B:
+    movie_id_in = _as_ids(features, "movieId", spec.n_movies, "movie id")
+    user_id_in = _as_ids(features, "userId", spec.n_users, "user id")
+    B = movie_id_in.shape[0]
+    if user_id_in.shape[0] != B:
         raise ValueError("userId and movieId differ in length")
     hist = movie_genre = user_genre = numerics = None
+    # one arena in the packed order of include/srs_ctr.h (srs_batch): the library then moves
+    # the whole batch host->device with a single copy
+    hist_keys = history_keys(spec.hist_len) if m == "din" else (["userRatedMovie1"] if m == "widendeep" else [])
+    dense = m not in ("neuralcf", "twotowers")
+    words = B * (2 + len(hist_keys) + (15 if dense else 0))
+    arena = arena_alloc(words * 4) if arena_alloc is not None else np.empty(words * 4, np.uint8)
+    cursor = [0]
 
-    if m in ("din", "widendeep"):
-        keys = history_keys(spec.hist_len) if m == "din" else ["userRatedMovie1"]
-        hist = np.empty((B, len(keys)), dtype=np.int32)
-        for p, k in enumerate(keys):
+    def carve(shape, dtype):
+        n = int(np.prod(shape)) * 4
+        view = arena[cursor[0]:cursor[0] + n].view(dtype).reshape(shape)
+        cursor[0] += n
+        return view
+
+    movie_id = carve((B,), np.int32)
+    movie_id[:] = movie_id_in
+    user_id = carve((B,), np.int32)
+    user_id[:] = user_id_in
+    if hist_keys:
+        hist = carve((B, len(hist_keys)), np.int32)
+        for p, k in enumerate(hist_keys):
             hist[:, p] = _as_ids(features, k, spec.n_movies, "history movie id")
-    if m not in ("neuralcf", "twotowers"):
-        numerics = np.empty((B, len(NUMERIC_KEYS)), dtype=np.float32)
+    if dense:
+        movie_genre = carve((B, 3), np.int32)
+        user_genre = carve((B, 5), np.int32)
+        numerics = carve((B, len(NUMERIC_KEYS)), np.float32)
+        movie_genre[:] = -1
+        user_genre[:] = -1
         for j, k in enumerate(NUMERIC_KEYS):
             numerics[:, j] = _as_1d(features, k).astype(np.float32)   # numeric_column casts
         n_mg = 3 if m in ("embeddingmlp", "widendeep") else 1
         n_ug = 5 if m in ("embeddingmlp", "widendeep") else 1
-        movie_genre = np.full((B, 3), -1, dtype=np.int32)
-        user_genre = np.full((B, 5), -1, dtype=np.int32)
         for j in range(n_mg):
             movie_genre[:, j] = genre_to_index(_as_1d(features, MOVIE_GENRE_KEYS[j]))
         for j in range(n_ug):

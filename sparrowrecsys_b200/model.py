@@ -177,12 +177,27 @@ class CTRModel:
         n = enc.B
         probs = np.empty(n, np.float32)
         logits = np.empty(n, np.float32) if want_logits else None
-        step = n if not batch_size else int(batch_size)
-        for lo in range(0, n, max(step, 1)):
-            hi = min(n, lo + step)
-            self.predict_encoded(enc.slice(lo, hi), probs[lo:hi],
-                                 None if logits is None else logits[lo:hi])
+        step = n if not batch_size else max(int(batch_size), 1)
+        if n <= step:
+            self.predict_encoded(enc, probs, logits)
+        else:   # the Keras predict loop over dataset batches -> one pipelined library call
+            bounds = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+            self.predict_batches([enc.slice(lo, hi) for lo, hi in bounds],
+                                 [probs[lo:hi] for lo, hi in bounds],
+                                 None if logits is None else [logits[lo:hi] for lo, hi in bounds])
         return probs.reshape(n, 1), (None if logits is None else logits.reshape(n, 1))
+
+    def predict_batches(self, encs, probs_list, logits_list=None):
+        """`srs_predict_host_batches`: score a list of encoded batches, H2D / kernel / D2H of
+        successive batches overlapped over the library's slots."""
+        n = len(encs)
+        keep = []
+        structs = (_lib.SrsBatch * n)(*[_host_struct(e, keep) for e in encs])
+        pp = (C.c_void_p * n)(*[p.ctypes.data for p in probs_list])
+        lp = None
+        if logits_list is not None:
+            lp = (C.c_void_p * n)(*[l.ctypes.data for l in logits_list])
+        _lib.check(self._lib.srs_predict_host_batches(self._h, n, structs, pp, lp))
 
     def predict_encoded(self, enc: EncodedBatch, probs: np.ndarray,
                         logits: Optional[np.ndarray] = None) -> np.ndarray:

@@ -391,3 +391,28 @@ def test_din_tensor_core_large_magnitudes(din_impl):
     assert np.abs(zo).max() > 2.0
     assert np.abs(p - po).max() <= 1e-4, np.abs(p - po).max()     # the north_star target
     assert np.abs(z - zo).max() <= 1e-3 * max(1.0, np.abs(zo).max())
+
+
+def test_predict_batches_packed_and_unpacked_agree():
+    """`srs_predict_host_batches`: packed arenas (one H2D copy) and scattered arrays (one copy
+    per array) give the same scores as the single-batch call; Keras-style batched predict."""
+    spec = default_spec("din", emb_dim=32, hist_len=20, n_movies=3000, n_users=2000)
+    W = init_weights(spec, 12)
+    feats = synthetic_features(spec, 5000, seed=12)
+    with _model(spec, W) as m:
+        ref = m.predict(feats)[:, 0]
+        encs, outs = [], []
+        for lo in range(0, 5000, 700):
+            sub = {k: v[lo:lo + 700] for k, v in feats.items()}
+            encs.append(encode_batch(spec, sub))                    # packed arena
+            outs.append(np.empty(encs[-1].B, np.float32))
+        m.predict_batches(encs, outs)
+        assert np.array_equal(np.concatenate(outs), ref)
+        scattered = []
+        for e in encs:                                              # break the adjacency
+            scattered.append(type(e)(e.B, e.movie_id.copy(), e.user_id.copy(), e.hist.copy(),
+                                     e.movie_genre.copy(), e.user_genre.copy(), e.numerics.copy()))
+        outs2 = [np.empty(e.B, np.float32) for e in scattered]
+        m.predict_batches(scattered, outs2)
+        assert np.array_equal(np.concatenate(outs2), ref)
+        assert np.array_equal(m.predict(feats, batch_size=12 * 50)[:, 0], ref)
