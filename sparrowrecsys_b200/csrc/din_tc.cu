@@ -19,18 +19,18 @@
 // oracle in tests/test_gpu_parity.py.
 //
 // Work decomposition: one persistent CTA per SM holds the weight images in shared memory
-// (bulk-copied once per launch) and runs four independent warpgroups ("workers"), each
-// with 128 tensor-memory columns and 13 KB of scratch.  A worker owns groups of G (8 or 16)
-// consecutive rows; the four workers interleave on the SM, which is what hides the
-// latencies of the serial per-group chain:
+// (bulk-copied once per launch) and owns super-groups of 32 consecutive rows.  Its four
+// warpgroups ("workers", 128 tensor-memory columns each) take 8 rows apiece through
 //   phase 0  candidate/user/genre row gathers (kept in registers), cst_b
 //   phase 1  per tile of 4 chunks x 32 positions, thread = (row, position) pair: its
 //            history row arrives by 8 x 128-bit loads prefetched one tile ahead, A operand
 //            -> TMEM, 12 MMAs, read back 32 accumulators, PReLU / sigmoid gate,
 //            butterfly-pool w_t * h_t over the chunk
+// and then run the top MLP together, once per super-group, with the 32 rows as the MMA N:
 //   phase 2  X operand tile (bf16 hi/lo, SW128) <- pooled + side rows, layer-1 MMAs (36),
 //            epilogue (bias, numerics, PReLU) -> H1 operand tile, layer-2 MMAs (16),
 //            epilogue, sigmoid, scores out.
+// The ids of the next super-group are requested from HBM before phase 2 of the current one.
 #include <climits>
 
 #include "kernels.h"
@@ -40,14 +40,16 @@ namespace srs {
 using namespace umma;
 
 constexpr int kTcWG = 4;                 // warpgroups (workers) per CTA
+constexpr int kTcG = 8;                  // rows per worker per super-group
+constexpr int kTcSG = kTcWG * kTcG;      // rows per super-group = N of the top-MLP MMAs
 constexpr int kTcMaxCPR = 4;             // chunks (of 32 positions) per row: T <= 128
 constexpr int kNoPair = INT_MIN;         // sentinel: this thread has no (row, position) pair
 
 // tensor-memory map of one worker (128 columns)
 constexpr uint32_t TM_A_HI = 0;          // 32 cols: bf16 pairs of [h | h*c], hi halves
 constexpr uint32_t TM_A_LO = 32;         // 32 cols: lo halves
-constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators; top layer 1 (16 cols)
-constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling; top layer 2 (16 cols)
+constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators; worker 0: top layer 1
+constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling; worker 0: top layer 2
 
 // shared-memory image (bulk-copied from global; built by build_din_tc in model.cu)
 constexpr uint32_t IMG_AUB_HI = 0;                       // [32 units][64 k] bf16, SW128
@@ -55,39 +57,41 @@ constexpr uint32_t IMG_AUB_LO = 4096;
 constexpr uint32_t IMG_W1_HI = 8192;                     // 3 K blocks x [128 units][64 k]
 constexpr uint32_t IMG_W1_LO = IMG_W1_HI + 3 * 16384;
 constexpr uint32_t IMG_W2 = IMG_W1_LO + 3 * 16384;       // 2 K blocks x [64 hi | 64 lo units][64 k]
-constexpr uint32_t IMG_ALPHAW = IMG_W2 + 2 * 16384;      // f32 [32 units][TP] alpha*wout, TP = CPR*32
-// per-worker scratch: phases 0/1 and phase 2 overlay the same 12 KB
-constexpr uint32_t WS_CAND = 0;                          // f32 [16][32]              (phase 0/1)
-constexpr uint32_t WS_CST = 2048;                        // f32 [16][32]              (phase 0/1)
-constexpr uint32_t WS_PART = 4096;                       // f32 [16][4][32] partials  (phase 1)
-constexpr uint32_t WS_XB_HI = 0;                         // 3 K blocks x [16 rows][64 k] bf16 (phase 2)
-constexpr uint32_t WS_XB_LO = 6144;
-constexpr uint32_t WS_H1_HI = 0;                         // 2 K blocks x [16 rows][64 k]; after layer 1
-constexpr uint32_t WS_H1_LO = 4096;
-constexpr uint32_t WS_RED = 8192;                        // f32 [64][16]; after layer 1
-constexpr uint32_t WS_NUMS = 12288;                      // f32 [16][8]
-constexpr uint32_t WS_ZP = 12800;                        // f32 [8][16] final partial sums
-constexpr uint32_t WS_BYTES = 13312;
+constexpr uint32_t IMG_PQ = IMG_W2 + 2 * 16384;          // f32 P[32 units][TP], then Q[32][TP]; TP = CPR*32
+// CTA scratch (28 KB).  Phase 0/1 view: worker w owns 6 KB at w*6144; phase 2 overlays all 24 KB.
+constexpr uint32_t WS_W_STRIDE = 6144;
+constexpr uint32_t WS_CAND = 0;                          // f32 [8][32]        (worker, phase 0/1)
+constexpr uint32_t WS_CST = 1024;                        // f32 [8][32]        (worker, phase 0/1)
+constexpr uint32_t WS_PART = 2048;                       // f32 [8][4][32]     (worker, phase 1)
+constexpr uint32_t WS_XB_HI = 0;                         // 3 K blocks x [32 rows][64 k] bf16 (phase 2)
+constexpr uint32_t WS_XB_LO = 12288;
+constexpr uint32_t WS_H1_HI = 0;                         // 2 K blocks x [32 rows][64 k]; after layer 1
+constexpr uint32_t WS_H1_LO = 8192;
+constexpr uint32_t WS_RED = 16384;                       // f32 [64][32]; after layer 1
+constexpr uint32_t WS_NUMS = 24576;                      // f32 [32][8]
+constexpr uint32_t WS_ZP = 25600;                        // f32 [16][32] final partial sums
+constexpr uint32_t WS_BYTES = 28672;
 
-// Phase timestamps (SM clock) of worker 0 of CTA 0, written when DinTcParams::trace != 0:
+// Phase timestamps (SM clock) of thread 0 of CTA 0, written when DinTcParams::trace != 0:
 // [0] kernel entry, [1] prologue done, [2] phase 0 done, [3] weight image landed,
-// [4 + k] tile k read back and pooled, [30] top layer 1 done, [31] group done, [32] exit.
+// [4 + k] tile k read back and pooled, [30] top layer 1 done, [31] super-group done, [32] exit.
 __device__ unsigned long long g_din_tc_trace[40];
 #define TC_TRACE(slot)                                                             \
   do {                                                                             \
     if (p.trace && blockIdx.x == 0 && tid == 0) g_din_tc_trace[slot] = clock64();  \
   } while (0)
 
-__host__ __device__ inline uint32_t din_tc_image_bytes(int cpr) { return IMG_ALPHAW + 32u * cpr * 32u * 4u; }
+__host__ __device__ inline uint32_t din_tc_image_bytes(int cpr) { return IMG_PQ + 2u * 32u * cpr * 32u * 4u; }
 
 __device__ __forceinline__ void wg_sync(int wg) {
   asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
 }
 
-// write 4 consecutive K elements (col % 4 == 0) of row rs into a bf16 hi/lo SW128 operand
-__device__ __forceinline__ void store_x4(uint8_t* hi, uint8_t* lo, int block, int rs, int col,
-                                         float4 v) {
-  const uint32_t off = block * 2048u + sw128_offset(rs, col >> 3) + ((col & 4) ? 8u : 0u);
+// write 4 consecutive K elements (col % 4 == 0) of row `row` into a bf16 hi/lo SW128 operand
+// whose K blocks are `block_bytes` apart
+__device__ __forceinline__ void store_x4(uint8_t* hi, uint8_t* lo, uint32_t block_bytes, int block,
+                                         int row, int col, float4 v) {
+  const uint32_t off = block * block_bytes + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
   const Split2 s0 = split_pack(v.x, v.y), s1 = split_pack(v.z, v.w);
   *reinterpret_cast<uint2*>(hi + off) = make_uint2(s0.hi, s1.hi);
   *reinterpret_cast<uint2*>(lo + off) = make_uint2(s0.lo, s1.lo);
@@ -97,39 +101,93 @@ __device__ __forceinline__ int f32_roundtrip_id(int id) {   // DIN.py:95,125: id
   return __float2int_rz(__int2float_rn(id));
 }
 
+__device__ __forceinline__ int div_cpr(int ch, int cpr) {   // ch < 32, cpr in 1..4
+  return cpr == 1 ? ch : cpr == 2 ? ch >> 1 : cpr == 4 ? ch >> 2 : (ch * 43) >> 7;
+}
+
+// values a thread requests from HBM for a super-group before it needs them
+struct GroupLoads {
+  int cid_raw, uid_raw, ug, mg;     // side ids of row (wg*8 + tw/8); kNoPair when no such row
+  float nv;                         // numeric tw%8 of that row
+  int raw0, raw1;                   // history ids of this thread's pair in tiles 0 and 1
+};
+
 __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_constant__ DinTcParams p,
                                                                  BatchView b) {
   extern __shared__ uint8_t raw[];
   __shared__ uint64_t wbar;                 // weight image landed
   __shared__ uint64_t mbar[kTcWG];          // per-worker "MMAs complete"
+  __shared__ uint64_t cbar;                 // CTA-wide "top-MLP MMAs complete"
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
   TC_TRACE(0);
   const int wg = tid >> 7, tw = tid & 127, warp_w = tw >> 5, lane = tw & 31;
+  const int srs = tw >> 3, sq = tw & 7;                 // side-feature role: row slot / float4 index
   uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* img = base;
   const uint32_t img_bytes = din_tc_image_bytes(p.CPR);
-  uint8_t* ws = base + ((img_bytes + 1023u) & ~1023u) + wg * WS_BYTES;
-  const float* alphaw = reinterpret_cast<const float*>(img + IMG_ALPHAW);
-  const int TP = p.CPR * 32;
+  uint8_t* cs_base = base + ((img_bytes + 1023u) & ~1023u);     // CTA scratch
+  uint8_t* ws = cs_base + wg * WS_W_STRIDE;                      // this worker's phase-0/1 view
+  const int CPR = p.CPR, T = p.T, TP = CPR * 32;
+  const float* Ptab = reinterpret_cast<const float*>(img + IMG_PQ);
+  const float* Qtab = Ptab + 32 * TP;
   float* cand = reinterpret_cast<float*>(ws + WS_CAND);
   float* cst = reinterpret_cast<float*>(ws + WS_CST);
   float* part = reinterpret_cast<float*>(ws + WS_PART);
-  float* nums = reinterpret_cast<float*>(ws + WS_NUMS);
+  float* nums = reinterpret_cast<float*>(cs_base + WS_NUMS);
+  const int n_tiles = 2 * CPR;                          // 8 rows * CPR chunks / 4 chunks per tile
+  const int n_sg = (b.B + kTcSG - 1) / kTcSG;
+
+  // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
+  auto pair_of = [&](int tile, int& rs, int& cq, int& t) {
+    const int ch = 4 * tile + warp_w;
+    rs = div_cpr(ch, CPR);
+    cq = ch - rs * CPR;
+    t = cq * 32 + lane;
+  };
+  // raw history id of this thread's pair (kNoPair if none); the value is not touched here so
+  // the load stays in flight until fix_id() a tile later
+  auto raw_id = [&](int row0, int tile) -> int {
+    if (tile >= n_tiles) return kNoPair;
+    int rs, cq, t;
+    pair_of(tile, rs, cq, t);
+    const int row = row0 + rs;
+    if (row >= b.B || t >= T) return kNoPair;
+    return __ldg(b.hist + (size_t)row * b.hist_stride + t);
+  };
+  auto issue_loads = [&](int sg) -> GroupLoads {
+    GroupLoads L;
+    L.cid_raw = L.uid_raw = kNoPair; L.ug = L.mg = -1; L.nv = 0.f; L.raw0 = L.raw1 = kNoPair;
+    if (sg >= n_sg) return L;
+    const int row0 = sg * kTcSG + wg * kTcG;
+    const int row = row0 + srs;
+    if (srs < kTcG && row < b.B) {
+      L.cid_raw = __ldg(b.movie_id + row);
+      L.uid_raw = __ldg(b.user_id + row);
+      L.ug = __ldg(b.user_genre + row * 5);
+      L.mg = __ldg(b.movie_genre + row * 3);
+      if (sq < kNumNumerics) L.nv = __ldg(b.numerics + row * kNumNumerics + sq);
+    }
+    L.raw0 = raw_id(row0, 0);
+    L.raw1 = raw_id(row0, 1);
+    return L;
+  };
+  GroupLoads pre = issue_loads(blockIdx.x);             // ids come from HBM: start before the prologue
 
   // ---- prologue ---------------------------------------------------------------------
   if (tid < 32) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&wbar, 1);
+    mbar_init(&cbar, 1);
     for (int i = 0; i < kTcWG; ++i) mbar_init(&mbar[i], 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(&wbar, img_bytes);
-    // activation-unit operand + alpha table first (needed first), then the top-MLP images
+    // activation-unit operand + P/Q tables first (needed first), then the top-MLP images
     bulk_g2s(img, p.image, 8192, &wbar);
-    bulk_g2s(img + IMG_ALPHAW, p.image + IMG_ALPHAW, img_bytes - IMG_ALPHAW, &wbar);
-    for (uint32_t off = 8192; off < IMG_ALPHAW; off += 32768u)
-      bulk_g2s(img + off, p.image + off, min(32768u, IMG_ALPHAW - off), &wbar);
+    bulk_g2s(img + IMG_PQ, p.image + IMG_PQ, img_bytes - IMG_PQ, &wbar);
+    for (uint32_t off = 8192; off < IMG_PQ; off += 32768u)
+      bulk_g2s(img + off, p.image + off, min(32768u, IMG_PQ - off), &wbar);
   }
   tc_fence_before();
   __syncthreads();
@@ -138,68 +196,40 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   const uint32_t tbase = tmem_slot + wg * 128;          // this worker's 128 TMEM columns
   const uint32_t lane_base = (uint32_t)(warp_w * 32) << 16;
   uint64_t* my_bar = &mbar[wg];
-  uint32_t phase = 0;
+  uint32_t phase = 0, cphase = 0;
   bool weights_ready = false;
 
-  const uint32_t idesc_au = idesc_bf16(128, 32), idesc_top = idesc_bf16(128, 16);
-  const uint32_t s_img = smem_u32(img), s_ws = smem_u32(ws);
+  const uint32_t idesc_au = idesc_bf16(128, 32), idesc_top = idesc_bf16(128, kTcSG);
+  const uint32_t s_img = smem_u32(img), s_cs = smem_u32(cs_base);
 
-  const int G = p.G;                                    // rows per group: 8 or 16
-  const int n_groups = (b.B + G - 1) / G;
-  const int n_workers = gridDim.x * kTcWG;
-  const int CPR = p.CPR, T = p.T;
-  const int n_tiles = (G * CPR) >> 2;                   // G rows * CPR chunks / 4 chunks per tile
+  auto fix_id = [&](int raw_v) -> int {
+    if (raw_v == kNoPair) return -1;
+    return checked_id(f32_roundtrip_id(raw_v), p.n_movies, b.err_flag);
+  };
+  auto load_row = [&](int id, float4 (&h)[8]) {
+    if (id >= 0) {
+      const float* src = p.movie + (size_t)id * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = ldg4(src + 4 * q);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
 
-  for (int g = blockIdx.x * kTcWG + wg; g < n_groups; g += n_workers) {
-    const int row0 = g * G;
-    // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
-    auto pair_of = [&](int tile, int& rs, int& cq, int& t) {
-      const int ch = 4 * tile + warp_w;
-      rs = ch / CPR;
-      cq = ch - rs * CPR;
-      t = cq * 32 + lane;
-    };
-    // raw history id of this thread's pair in `tile` (kNoPair if none); the value is not
-    // touched here so the load stays in flight until fix_id() a tile later
-    auto raw_id = [&](int tile) -> int {
-      if (tile >= n_tiles) return kNoPair;
-      int rs, cq, t;
-      pair_of(tile, rs, cq, t);
-      const int row = row0 + rs;
-      if (row >= b.B || t >= T) return kNoPair;
-      return __ldg(b.hist + (size_t)row * b.hist_stride + t);
-    };
-    auto fix_id = [&](int raw) -> int {
-      if (raw == kNoPair) return -1;
-      return checked_id(f32_roundtrip_id(raw), p.n_movies, b.err_flag);
-    };
-    auto load_row = [&](int id, float4 (&h)[8]) {
-      if (id >= 0) {
-        const float* src = p.movie + (size_t)id * 32;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = ldg4(src + 4 * q);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    int raw0 = raw_id(0), raw1 = raw_id(1);             // ids come from HBM: start them now
+  for (int sg = blockIdx.x; sg < n_sg; sg += gridDim.x) {
+    const int row0 = sg * kTcSG + wg * kTcG;            // this worker's first row
+    int raw1 = pre.raw1;
+    int raw0 = raw_id(row0, 2);                          // raw1 = tile 1, raw0 = tile 2
 
     // ================= phase 0: side gathers (registers), candidate rows, cst ============
-    // thread (rs = tw / 8, q = tw % 8) owns floats [4q, 4q+4) of the side rows of row rs
-    const int srs = tw >> 3, sq = tw & 7;
     float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), ug4 = u4, mg4 = u4;
-    {
-      const int row = row0 + srs;
-      const bool vr = srs < G && row < b.B;
+    if (srs < kTcG) {
       float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float nv = 0.f;
-      if (vr) {
-        const int cid_raw = __ldg(b.movie_id + row), uid_raw = __ldg(b.user_id + row);
-        int ug = __ldg(b.user_genre + row * 5), mg = __ldg(b.movie_genre + row * 3);
-        if (sq < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + sq);
-        const int cid = checked_id(f32_roundtrip_id(cid_raw), p.n_movies, b.err_flag);
-        const int uid = checked_id(uid_raw, p.n_users, b.err_flag);
+      if (pre.cid_raw != kNoPair) {
+        const int cid = checked_id(f32_roundtrip_id(pre.cid_raw), p.n_movies, b.err_flag);
+        const int uid = checked_id(pre.uid_raw, p.n_users, b.err_flag);
+        int ug = pre.ug, mg = pre.mg;
         c4 = ldg4(p.movie + (size_t)cid * 32 + 4 * sq);
         u4 = ldg4(p.user + (size_t)uid * 32 + 4 * sq);
         if (ug >= p.n_genres) { atomicExch(b.err_flag, 1); ug = -1; }
@@ -208,30 +238,26 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         if (mg >= 0) mg4 = ldg4(p.mgenre + mg * 32 + 4 * sq);
       }
       *reinterpret_cast<float4*>(cand + srs * 32 + 4 * sq) = c4;
-      nums[srs * 8 + sq] = nv;
+      nums[(wg * kTcG + srs) * 8 + sq] = pre.nv;
     }
     float4 hn[8];                                        // history row of the next tile to build
     bool valid_nxt;
     {
-      const int id0 = fix_id(raw0);
+      const int id0 = fix_id(pre.raw0);
       valid_nxt = id0 >= 0;
       load_row(id0, hn);
-      raw0 = raw_id(2);                                  // raw1 = tile 1, raw0 = tile 2
     }
     wg_sync(wg);
-    {  // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]
-      float acc[4];
-      const float ab = __ldg(p.au_b + lane);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = ab;
+    {  // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4
+      float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
 #pragma unroll 8
       for (int e = 0; e < 32; ++e) {
         const float wc = __ldg(p.au_wc + e * 32 + lane);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(cand[(warp_w + 4 * i) * 32 + e], wc, acc[i]);
+        acc0 = fmaf(cand[warp_w * 32 + e], wc, acc0);
+        acc1 = fmaf(cand[(warp_w + 4) * 32 + e], wc, acc1);
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cst[(warp_w + 4 * i) * 32 + lane] = acc[i];
+      cst[warp_w * 32 + lane] = acc0;
+      cst[(warp_w + 4) * 32 + lane] = acc1;
     }
     wg_sync(wg);
     TC_TRACE(2);
@@ -296,7 +322,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         valid_nxt = idn >= 0;
         load_row(tile + 1 < n_tiles ? idn : -1, hn);
         raw1 = raw0;
-        raw0 = raw_id(tile + 3);
+        raw0 = raw_id(row0, tile + 3);
       }
       mbar_wait(my_bar, phase);
       phase ^= 1;
@@ -305,24 +331,26 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       uint32_t d[32];
       tmem_ld32(tbase + TM_D + lane_base, d);
       tmem_ld_wait();
-      // ---- epilogue: + cst, PReLU (alpha per position), Dense(1), sigmoid gate
+      // ---- epilogue: + cst, PReLU (alpha per position) and Dense(1) folded into two tables
+      //      sum_j wout_j max(v,0) + alpha_tj wout_j min(v,0) = sum_j v P_tj + |v| Q_tj
       float s0 = p.au_bout, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       {
         const float* cs = cst + rs * 32;
-        const float* aw = alphaw + t;
+        const float* pt = Ptab + t;
+        const float* qt = Qtab + t;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
           const float v0 = __uint_as_float(d[j]) + c4.x, v1 = __uint_as_float(d[j + 1]) + c4.y;
           const float v2 = __uint_as_float(d[j + 2]) + c4.z, v3 = __uint_as_float(d[j + 3]) + c4.w;
-          s0 = fmaf(fmaxf(v0, 0.f), p.au_wout[j], s0);
-          s1 = fmaf(fmaxf(v1, 0.f), p.au_wout[j + 1], s1);
-          s2 = fmaf(fmaxf(v2, 0.f), p.au_wout[j + 2], s2);
-          s3 = fmaf(fmaxf(v3, 0.f), p.au_wout[j + 3], s3);
-          s0 = fmaf(fminf(v0, 0.f), aw[j * TP], s0);
-          s1 = fmaf(fminf(v1, 0.f), aw[(j + 1) * TP], s1);
-          s2 = fmaf(fminf(v2, 0.f), aw[(j + 2) * TP], s2);
-          s3 = fmaf(fminf(v3, 0.f), aw[(j + 3) * TP], s3);
+          s0 = fmaf(v0, pt[j * TP], s0);
+          s1 = fmaf(v1, pt[(j + 1) * TP], s1);
+          s2 = fmaf(v2, pt[(j + 2) * TP], s2);
+          s3 = fmaf(v3, pt[(j + 3) * TP], s3);
+          s0 = fmaf(fabsf(v0), qt[j * TP], s0);
+          s1 = fmaf(fabsf(v1), qt[(j + 1) * TP], s1);
+          s2 = fmaf(fabsf(v2), qt[(j + 2) * TP], s2);
+          s3 = fmaf(fabsf(v3), qt[(j + 3) * TP], s3);
         }
       }
       const float s = (s0 + s1) + (s2 + s3);
@@ -348,144 +376,150 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     }
     wg_sync(wg);
 
-    // ================= phase 2: top MLP on the group's rows ================================
-    {  // pooled and candidate leave the phase-1 scratch before the X operand overlays it
-      float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = 0; c < (srs < G ? CPR : 0); ++c) {
+    // ================= phase 2: top MLP on the super-group's 32 rows, whole CTA ===========
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f), c4s = pl;
+    if (srs < kTcG) {   // pooled and candidate leave the phase-1 scratch before the X operand overlays it
+      for (int c = 0; c < CPR; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(part + (srs * kTcMaxCPR + c) * 32 + 4 * sq);
         pl.x += v.x; pl.y += v.y; pl.z += v.z; pl.w += v.w;
       }
-      const float4 c4 = *reinterpret_cast<const float4*>(cand + srs * 32 + 4 * sq);
-      wg_sync(wg);
-      uint8_t* xh = ws + WS_XB_HI;
-      uint8_t* xl = ws + WS_XB_LO;
-      store_x4(xh, xl, 0, srs, 4 * sq, ug4);           // K block 0: [userGenre1 | userId]
-      store_x4(xh, xl, 0, srs, 32 + 4 * sq, u4);
-      store_x4(xh, xl, 1, srs, 4 * sq, pl);            // K block 1: [pooled | candidate]
-      store_x4(xh, xl, 1, srs, 32 + 4 * sq, c4);
-      store_x4(xh, xl, 2, srs, 4 * sq, mg4);           // K block 2: [movieGenre1 | 0]
-      const uint32_t zoff = 2 * 2048u + sw128_offset(srs, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
+      c4s = *reinterpret_cast<const float4*>(cand + srs * 32 + 4 * sq);
+    }
+    pre = issue_loads(sg + gridDim.x);                   // next super-group's ids: request from HBM now
+    tc_fence_before();
+    __syncthreads();
+    if (srs < kTcG) {
+      uint8_t* xh = cs_base + WS_XB_HI;
+      uint8_t* xl = cs_base + WS_XB_LO;
+      const int xr = wg * kTcG + srs;                    // row slot in the super-group
+      store_x4(xh, xl, 4096, 0, xr, 4 * sq, ug4);        // K block 0: [userGenre1 | userId]
+      store_x4(xh, xl, 4096, 0, xr, 32 + 4 * sq, u4);
+      store_x4(xh, xl, 4096, 1, xr, 4 * sq, pl);         // K block 1: [pooled | candidate]
+      store_x4(xh, xl, 4096, 1, xr, 32 + 4 * sq, c4s);
+      store_x4(xh, xl, 4096, 2, xr, 4 * sq, mg4);        // K block 2: [movieGenre1 | 0]
+      const uint32_t zoff = 2 * 4096u + sw128_offset(xr, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
       *reinterpret_cast<uint2*>(xh + zoff) = make_uint2(0u, 0u);
       *reinterpret_cast<uint2*>(xl + zoff) = make_uint2(0u, 0u);
     }
     fence_async_smem();
     tc_fence_before();
-    wg_sync(wg);
-    if (tw == 0) {
+    __syncthreads();
+    const uint32_t tD1 = tmem_slot + TM_D, tD2 = tmem_slot + TM_HS;   // worker 0's columns
+    if (tid == 0) {
       tc_fence_after();
       uint32_t acc = 0;
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         const uint64_t ah = smem_desc_sw128(s_img + IMG_W1_HI + kb * 16384);
         const uint64_t al = smem_desc_sw128(s_img + IMG_W1_LO + kb * 16384);
-        const uint64_t xh = smem_desc_sw128(s_ws + WS_XB_HI + kb * 2048);
-        const uint64_t xl = smem_desc_sw128(s_ws + WS_XB_LO + kb * 2048);
+        const uint64_t xh = smem_desc_sw128(s_cs + WS_XB_HI + kb * 4096);
+        const uint64_t xl = smem_desc_sw128(s_cs + WS_XB_LO + kb * 4096);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tbase + TM_D, ah + 2 * ks, xh + 2 * ks, idesc_top, acc);
+          mma_ss(tD1, ah + 2 * ks, xh + 2 * ks, idesc_top, acc);
           acc = 1;
-          mma_ss(tbase + TM_D, al + 2 * ks, xh + 2 * ks, idesc_top, 1);
-          mma_ss(tbase + TM_D, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
+          mma_ss(tD1, al + 2 * ks, xh + 2 * ks, idesc_top, 1);
+          mma_ss(tD1, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(my_bar);
+      mma_commit(&cbar);
     }
     __syncwarp();
-    // this thread is unit `tw` of layer 1: its constants arrive while the MMAs run
+    // this thread is unit `tw` of layer 1 for rows 8*wg .. 8*wg+7: constants arrive while the MMAs run
     const float b1 = __ldg(p.b1 + tw), a1 = __ldg(p.a1 + tw);
     float w1n[kNumNumerics];
 #pragma unroll
     for (int n = 0; n < kNumNumerics; ++n) w1n[n] = __ldg(p.w1num + n * 128 + tw);
-    mbar_wait(my_bar, phase);
-    phase ^= 1;
+    mbar_wait(&cbar, cphase);
+    cphase ^= 1;
     __syncwarp();
     tc_fence_after();
     TC_TRACE(30);
     {
-      uint32_t d[16];
-      tmem_ld16(tbase + TM_D + lane_base, d);
+      uint32_t d[8];
+      tmem_ld8(tD1 + 8 * wg + lane_base, d);
       tmem_ld_wait();
-      // layer-1 epilogue for unit tw: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo),
-      // which overlays the X operand (its MMAs have completed)
-      const uint32_t koff = (uint32_t)(tw >> 6) * 2048u;
+      // layer-1 epilogue: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo), which
+      // overlays the X operand (its MMAs have completed)
+      const uint32_t koff = (uint32_t)(tw >> 6) * 4096u;
       const uint32_t chunk = (tw & 63) >> 3, within = (tw & 7) * 2;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float4 n0 = *reinterpret_cast<const float4*>(nums + r * 8);
-        const float4 n1 = *reinterpret_cast<const float4*>(nums + r * 8 + 4);
+      for (int r = 0; r < 8; ++r) {
+        const int xr = wg * kTcG + r;
+        const float4 n0 = *reinterpret_cast<const float4*>(nums + xr * 8);
+        const float4 n1 = *reinterpret_cast<const float4*>(nums + xr * 8 + 4);
         float v = __uint_as_float(d[r]) + b1;
         v = fmaf(n0.x, w1n[0], v); v = fmaf(n0.y, w1n[1], v); v = fmaf(n0.z, w1n[2], v);
         v = fmaf(n0.w, w1n[3], v); v = fmaf(n1.x, w1n[4], v); v = fmaf(n1.y, w1n[5], v);
         v = fmaf(n1.z, w1n[6], v);
         v = v > 0.f ? v : a1 * v;
-        const uint32_t off = koff + sw128_offset(r, chunk) + within;
+        const uint32_t off = koff + sw128_offset(xr, chunk) + within;
         const __nv_bfloat16 vh = __float2bfloat16_rn(v);
-        *reinterpret_cast<__nv_bfloat16*>(ws + WS_H1_HI + off) = vh;
-        *reinterpret_cast<__nv_bfloat16*>(ws + WS_H1_LO + off) = __float2bfloat16_rn(v - __bfloat162float(vh));
+        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1_HI + off) = vh;
+        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1_LO + off) = __float2bfloat16_rn(v - __bfloat162float(vh));
       }
     }
     fence_async_smem();
     tc_fence_before();
-    wg_sync(wg);
-    if (tw == 0) {
+    __syncthreads();
+    if (tid == 0) {
       tc_fence_after();
       uint32_t acc = 0;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         const uint64_t a = smem_desc_sw128(s_img + IMG_W2 + kb * 16384);
-        const uint64_t hh = smem_desc_sw128(s_ws + WS_H1_HI + kb * 2048);
-        const uint64_t hl = smem_desc_sw128(s_ws + WS_H1_LO + kb * 2048);
+        const uint64_t hh = smem_desc_sw128(s_cs + WS_H1_HI + kb * 4096);
+        const uint64_t hl = smem_desc_sw128(s_cs + WS_H1_LO + kb * 4096);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tbase + TM_HS, a + 2 * ks, hh + 2 * ks, idesc_top, acc);
+          mma_ss(tD2, a + 2 * ks, hh + 2 * ks, idesc_top, acc);
           acc = 1;
-          mma_ss(tbase + TM_HS, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
+          mma_ss(tD2, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
         }
       }
-      mma_commit(my_bar);
+      mma_commit(&cbar);
     }
     __syncwarp();
     const float b2 = __ldg(p.b2 + (tw & 63)), a2 = __ldg(p.a2 + (tw & 63)), w3 = __ldg(p.w3 + (tw & 63));
-    mbar_wait(my_bar, phase);
-    phase ^= 1;
+    mbar_wait(&cbar, cphase);
+    cphase ^= 1;
     __syncwarp();
     tc_fence_after();
     {
-      uint32_t d[16];
-      tmem_ld16(tbase + TM_HS + lane_base, d);
+      uint32_t d[8];
+      tmem_ld8(tD2 + 8 * wg + lane_base, d);
       tmem_ld_wait();
-      float* red = reinterpret_cast<float*>(ws + WS_RED);     // [64 units][16 rows]
-      float* zp = reinterpret_cast<float*>(ws + WS_ZP);       // [8][16]
-      if (tw >= 64) {
-#pragma unroll
-        for (int r = 0; r < 16; r += 4)
-          *reinterpret_cast<float4*>(red + (tw - 64) * 16 + r) =
-              make_float4(__uint_as_float(d[r]), __uint_as_float(d[r + 1]), __uint_as_float(d[r + 2]),
-                          __uint_as_float(d[r + 3]));
+      float* red = reinterpret_cast<float*>(cs_base + WS_RED);    // [64 units][32 rows]
+      float* zp = reinterpret_cast<float*>(cs_base + WS_ZP);      // [16][32]
+      if (tw >= 64) {                                              // lo halves of W2 -> smem
+        *reinterpret_cast<float4*>(red + (tw - 64) * 32 + 8 * wg) =
+            make_float4(__uint_as_float(d[0]), __uint_as_float(d[1]), __uint_as_float(d[2]), __uint_as_float(d[3]));
+        *reinterpret_cast<float4*>(red + (tw - 64) * 32 + 8 * wg + 4) =
+            make_float4(__uint_as_float(d[4]), __uint_as_float(d[5]), __uint_as_float(d[6]), __uint_as_float(d[7]));
       }
-      wg_sync(wg);
+      __syncthreads();
       if (tw < 64) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          float v = __uint_as_float(d[r]) + red[tw * 16 + r] + b2;   // (W2hi + W2lo) . (H1hi + H1lo)
+        for (int r = 0; r < 8; ++r) {
+          float v = __uint_as_float(d[r]) + red[tw * 32 + 8 * wg + r] + b2;   // (W2hi + W2lo) . (H1hi + H1lo)
           v = v > 0.f ? v : a2 * v;
-          red[tw * 16 + r] = v * w3;
+          red[tw * 32 + 8 * wg + r] = v * w3;
         }
       }
-      wg_sync(wg);
-      {  // 16 rows x 8 partial sums of 8 units
-        const int r = tw & 15, pt = tw >> 4;
+      __syncthreads();
+      {  // 32 rows x 16 partial sums of 4 units
+        const int r = tid & 31, pt = tid >> 5;
         float s = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += red[(pt * 8 + u) * 16 + r];
-        zp[pt * 16 + r] = s;
+        for (int u = 0; u < 4; ++u) s += red[(pt * 4 + u) * 32 + r];
+        zp[pt * 32 + r] = s;
       }
-      wg_sync(wg);
-      if (tw < G) {
+      __syncthreads();
+      if (tid < kTcSG) {
         float z = p.b3;
 #pragma unroll
-        for (int pt = 0; pt < 8; ++pt) z += zp[pt * 16 + tw];
-        const int row = row0 + tw;
+        for (int pt = 0; pt < 16; ++pt) z += zp[pt * 32 + tid];
+        const int row = sg * kTcSG + tid;
         if (row < b.B) {
           b.probs[row] = sigmoidf_acc(z);
           if (b.logits) b.logits[row] = z;
@@ -493,7 +527,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       }
     }
     tc_fence_before();
-    wg_sync(wg);                                         // scratch is reused by the next group
+    __syncthreads();                                     // scratch is reused by the next super-group
     TC_TRACE(31);
   }
   if (!weights_ready) mbar_wait(&wbar, 0);               // never exit with the bulk copy in flight
@@ -508,18 +542,13 @@ cudaError_t read_din_tc_trace(unsigned long long* out40) {
 }
 
 size_t din_tc_smem_bytes(int cpr) {
-  return 1024 + ((din_tc_image_bytes(cpr) + 1023u) & ~1023u) + (size_t)kTcWG * WS_BYTES;
+  return 1024 + ((din_tc_image_bytes(cpr) + 1023u) & ~1023u) + WS_BYTES;
 }
 
-cudaError_t launch_din_tc(const DinTcParams& p0, const BatchView& b, cudaStream_t s) {
+cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
   if (b.B <= 0) return cudaSuccess;
-  DinTcParams p = p0;
-  // rows per group: 16 when there is enough work to keep every worker busy, else 8
-  const int workers = p.num_sms * kTcWG;
-  p.G = (b.B >= 16 * workers) ? 16 : 8;
-  const int n_groups = (b.B + p.G - 1) / p.G;
-  int grid = (n_groups + kTcWG - 1) / kTcWG;
-  if (grid > p.num_sms) grid = p.num_sms;
+  const int n_sg = (b.B + kTcSG - 1) / kTcSG;
+  const int grid = n_sg < p.num_sms ? n_sg : p.num_sms;
   din_tc_kernel<<<grid, kTcWG * 128, din_tc_smem_bytes(p.CPR), s>>>(p, b);
   ++g_launch_count;
   return cudaGetLastError();

@@ -125,7 +125,7 @@ struct DinTcParams {
   const float* user;       // [n_users][32]
   const float* ugenre;     // [19][32]
   const float* mgenre;     // [19][32]
-  const uint8_t* image;    // shared-memory image: bf16 hi/lo SW128 operand tiles + alpha*wout table
+  const uint8_t* image;    // shared-memory image: bf16 hi/lo SW128 operand tiles + P/Q epilogue tables
   const float* au_wc;      // [32][32]  W_c - W_sub
   const float* au_b;       // [32]
   const float* b1;         // [128]
@@ -141,7 +141,6 @@ struct DinTcParams {
   int T;
   int CPR;                 // 32-position chunks per row = ceil(T / 32)
   int num_sms;
-  int G;                   // rows per group (8 or 16), chosen per launch
   int trace;               // debug: record phase timestamps of worker 0 (srs_debug_din_trace)
 };
 
