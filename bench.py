@@ -44,6 +44,24 @@ METRIC = "CTR inferences/sec (DIN, batch=4096, hist_len=50)"
 WORKLOAD = "cfg3_din"
 L2_BYTES = 126 * 1024 * 1024
 
+# BASELINE.json configs -> (default rows per GPU per step, metric label).  cfg3_din is the
+# configuration the headline metric is quoted on (the default); the others are the remaining
+# rows of SURVEY.md section 8d and run with `--workload <name>`.
+WORKLOADS = {
+    "cfg1_embeddingmlp": (128, "EmbeddingMLP, MovieLens-1K vocab, batch=128"),
+    "cfg2_deepfm": (4096, "DeepFM, ML-20M vocab, emb_dim=16, batch=4096"),
+    "cfg2_deepfm_v2": (4096, "DeepFM_v2, ML-20M vocab, emb_dim=16, batch=4096"),
+    "cfg3_din": (4096, "DIN, batch=4096, hist_len=50"),
+    "cfg4_widendeep": (8192, "Wide&Deep, batch=65536 over 8 GPUs = 8192 per GPU"),
+    "cfg4_neuralcf": (8192, "NeuralCF, batch=65536 over 8 GPUs = 8192 per GPU"),
+    "cfg4_twotowers": (8192, "two towers, batch=65536 over 8 GPUs = 8192 per GPU"),
+    "cfg5_din": (8192, "DIN, 100M-item vocab, emb_dim=64, hist_len=200, batch=8192"),
+}
+
+
+def metric_name(workload):
+    return METRIC if workload == WORKLOAD else "CTR inferences/sec (%s)" % WORKLOADS[workload][1]
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -51,13 +69,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="rows per GPU per step")
-    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--batch", type=int, default=None, help="rows per GPU per step")
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--gather", action="store_true", help="all-gather scores every step (N>1)")
     ap.add_argument("--no-graph", action="store_true", help="launch directly instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = WORKLOADS[args.workload][0]
+    return args
 
 
 def dist_env():
@@ -65,11 +86,49 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
-def workload_desc(spec, batch):
-    return ("%s: DIN forward, hist_len=%d, emb_dim=%d, batch=%d per GPU, V_movie=%d, V_user=%d, "
-            "activation unit 4E->32->1 sigmoid-gated sum pooling, top MLP %d->128->64->1"
-            % (WORKLOAD, spec.hist_len, spec.emb_dim, batch, spec.n_movies, spec.n_users,
-               5 * spec.emb_dim + 7))
+def workload_desc(name, spec, batch):
+    if spec.model == "din":
+        return ("%s: DIN forward, hist_len=%d, emb_dim=%d, batch=%d per GPU, V_movie=%d, V_user=%d, "
+                "activation unit 4E->32->1 sigmoid-gated sum pooling, top MLP %d->128->64->1"
+                % (name, spec.hist_len, spec.emb_dim, batch, spec.n_movies, spec.n_users,
+                   5 * spec.emb_dim + 7))
+    return ("%s: %s forward, emb_dim=%d, batch=%d per GPU, V_movie=%d, V_user=%d, hidden=%s"
+            % (name, spec.model, spec.emb_dim, batch, spec.n_movies, spec.n_users, list(spec.hidden)))
+
+
+def make_weights(spec, device=None):
+    """Seeded random-init weights of the reference architecture.  The 25.6 GB movie table of
+    cfg 5 is generated in place in HBM (srs_fill_uniform) and handed over without a copy; on
+    the CPU side a 10^6-row surrogate of the same formula is used for timing only."""
+    from sparrowrecsys_b200.weights import init_weights
+    big = spec.model == "din" and spec.n_movies > 10_000_000
+    if not big:
+        return init_weights(spec, 2), None
+    W = init_weights(spec, 2, skip=("embedding",))
+    if device is None:
+        return W, None
+    import torch
+    from sparrowrecsys_b200 import _lib
+    table = torch.empty(spec.n_movies, spec.emb_dim, dtype=torch.float32, device=device)
+    _lib.check(_lib.load().srs_fill_uniform(table.data_ptr(), table.numel(), 1234, -0.05, 0.05,
+                                            device.index, None))
+    torch.cuda.synchronize(device)
+    W["embedding"] = table
+    return W, table
+
+
+def cpu_spec_and_weights(spec):
+    """Spec/weights the numpy oracle can hold (cfg 5: 10^6-row surrogate vocabulary)."""
+    from dataclasses import replace
+    from sparrowrecsys_b200.weights import init_weights
+    from oracle import ctr_oracle as O
+    if spec.model == "din" and spec.n_movies > 10_000_000:
+        small = replace(spec, n_movies=1_000_000)
+        W = init_weights(small, 2, skip=("embedding",))
+        W["embedding"] = O.fill_uniform(np.arange(small.n_movies * small.emb_dim), 1234, -0.05,
+                                        0.05).reshape(small.n_movies, small.emb_dim)
+        return small, W, " (10^6-row surrogate movie table for the CPU timing)"
+    return spec, init_weights(spec, 2), ""
 
 
 # ----------------------------------------------------------------------------------------
@@ -183,9 +242,8 @@ def run_reference(args):
     from sparrowrecsys_b200.features import synthetic_features
     from sparrowrecsys_b200.spec import baseline_spec
     from sparrowrecsys_b200.weights import init_weights
-    spec = baseline_spec(args.workload)
-    W = init_weights(spec, 2)
-    feats = synthetic_features(spec, args.batch, seed=2)
+    spec, W, note = cpu_spec_and_weights(baseline_spec(args.workload))
+    feats = synthetic_features(spec, args.batch, seed=2, uniform_history=args.workload == "cfg5_din")
     cores = os.cpu_count() or 1
     # size the per-step sample so that steps+warmup stay within ~2 minutes
     t0 = time.perf_counter()
@@ -206,11 +264,11 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "inferences/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "inferences/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc(spec, args.batch), "rows_per_step": rows},
+        "config": {"workload": workload_desc(args.workload, spec, args.batch) + note, "rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "inferences/s", "cores": cores, "kind": "port",
                          "sample": "%d of %d rows per step, numpy float32 oracle (OpenBLAS, %d threads); "
                                    "TF2 itself is not installable here" % (rows, args.batch, cores)},
@@ -243,24 +301,30 @@ def run_ours(args):
     lib = _lib.load()
     spec = baseline_spec(args.workload)
     B = args.batch
-    W = init_weights(spec, 2)                       # same weights on every rank (replicated)
+    W, _table = make_weights(spec, dev)               # same weights on every rank (replicated)
     model = CTRModel(spec, W, device=local_rank)
-    T = spec.hist_len
+    T = model.hist_cols
+    uniform_hist = args.workload == "cfg5_din"        # worst case for the 25.6 GB table: defeats L2
 
     # ---- input ring: distinct batches, footprint > L2 ------------------------------
-    bytes_per_batch = B * (4 * (T + 2) + 4 * 8 + 4 * 7 + 4)
-    ring = int(np.ceil(1.25 * L2_BYTES / bytes_per_batch))
-    feats = synthetic_features(spec, ring * B, seed=1000 + rank)   # each rank its own user-batches
-    enc = encode_batch(spec, feats)
+    probe = encode_batch(spec, synthetic_features(spec, 8, seed=0))
+    cols = [a for a in (probe.movie_id, probe.user_id, probe.hist, probe.movie_genre,
+                        probe.user_genre, probe.numerics) if a is not None]
+    bytes_per_row = sum(a.nbytes for a in cols) // 8 + 4          # inputs + the score written back
+    bytes_per_batch = B * bytes_per_row
+    ring = max(2, int(np.ceil(1.25 * L2_BYTES / bytes_per_batch)))
+    ring = min(ring, 4096)
+    feats = synthetic_features(spec, ring * B, seed=1000 + rank, uniform_history=uniform_hist)
+    enc = encode_batch(spec, feats)                   # each rank scores its own user-batches
     d = model.to_device(enc)                          # one big device allocation per column
     out = torch.empty(ring, B, dtype=torch.float32, device=dev)
+    ptr = lambda t, lo, width: None if t is None else t.data_ptr() + 4 * lo * width
     structs = []
     for i in range(ring):
         lo = i * B
-        structs.append(_lib.SrsBatch(
-            B, T, d.movie_id.data_ptr() + 4 * lo, d.user_id.data_ptr() + 4 * lo,
-            d.hist.data_ptr() + 4 * lo * T, d.movie_genre.data_ptr() + 4 * lo * 3,
-            d.user_genre.data_ptr() + 4 * lo * 5, d.numerics.data_ptr() + 4 * lo * 7))
+        structs.append(_lib.SrsBatch(B, T, ptr(d.movie_id, lo, 1), ptr(d.user_id, lo, 1),
+                                     ptr(d.hist, lo, max(T, 1)), ptr(d.movie_genre, lo, 3),
+                                     ptr(d.user_genre, lo, 5), ptr(d.numerics, lo, 7)))
     out_ptrs = [out[i].data_ptr() for i in range(ring)]
     handle = model._h
 
@@ -344,10 +408,10 @@ def run_ours(args):
         e = encode_batch(spec, {k: np.asarray(v)[i * B:(i + 1) * B] for k, v in feats.items()},
                          arena_alloc=pinned_arena)
         henc.append(e)
-        hstructs.append(_lib.SrsBatch(B, T, e.movie_id.ctypes.data, e.user_id.ctypes.data,
-                                      e.hist.ctypes.data, e.movie_genre.ctypes.data,
-                                      e.user_genre.ctypes.data, e.numerics.ctypes.data))
-    h2d = B * (4 * (T + 2) + 4 * 3 + 4 * 5 + 4 * 7)
+        hp = lambda a: None if a is None else a.ctypes.data
+        hstructs.append(_lib.SrsBatch(B, T, hp(e.movie_id), hp(e.user_id), hp(e.hist),
+                                      hp(e.movie_genre), hp(e.user_genre), hp(e.numerics)))
+    h2d = B * (bytes_per_row - 4)
     d2h = B * 4 + 4
 
 
@@ -389,21 +453,23 @@ def run_ours(args):
         launch_us = 1e3 * ms / max(args.steps, 1)
         achieved = bpi * B / (launch_us * 1e-6) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "inferences/s", "n_gpus": world,
+            "metric": metric_name(args.workload), "value": value, "unit": "inferences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": workload_desc(spec, B), "batch_per_gpu": B, "global_batch": world * B,
+                "workload": workload_desc(args.workload, spec, B), "batch_per_gpu": B, "global_batch": world * B,
                 "parallelism": "dp%d: rows sharded by user-batch, weights replicated, no data-path "
                                "collective%s" % (world, " + all-gather of scores" if gather_buf is not None else ""),
                 "kernel": model.kernel_name, "launch": launch_mode,
                 "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB > 126 MB L2): ids/"
-                      "numerics are read from HBM every step; embedding tables (%.1f MB) are L2-resident "
-                      "by size" % (ring, ring * bytes_per_batch / 1e6,
-                                   4 * spec.emb_dim * (spec.n_movies + spec.n_users) / 1e6),
-                "weights": "random init of the reference architecture (seed 2), Zipf(1.05) movie ids, "
-                           "history length U[1,50] zero-padded (padding included, as in the reference)",
+                      "numerics are read from HBM every step; embedding tables total %.1f MB (%s)"
+                      % (ring, ring * bytes_per_batch / 1e6,
+                         4 * spec.emb_dim * (spec.n_movies + spec.n_users) / 1e6,
+                         "L2-resident by size" if spec.n_movies < 10_000_000 else "HBM-resident, uniform ids"),
+                "weights": "random init of the reference architecture (seed 2), %s movie ids, "
+                           "history 0-padded to T (padding included, as in the reference)"
+                           % ("uniform" if uniform_hist else "Zipf(1.05)"),
             },
             "e2e": {"value": e2e_value, "unit": "inferences/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_n,
@@ -412,18 +478,22 @@ def run_ours(args):
             "gpu_launches": args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic() if args.workload == WORKLOAD else None,
                          "algorithmic_bytes_per_launch": bpi * B, "launch_us": launch_us,
                          "peak_source": peak_src},
         }
         if not args.no_cpu_baseline:
             n_cpu = min(B, 4096)
+            cspec, cW, cnote = cpu_spec_and_weights(spec)
             cpu_feats = {k: np.asarray(v)[:n_cpu] for k, v in feats.items()}
-            v, reps, dt = cpu_oracle_throughput(spec, W, cpu_feats, args.cpu_seconds)
+            if cspec is not spec:
+                cpu_feats = synthetic_features(cspec, n_cpu, seed=7, uniform_history=True)
+            v, reps, dt = cpu_oracle_throughput(cspec, cW, cpu_feats, args.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": v, "unit": "inferences/s", "cores": os.cpu_count() or 1, "kind": "port",
                 "sample": "%d x %d-row batch of the same workload in %.1f s, numpy float32 oracle "
-                          "(OpenBLAS threads = cores); TF2 is not installable here" % (reps, n_cpu, dt)}
+                          "(OpenBLAS threads = cores); TF2 is not installable here%s" % (reps, n_cpu, dt, cnote)}
         print(json.dumps(line))
     model.close()
     if distributed:

@@ -30,6 +30,9 @@ for rep in range(3):
     names = {0: "entry", 1: "prologue", 2: "phase0", 3: "weights", 30: "layer1", 31: "group", 32: "exit"}
     line = []
     prev = t0
+    fine = {20: "t1.built", 21: "t1.stwait", 22: "t1.sync", 23: "t1.issued", 24: "t1.prefetched",
+            25: "t1.mma_done", 26: "t1.epilogue"}
+    print("  tile-1 detail: " + " ".join("%s=%d" % (fine[i], t[i] - t[5 - 1]) for i in sorted(fine) if t[i]))
     for i in list(range(0, 4 + 8)) + [30, 31, 32]:
         if t[i] == 0:
             continue

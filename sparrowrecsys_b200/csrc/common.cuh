@@ -91,8 +91,25 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ld
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  // weights stream from L2/L1: the next 4 rows of W are requested before the current 4 are used
+  float4 wn[4][TN / 4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+    for (int j = 0; j < TN / 4; ++j) wn[kk][j] = ldg4(W + (size_t)kk * N + col0 + 4 * j);
   for (int k = 0; k < K; k += 4) {
     float4 xv[TM];
+    float4 wc[4][TN / 4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int j = 0; j < TN / 4; ++j) wc[kk][j] = wn[kk][j];
+    if (k + 4 < K) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int j = 0; j < TN / 4; ++j) wn[kk][j] = ldg4(W + (size_t)(k + 4 + kk) * N + col0 + 4 * j);
+    }
 #pragma unroll
     for (int i = 0; i < TM; ++i)
       xv[i] = *reinterpret_cast<const float4*>(xs + (ry + i * RT) * ldx + k);
@@ -101,7 +118,7 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ld
       float w[TN];
 #pragma unroll
       for (int j = 0; j < TN; j += 4) {
-        float4 t = ldg4(W + (size_t)(k + kk) * N + col0 + j);
+        const float4 t = wc[kk][j / 4];
         w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
       }
 #pragma unroll

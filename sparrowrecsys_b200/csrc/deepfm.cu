@@ -12,7 +12,8 @@
 
 namespace srs {
 
-constexpr int kFmRows = 64;
+constexpr int kFmRows = 64;      // DeepFM_v2 tile
+constexpr int kFm1Rows = 32;     // DeepFM tile: 4096 rows -> 128 CTAs
 
 __device__ __forceinline__ int genre_id(const int32_t* col, int row, int stride, int n_genres,
                                         int* err_flag) {
@@ -26,7 +27,7 @@ __device__ __forceinline__ int genre_id(const int32_t* col, int row, int stride,
 // ------------------------------------------------------------------------------------
 template <int EP>
 __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchView b) {
-  constexpr int R = kFmRows;
+  constexpr int R = kFm1Rows;
   constexpr int Q = EP / 4;
   constexpr int KP = 2 * EP + kNumPad;
   constexpr int LDX = KP + 4;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
     Xs[r * LDX + 2 * EP + j] = v;
   }
   __syncthreads();
-  {  // four dots per row (DeepFM.py:100-103): <item,user> <ig,ug> <ig,user> <item,ug>
+  if (tid < R * 4) {  // four dots per row (DeepFM.py:100-103): <item,user> <ig,ug> <ig,user> <item,ug>
     const int r = tid >> 2, d = tid & 3;
     const float* f = Fs + r * LDF;
     const float* a = (d == 0 || d == 3) ? f : f + 2 * EP;            // item or item_genre
@@ -84,9 +85,9 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
     for (int k = 0; k < EP; ++k) s = fmaf(a[k], c[k], s);
     Ds[r * 4 + d] = s;
   }
-  dense_layer<R, 64, 2, 8>(Xs, LDX, KP, p.W1, p.b1, ACT_RELU, nullptr, H1, LDH);
+  dense_layer<R, 64, 1, 8>(Xs, LDX, KP, p.W1, p.b1, ACT_RELU, nullptr, H1, LDH);
   __syncthreads();
-  dense_layer<R, 64, 2, 8>(H1, LDH, 64, p.W2, p.b2, ACT_RELU, nullptr, H2, LDH);
+  dense_layer<R, 64, 1, 8>(H1, LDH, 64, p.W2, p.b2, ACT_RELU, nullptr, H2, LDH);
   __syncthreads();
   row_dot<R>(H2, LDH, 64, p.wdeep, [&](int r, float s) {
     const int row = row0 + r;
@@ -112,12 +113,12 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
 
 template <int EP>
 static size_t deepfm_smem() {
-  return (size_t)kFmRows * ((2 * EP + kNumPad + 4) + (4 * EP + 4) + 68 + 68 + 4) * sizeof(float);
+  return (size_t)kFm1Rows * ((2 * EP + kNumPad + 4) + (4 * EP + 4) + 68 + 68 + 4) * sizeof(float);
 }
 
 template <int EP>
 static cudaError_t launch_deepfm_t(const DeepFmParams& p, const BatchView& b, cudaStream_t s) {
-  const int blocks = (b.B + kFmRows - 1) / kFmRows;
+  const int blocks = (b.B + kFm1Rows - 1) / kFm1Rows;
   deepfm_kernel<EP><<<blocks, kThreads, deepfm_smem<EP>(), s>>>(p, b);
   ++g_launch_count;
   return cudaGetLastError();

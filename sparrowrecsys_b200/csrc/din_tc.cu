@@ -112,6 +112,7 @@ struct GroupLoads {
   int raw0, raw1;                   // history ids of this thread's pair in tiles 0 and 1
 };
 
+template <int CPR>
 __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_constant__ DinTcParams p,
                                                                  BatchView b) {
   extern __shared__ uint8_t raw[];
@@ -126,17 +127,18 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   const int srs = tw >> 3, sq = tw & 7;                 // side-feature role: row slot / float4 index
   uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* img = base;
-  const uint32_t img_bytes = din_tc_image_bytes(p.CPR);
+  const uint32_t img_bytes = din_tc_image_bytes(CPR);
   uint8_t* cs_base = base + ((img_bytes + 1023u) & ~1023u);     // CTA scratch
   uint8_t* ws = cs_base + wg * WS_W_STRIDE;                      // this worker's phase-0/1 view
-  const int CPR = p.CPR, T = p.T, TP = CPR * 32;
+  constexpr int TP = CPR * 32;
+  const int T = p.T;
   const float* Ptab = reinterpret_cast<const float*>(img + IMG_PQ);
   const float* Qtab = Ptab + 32 * TP;
   float* cand = reinterpret_cast<float*>(ws + WS_CAND);
   float* cst = reinterpret_cast<float*>(ws + WS_CST);
   float* part = reinterpret_cast<float*>(ws + WS_PART);
   float* nums = reinterpret_cast<float*>(cs_base + WS_NUMS);
-  const int n_tiles = 2 * CPR;                          // 8 rows * CPR chunks / 4 chunks per tile
+  constexpr int n_tiles = 2 * CPR;                      // 8 rows * CPR chunks / 4 chunks per tile
   const int n_sg = (b.B + kTcSG - 1) / kTcSG;
 
   // thread <-> (chunk = 4*tile + warp_w, position = lane): row slot rs = chunk / CPR
@@ -248,18 +250,6 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       load_row(id0, hn);
     }
     wg_sync(wg);
-    {  // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4
-      float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
-#pragma unroll 8
-      for (int e = 0; e < 32; ++e) {
-        const float wc = __ldg(p.au_wc + e * 32 + lane);
-        acc0 = fmaf(cand[warp_w * 32 + e], wc, acc0);
-        acc1 = fmaf(cand[(warp_w + 4) * 32 + e], wc, acc1);
-      }
-      cst[warp_w * 32 + lane] = acc0;
-      cst[(warp_w + 4) * 32 + lane] = acc1;
-    }
-    wg_sync(wg);
     TC_TRACE(2);
     if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
     TC_TRACE(3);
@@ -293,17 +283,22 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * q);
-          const Split2 s0 = split_pack(hn[q].x * c4.x, hn[q].y * c4.y);
-          const Split2 s1 = split_pack(hn[q].z * c4.z, hn[q].w * c4.w);
+          const float2 g01 = mul2(make_float2(hn[q].x, hn[q].y), make_float2(c4.x, c4.y));
+          const float2 g23 = mul2(make_float2(hn[q].z, hn[q].w), make_float2(c4.z, c4.w));
+          const Split2 s0 = split_pack(g01.x, g01.y);
+          const Split2 s1 = split_pack(g23.x, g23.y);
           ahi[2 * q] = s0.hi; ahi[2 * q + 1] = s1.hi;
           alo[2 * q] = s0.lo; alo[2 * q + 1] = s1.lo;
         }
         tmem_st16(tbase + TM_A_HI + 16 + lane_base, ahi);
         tmem_st16(tbase + TM_A_LO + 16 + lane_base, alo);
       }
+      if (tile == 1) TC_TRACE(20);
       tmem_st_wait();
       tc_fence_before();
+      if (tile == 1) TC_TRACE(21);
       wg_sync(wg);
+      if (tile == 1) TC_TRACE(22);
       if (tw == 0) {
         tc_fence_after();
         const uint64_t bh = smem_desc_sw128(s_img + IMG_AUB_HI), bl = smem_desc_sw128(s_img + IMG_AUB_LO);
@@ -316,6 +311,20 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         mma_commit(my_bar);
       }
       __syncwarp();
+      if (tile == 1) TC_TRACE(23);
+      if (tile == 0) {
+        // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4.
+        // First needed by the first epilogue: computed while the first MMAs run.
+        float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
+#pragma unroll 8
+        for (int e = 0; e < 32; ++e) {
+          const float wc = __ldg(p.au_wc + e * 32 + lane);
+          acc0 = fmaf(cand[warp_w * 32 + e], wc, acc0);
+          acc1 = fmaf(cand[(warp_w + 4) * 32 + e], wc, acc1);
+        }
+        cst[warp_w * 32 + lane] = acc0;
+        cst[(warp_w + 4) * 32 + lane] = acc1;
+      }
       // ---- prefetch the next tile's history rows while the MMAs run
       {
         const int idn = fix_id(raw1);
@@ -324,8 +333,11 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         raw1 = raw0;
         raw0 = raw_id(row0, tile + 3);
       }
+      if (tile == 1) TC_TRACE(24);
       mbar_wait(my_bar, phase);
       phase ^= 1;
+      if (tile == 1) TC_TRACE(25);
+      if (tile == 0) wg_sync(wg);                       // cst of all 8 rows is in place
       __syncwarp();
       tc_fence_after();
       uint32_t d[32];
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       tmem_ld_wait();
       // ---- epilogue: + cst, PReLU (alpha per position) and Dense(1) folded into two tables
       //      sum_j wout_j max(v,0) + alpha_tj wout_j min(v,0) = sum_j v P_tj + |v| Q_tj
-      float s0 = p.au_bout, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
       {
         const float* cs = cst + rs * 32;
         const float* pt = Ptab + t;
@@ -341,35 +353,49 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
-          const float v0 = __uint_as_float(d[j]) + c4.x, v1 = __uint_as_float(d[j + 1]) + c4.y;
-          const float v2 = __uint_as_float(d[j + 2]) + c4.z, v3 = __uint_as_float(d[j + 3]) + c4.w;
-          s0 = fmaf(v0, pt[j * TP], s0);
-          s1 = fmaf(v1, pt[(j + 1) * TP], s1);
-          s2 = fmaf(v2, pt[(j + 2) * TP], s2);
-          s3 = fmaf(v3, pt[(j + 3) * TP], s3);
-          s0 = fmaf(fabsf(v0), qt[j * TP], s0);
-          s1 = fmaf(fabsf(v1), qt[(j + 1) * TP], s1);
-          s2 = fmaf(fabsf(v2), qt[(j + 2) * TP], s2);
-          s3 = fmaf(fabsf(v3), qt[(j + 3) * TP], s3);
+          const float2 v01 = add2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])),
+                                  make_float2(c4.x, c4.y));
+          const float2 v23 = add2(make_float2(__uint_as_float(d[j + 2]), __uint_as_float(d[j + 3])),
+                                  make_float2(c4.z, c4.w));
+          sa = fma2(v01, make_float2(pt[j * TP], pt[(j + 1) * TP]), sa);
+          sb = fma2(v23, make_float2(pt[(j + 2) * TP], pt[(j + 3) * TP]), sb);
+          sa = fma2(make_float2(fabsf(v01.x), fabsf(v01.y)), make_float2(qt[j * TP], qt[(j + 1) * TP]), sa);
+          sb = fma2(make_float2(fabsf(v23.x), fabsf(v23.y)), make_float2(qt[(j + 2) * TP], qt[(j + 3) * TP]), sb);
         }
       }
-      const float s = (s0 + s1) + (s2 + s3);
+      const float s = (sa.x + sa.y) + (sb.x + sb.y);
+      if (tile == 1) TC_TRACE(26);
       const float w = valid ? 1.f / (1.f + __expf(-s)) : 0.f;
       // ---- pooling: out[e = lane] = sum over the chunk's 32 positions of w_t * h_t[e]
       tmem_ld32(tbase + TM_HS + lane_base, d);
       tmem_ld_wait();
       float h[32];
+      {
+        const float2 w2 = make_float2(w, w);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) h[e] = __uint_as_float(d[e]) * w;
+        for (int e = 0; e < 32; e += 2) {
+          const float2 v = mul2(make_float2(__uint_as_float(d[e]), __uint_as_float(d[e + 1])), w2);
+          h[e] = v.x; h[e + 1] = v.y;
+        }
+      }
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
+      for (int o = 16; o >= 2; o >>= 1) {
         const bool up = (lane & o) != 0;
 #pragma unroll
-        for (int i = 0; i < o; ++i) {
-          const float send = up ? h[i] : h[i + o];
-          const float keep = up ? h[i + o] : h[i];
-          h[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        for (int i = 0; i < o; i += 2) {
+          const float send0 = up ? h[i] : h[i + o], send1 = up ? h[i + 1] : h[i + 1 + o];
+          const float keep0 = up ? h[i + o] : h[i], keep1 = up ? h[i + 1 + o] : h[i + 1];
+          const float2 r = add2(make_float2(keep0, keep1),
+                                make_float2(__shfl_xor_sync(0xffffffffu, send0, o),
+                                            __shfl_xor_sync(0xffffffffu, send1, o)));
+          h[i] = r.x; h[i + 1] = r.y;
         }
+      }
+      {
+        const bool up = (lane & 1) != 0;
+        const float send = up ? h[0] : h[1];
+        const float keep = up ? h[1] : h[0];
+        h[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
       part[(rs * kTcMaxCPR + cq) * 32 + lane] = h[0];
       if (tile < 24) TC_TRACE(4 + tile);
@@ -545,18 +571,35 @@ size_t din_tc_smem_bytes(int cpr) {
   return 1024 + ((din_tc_image_bytes(cpr) + 1023u) & ~1023u) + WS_BYTES;
 }
 
-cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
-  if (b.B <= 0) return cudaSuccess;
+template <int CPR>
+static cudaError_t launch_din_tc_t(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
   const int n_sg = (b.B + kTcSG - 1) / kTcSG;
   const int grid = n_sg < p.num_sms ? n_sg : p.num_sms;
-  din_tc_kernel<<<grid, kTcWG * 128, din_tc_smem_bytes(p.CPR), s>>>(p, b);
+  din_tc_kernel<CPR><<<grid, kTcWG * 128, din_tc_smem_bytes(CPR), s>>>(p, b);
   ++g_launch_count;
   return cudaGetLastError();
 }
 
+cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
+  if (b.B <= 0) return cudaSuccess;
+  switch (p.CPR) {
+    case 1: return launch_din_tc_t<1>(p, b, s);
+    case 2: return launch_din_tc_t<2>(p, b, s);
+    case 3: return launch_din_tc_t<3>(p, b, s);
+    case 4: return launch_din_tc_t<4>(p, b, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t setup_din_tc_attributes() {
-  return cudaFuncSetAttribute(din_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)din_tc_smem_bytes(kTcMaxCPR));
+  cudaError_t e;
+#define SRS_ATTR(C_)                                                                     \
+  e = cudaFuncSetAttribute(din_tc_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)din_tc_smem_bytes(C_));                                  \
+  if (e != cudaSuccess) return e;
+  SRS_ATTR(1) SRS_ATTR(2) SRS_ATTR(3) SRS_ATTR(4)
+#undef SRS_ATTR
+  return cudaSuccess;
 }
 
 }  // namespace srs

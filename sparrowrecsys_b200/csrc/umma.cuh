@@ -194,14 +194,57 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // ---- bf16 hi/lo split ("bf16x3": x*w ~ hi*whi + lo*whi + hi*wlo) ------------------------------
 // hi = x rounded to bf16 (round-to-nearest-even), lo = (x - hi) rounded to bf16; x - hi is
 // exact in fp32 and |x - hi - lo| <= 2^-17 |x|.
+// ---- packed fp32x2 arithmetic (sm_100: one issue slot for two fp32 operations) -----------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 struct Split2 {
   uint32_t hi, lo;      // packed pairs: first value in the low half
 };
 __device__ __forceinline__ Split2 split_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
-  const float ha = __uint_as_float(hb << 16), hbv = __uint_as_float(hb & 0xFFFF0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hbv);
+  const float2 lo2 = sub2(make_float2(a, b), make_float2(__uint_as_float(hb << 16),
+                                                          __uint_as_float(hb & 0xFFFF0000u)));
+  __nv_bfloat162 l = __floats2bfloat162_rn(lo2.x, lo2.y);
   Split2 r;
   r.hi = hb;
   r.lo = *reinterpret_cast<uint32_t*>(&l);

@@ -66,6 +66,15 @@ def genre_to_index(values) -> np.ndarray:
     if arr.dtype.kind in "iu":          # already indexed by the caller
         return arr.astype(np.int32)
     flat = arr.ravel()
+    if flat.shape[0] > 4096:            # vectorised: look up each distinct value once
+        as_str = np.array([v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat[:0]],
+                          dtype=object)
+        uniq, inv = np.unique(flat.astype(str) if flat.dtype != object or not any(
+            isinstance(v, bytes) for v in flat[:64]) else np.array(
+                [v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat], dtype=str),
+            return_inverse=True)
+        lut = np.array([_GENRE_INDEX.get(str(u), -1) for u in uniq], dtype=np.int32)
+        return lut[inv].reshape(arr.shape)
     out = np.empty(flat.shape[0], dtype=np.int32)
     for i, v in enumerate(flat):
         if isinstance(v, bytes):
