@@ -187,6 +187,14 @@ int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, 
  * copy the 40 recorded values out.  No effect on results. */
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40);
 
+/* Micro-benchmark behind the DIN kernel's MMA shape choice: SM cycles for a chain of n_mma
+ * tcgen05.mma (M = 128, K = 16 bf16) with N in {32, 64, 128}, A from shared (0) or tensor (1)
+ * memory, into one accumulator (two_acc bit 0 = 0) or alternating two (bit 0 = 1); bit 1 of
+ * two_acc selects warp-uniform issue through elect.sync instead of a divergent single thread.
+ * out2[0] = issue cycles, out2[1] = cycles until the commit barrier completes. */
+int srs_debug_umma_bench(int32_t N, int32_t n_mma, int32_t a_in_tmem, int32_t two_acc,
+                         int32_t device, uint64_t* out2);
+
 /* Known-answer self test of the tcgen05 / TMEM plumbing the DIN kernel is built on:
  * D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T (inputs truncated to bf16, fp32 accumulate),
  * K = 64 * k_blocks (1..3), N = 16 or 32, A staged through shared memory (a_in_tmem = 0)

@@ -250,6 +250,23 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       load_row(id0, hn);
     }
     wg_sync(wg);
+    // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4.
+    // First needed by the first epilogue.  Workers 0/1 compute it while their first MMAs run,
+    // workers 2/3 before their first tile: that skews the two pairs by one cst time, so the
+    // pairs' tensor-core phases and CUDA-core phases interleave instead of colliding.
+    auto compute_cst = [&]() {
+      float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
+#pragma unroll 8
+      for (int e = 0; e < 32; ++e) {
+        const float wc = __ldg(p.au_wc + e * 32 + lane);
+        acc0 = fmaf(cand[warp_w * 32 + e], wc, acc0);
+        acc1 = fmaf(cand[(warp_w + 4) * 32 + e], wc, acc1);
+      }
+      cst[warp_w * 32 + lane] = acc0;
+      cst[(warp_w + 4) * 32 + lane] = acc1;
+    };
+    const bool cst_early = wg >= 2;
+    if (cst_early) compute_cst();
     TC_TRACE(2);
     if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
     TC_TRACE(3);
@@ -312,19 +329,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       }
       __syncwarp();
       if (tile == 1) TC_TRACE(23);
-      if (tile == 0) {
-        // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4.
-        // First needed by the first epilogue: computed while the first MMAs run.
-        float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
-#pragma unroll 8
-        for (int e = 0; e < 32; ++e) {
-          const float wc = __ldg(p.au_wc + e * 32 + lane);
-          acc0 = fmaf(cand[warp_w * 32 + e], wc, acc0);
-          acc1 = fmaf(cand[(warp_w + 4) * 32 + e], wc, acc1);
-        }
-        cst[warp_w * 32 + lane] = acc0;
-        cst[(warp_w + 4) * 32 + lane] = acc1;
-      }
+      if (tile == 0 && !cst_early) compute_cst();
       // ---- prefetch the next tile's history rows while the MMAs run
       {
         const int idn = fix_id(raw1);

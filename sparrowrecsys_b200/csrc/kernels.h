@@ -156,6 +156,8 @@ cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, fl
                                 cudaStream_t s);
 cudaError_t launch_umma_selftest(const float* A, const float* B, float* D, int N, int KB,
                                  int a_in_tmem, cudaStream_t s);
+cudaError_t launch_umma_bench(unsigned long long* out, int N, int n_mma, int a_in_tmem, int two_acc,
+                              int uniform, cudaStream_t s);
 cudaError_t launch_cosine(const float* q, const float* c, int n, int dim, float* out,
                           cudaStream_t s);
 

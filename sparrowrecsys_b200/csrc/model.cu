@@ -995,6 +995,21 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   return SRS_OK;
 }
 
+int srs_debug_umma_bench(int32_t N, int32_t n_mma, int32_t a_in_tmem, int32_t two_acc,
+                         int32_t device, uint64_t* out2) {
+  if (!out2 || (N != 32 && N != 64 && N != 128) || n_mma < 1 || n_mma > 4096)
+    return fail(SRS_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 16));
+  cudaError_t e = launch_umma_bench(d, N, n_mma, a_in_tmem & 1, two_acc & 1, (two_acc >> 1) & 1, nullptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "umma bench failed: %s", cudaGetErrorString(e));
+  return SRS_OK;
+}
+
 int srs_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t k_blocks,
                       int32_t a_in_tmem, int32_t device) {
   if (!A || !B || !D) return fail(SRS_ERR_INVALID, "null pointer");

@@ -116,6 +116,19 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
   return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }
 
+// One lane of a converged warp (warp-uniform control flow around it keeps descriptor math on
+// the uniform datapath - a divergent `if (tid == 0)` forces every tcgen05.mma operand through
+// R2UR and costs ~100 cycles per instruction, measured with srs_debug_umma_bench).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue (one thread) -----------------------------------------------------------------
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
