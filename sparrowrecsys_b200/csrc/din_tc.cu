@@ -48,8 +48,8 @@ constexpr int kNoPair = INT_MIN;         // sentinel: this thread has no (row, p
 // tensor-memory map of one worker (128 columns)
 constexpr uint32_t TM_A_HI = 0;          // 32 cols: bf16 pairs of [h | h*c], hi halves
 constexpr uint32_t TM_A_LO = 32;         // 32 cols: lo halves
-constexpr uint32_t TM_D = 64;            // 32 cols: activation-unit accumulators; worker 0: top layer 1
-constexpr uint32_t TM_HS = 96;           // 32 cols: fp32 stash of h for pooling; worker 0: top layer 2
+constexpr uint32_t TM_D = 64;            // 64 cols: accumulators, N-stacked: [A.Bhi (32) | A.Blo (32)];
+                                         //          worker 0: top layer 1, worker 1: top layer 2
 
 // shared-memory image (bulk-copied from global; built by build_din_tc in model.cu)
 constexpr uint32_t IMG_AUB_HI = 0;                       // [32 units][64 k] bf16, SW128
@@ -63,10 +63,10 @@ constexpr uint32_t WS_W_STRIDE = 6144;
 constexpr uint32_t WS_CAND = 0;                          // f32 [8][32]        (worker, phase 0/1)
 constexpr uint32_t WS_CST = 1024;                        // f32 [8][32]        (worker, phase 0/1)
 constexpr uint32_t WS_PART = 2048;                       // f32 [8][4][32]     (worker, phase 1)
-constexpr uint32_t WS_XB_HI = 0;                         // 3 K blocks x [32 rows][64 k] bf16 (phase 2)
-constexpr uint32_t WS_XB_LO = 12288;
-constexpr uint32_t WS_H1_HI = 0;                         // 2 K blocks x [32 rows][64 k]; after layer 1
-constexpr uint32_t WS_H1_LO = 8192;
+// operand tiles of phase 2 are N-stacked per K block: [32 rows hi | 32 rows lo] x 128 B = 8 KB,
+// so one MMA with N = 64 multiplies a weight tile by both halves of the activations
+constexpr uint32_t WS_XB = 0;                            // 3 K blocks x 8 KB (phase 2)
+constexpr uint32_t WS_H1 = 0;                            // 2 K blocks x 8 KB; after layer 1
 constexpr uint32_t WS_RED = 16384;                       // f32 [64][32]; after layer 1
 constexpr uint32_t WS_NUMS = 24576;                      // f32 [32][8]
 constexpr uint32_t WS_ZP = 25600;                        // f32 [16][32] final partial sums
@@ -87,14 +87,13 @@ __device__ __forceinline__ void wg_sync(int wg) {
   asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
 }
 
-// write 4 consecutive K elements (col % 4 == 0) of row `row` into a bf16 hi/lo SW128 operand
-// whose K blocks are `block_bytes` apart
-__device__ __forceinline__ void store_x4(uint8_t* hi, uint8_t* lo, uint32_t block_bytes, int block,
-                                         int row, int col, float4 v) {
-  const uint32_t off = block * block_bytes + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
+// write 4 consecutive K elements (col % 4 == 0) of row `row` (0..31) into an N-stacked bf16
+// operand: K block `block` is 8 KB, hi halves in rows 0..31, lo halves in rows 32..63
+__device__ __forceinline__ void store_x4(uint8_t* tile, int block, int row, int col, float4 v) {
+  const uint32_t off = block * 8192u + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
   const Split2 s0 = split_pack(v.x, v.y), s1 = split_pack(v.z, v.w);
-  *reinterpret_cast<uint2*>(hi + off) = make_uint2(s0.hi, s1.hi);
-  *reinterpret_cast<uint2*>(lo + off) = make_uint2(s0.lo, s1.lo);
+  *reinterpret_cast<uint2*>(tile + off) = make_uint2(s0.hi, s1.hi);
+  *reinterpret_cast<uint2*>(tile + off + 4096u) = make_uint2(s0.lo, s1.lo);   // row + 32: same swizzle phase
 }
 
 __device__ __forceinline__ int f32_roundtrip_id(int id) {   // DIN.py:95,125: ids pass through float32
@@ -175,9 +174,11 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     L.raw1 = raw_id(row0, 1);
     return L;
   };
-  GroupLoads pre = issue_loads(blockIdx.x);             // ids come from HBM: start before the prologue
-
   // ---- prologue ---------------------------------------------------------------------
+  // Programmatic dependent launch: the next launch in the stream may start its own prologue
+  // (TMEM allocation, barrier init, weight image copy - nothing that depends on this launch)
+  // as soon as an SM frees up; it reads no input before its griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid < 32) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&wbar, 1);
@@ -191,6 +192,8 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     for (uint32_t off = 8192; off < IMG_PQ; off += 32768u)
       bulk_g2s(img + off, p.image + off, min(32768u, IMG_PQ - off), &wbar);
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
+  GroupLoads pre = issue_loads(blockIdx.x);             // ids come from HBM: in flight during the sync
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   uint32_t phase = 0, cphase = 0;
   bool weights_ready = false;
 
-  const uint32_t idesc_au = idesc_bf16(128, 32), idesc_top = idesc_bf16(128, kTcSG);
+  const uint32_t idesc_au = idesc_bf16(128, 64), idesc_top = idesc_bf16(128, 2 * kTcSG);
   const uint32_t s_img = smem_u32(img), s_cs = smem_u32(cs_base);
 
   auto fix_id = [&](int raw_v) -> int {
@@ -276,19 +279,10 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       int rs, cq, t;
       pair_of(tile, rs, cq, t);
       const bool valid = valid_nxt;
-      // ---- A operand [h | h*c] as bf16 hi / lo (two K elements per column) + fp32 stash of h
+      // ---- A operand [h | h*c] as bf16 hi / lo (two K elements per column)
       {
         const float* c = cand + rs * 32;
         uint32_t ahi[16], alo[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          ahi[4 * q] = __float_as_uint(hn[q].x); ahi[4 * q + 1] = __float_as_uint(hn[q].y);
-          ahi[4 * q + 2] = __float_as_uint(hn[q].z); ahi[4 * q + 3] = __float_as_uint(hn[q].w);
-          alo[4 * q] = __float_as_uint(hn[q + 4].x); alo[4 * q + 1] = __float_as_uint(hn[q + 4].y);
-          alo[4 * q + 2] = __float_as_uint(hn[q + 4].z); alo[4 * q + 3] = __float_as_uint(hn[q + 4].w);
-        }
-        tmem_st16(tbase + TM_HS + lane_base, ahi);
-        tmem_st16(tbase + TM_HS + 16 + lane_base, alo);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const Split2 s0 = split_pack(hn[q].x, hn[q].y), s1 = split_pack(hn[q].z, hn[q].w);
@@ -317,27 +311,20 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       wg_sync(wg);
       if (tile == 1) TC_TRACE(22);
       if (tw == 0) {
+        // B operand N-stacked: rows 0..31 = Bhi, rows 32..63 = Blo  ->  D[:, :32] = A.Bhi, D[:, 32:] = A.Blo;
+        // two MMAs per K step (A hi, A lo) instead of three
         tc_fence_after();
-        const uint64_t bh = smem_desc_sw128(s_img + IMG_AUB_HI), bl = smem_desc_sw128(s_img + IMG_AUB_LO);
+        const uint64_t bst = smem_desc_sw128(s_img + IMG_AUB_HI);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ts(tbase + TM_D, tbase + TM_A_HI + 8 * ks, bh + 2 * ks, idesc_au, ks > 0);
-          mma_ts(tbase + TM_D, tbase + TM_A_LO + 8 * ks, bh + 2 * ks, idesc_au, 1);
-          mma_ts(tbase + TM_D, tbase + TM_A_HI + 8 * ks, bl + 2 * ks, idesc_au, 1);
+          mma_ts(tbase + TM_D, tbase + TM_A_HI + 8 * ks, bst + 2 * ks, idesc_au, ks > 0);
+          mma_ts(tbase + TM_D, tbase + TM_A_LO + 8 * ks, bst + 2 * ks, idesc_au, 1);
         }
         mma_commit(my_bar);
       }
       __syncwarp();
       if (tile == 1) TC_TRACE(23);
       if (tile == 0 && !cst_early) compute_cst();
-      // ---- prefetch the next tile's history rows while the MMAs run
-      {
-        const int idn = fix_id(raw1);
-        valid_nxt = idn >= 0;
-        load_row(tile + 1 < n_tiles ? idn : -1, hn);
-        raw1 = raw0;
-        raw0 = raw_id(row0, tile + 3);
-      }
       if (tile == 1) TC_TRACE(24);
       mbar_wait(my_bar, phase);
       phase ^= 1;
@@ -345,42 +332,57 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       if (tile == 0) wg_sync(wg);                       // cst of all 8 rows is in place
       __syncwarp();
       tc_fence_after();
-      uint32_t d[32];
-      tmem_ld32(tbase + TM_D + lane_base, d);
-      tmem_ld_wait();
-      // ---- epilogue: + cst, PReLU (alpha per position) and Dense(1) folded into two tables
-      //      sum_j wout_j max(v,0) + alpha_tj wout_j min(v,0) = sum_j v P_tj + |v| Q_tj
+      // ---- epilogue: v = A.Bhi + A.Blo + cst; PReLU (alpha per position) and Dense(1) folded into
+      //      two tables: sum_j wout_j max(v,0) + alpha_tj wout_j min(v,0) = sum_j v P_tj + |v| Q_tj
       float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
       {
         const float* cs = cst + rs * 32;
         const float* pt = Ptab + t;
         const float* qt = Qtab + t;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
-          const float2 v01 = add2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])),
-                                  make_float2(c4.x, c4.y));
-          const float2 v23 = add2(make_float2(__uint_as_float(d[j + 2]), __uint_as_float(d[j + 3])),
-                                  make_float2(c4.z, c4.w));
-          sa = fma2(v01, make_float2(pt[j * TP], pt[(j + 1) * TP]), sa);
-          sb = fma2(v23, make_float2(pt[(j + 2) * TP], pt[(j + 3) * TP]), sb);
-          sa = fma2(make_float2(fabsf(v01.x), fabsf(v01.y)), make_float2(qt[j * TP], qt[(j + 1) * TP]), sa);
-          sb = fma2(make_float2(fabsf(v23.x), fabsf(v23.y)), make_float2(qt[(j + 2) * TP], qt[(j + 3) * TP]), sb);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t dh[16], dl[16];
+          tmem_ld16(tbase + TM_D + 16 * half + lane_base, dh);
+          tmem_ld16(tbase + TM_D + 32 + 16 * half + lane_base, dl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 4) {
+            const int j = 16 * half + jj;
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
+            float2 v01 = add2(make_float2(__uint_as_float(dh[jj]), __uint_as_float(dh[jj + 1])),
+                              make_float2(__uint_as_float(dl[jj]), __uint_as_float(dl[jj + 1])));
+            float2 v23 = add2(make_float2(__uint_as_float(dh[jj + 2]), __uint_as_float(dh[jj + 3])),
+                              make_float2(__uint_as_float(dl[jj + 2]), __uint_as_float(dl[jj + 3])));
+            v01 = add2(v01, make_float2(c4.x, c4.y));
+            v23 = add2(v23, make_float2(c4.z, c4.w));
+            sa = fma2(v01, make_float2(pt[j * TP], pt[(j + 1) * TP]), sa);
+            sb = fma2(v23, make_float2(pt[(j + 2) * TP], pt[(j + 3) * TP]), sb);
+            sa = fma2(make_float2(fabsf(v01.x), fabsf(v01.y)), make_float2(qt[j * TP], qt[(j + 1) * TP]), sa);
+            sb = fma2(make_float2(fabsf(v23.x), fabsf(v23.y)), make_float2(qt[(j + 2) * TP], qt[(j + 3) * TP]), sb);
+          }
         }
       }
       const float s = (sa.x + sa.y) + (sb.x + sb.y);
       if (tile == 1) TC_TRACE(26);
       const float w = valid ? 1.f / (1.f + __expf(-s)) : 0.f;
+      // ---- the next tile's history rows are requested now and land during the pooling
+      float4 hnext[8];
+      {
+        const int idn = fix_id(raw1);
+        valid_nxt = idn >= 0;
+        load_row(tile + 1 < n_tiles ? idn : -1, hnext);
+        raw1 = raw0;
+        raw0 = raw_id(row0, tile + 3);
+      }
       // ---- pooling: out[e = lane] = sum over the chunk's 32 positions of w_t * h_t[e]
-      tmem_ld32(tbase + TM_HS + lane_base, d);
-      tmem_ld_wait();
       float h[32];
       {
         const float2 w2 = make_float2(w, w);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float2 v = mul2(make_float2(__uint_as_float(d[e]), __uint_as_float(d[e + 1])), w2);
-          h[e] = v.x; h[e + 1] = v.y;
+        for (int q = 0; q < 8; ++q) {
+          const float2 a = mul2(make_float2(hn[q].x, hn[q].y), w2);
+          const float2 bq = mul2(make_float2(hn[q].z, hn[q].w), w2);
+          h[4 * q] = a.x; h[4 * q + 1] = a.y; h[4 * q + 2] = bq.x; h[4 * q + 3] = bq.y;
         }
       }
 #pragma unroll
@@ -402,6 +404,8 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const float keep = up ? h[1] : h[0];
         h[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) hn[q] = hnext[q];
       part[(rs * kTcMaxCPR + cq) * 32 + lane] = h[0];
       if (tile < 24) TC_TRACE(4 + tile);
     }
@@ -420,22 +424,21 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (srs < kTcG) {
-      uint8_t* xh = cs_base + WS_XB_HI;
-      uint8_t* xl = cs_base + WS_XB_LO;
+      uint8_t* xb = cs_base + WS_XB;
       const int xr = wg * kTcG + srs;                    // row slot in the super-group
-      store_x4(xh, xl, 4096, 0, xr, 4 * sq, ug4);        // K block 0: [userGenre1 | userId]
-      store_x4(xh, xl, 4096, 0, xr, 32 + 4 * sq, u4);
-      store_x4(xh, xl, 4096, 1, xr, 4 * sq, pl);         // K block 1: [pooled | candidate]
-      store_x4(xh, xl, 4096, 1, xr, 32 + 4 * sq, c4s);
-      store_x4(xh, xl, 4096, 2, xr, 4 * sq, mg4);        // K block 2: [movieGenre1 | 0]
-      const uint32_t zoff = 2 * 4096u + sw128_offset(xr, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
-      *reinterpret_cast<uint2*>(xh + zoff) = make_uint2(0u, 0u);
-      *reinterpret_cast<uint2*>(xl + zoff) = make_uint2(0u, 0u);
+      store_x4(xb, 0, xr, 4 * sq, ug4);                  // K block 0: [userGenre1 | userId]
+      store_x4(xb, 0, xr, 32 + 4 * sq, u4);
+      store_x4(xb, 1, xr, 4 * sq, pl);                   // K block 1: [pooled | candidate]
+      store_x4(xb, 1, xr, 32 + 4 * sq, c4s);
+      store_x4(xb, 2, xr, 4 * sq, mg4);                  // K block 2: [movieGenre1 | 0]
+      const uint32_t zoff = 2 * 8192u + sw128_offset(xr, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
+      *reinterpret_cast<uint2*>(xb + zoff) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(xb + zoff + 4096u) = make_uint2(0u, 0u);
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    const uint32_t tD1 = tmem_slot + TM_D, tD2 = tmem_slot + TM_HS;   // worker 0's columns
+    const uint32_t tD1 = tmem_slot + TM_D, tD2 = tmem_slot + 128 + TM_D;   // workers 0 / 1 accumulators
     if (tid == 0) {
       tc_fence_after();
       uint32_t acc = 0;
@@ -443,14 +446,12 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       for (int kb = 0; kb < 3; ++kb) {
         const uint64_t ah = smem_desc_sw128(s_img + IMG_W1_HI + kb * 16384);
         const uint64_t al = smem_desc_sw128(s_img + IMG_W1_LO + kb * 16384);
-        const uint64_t xh = smem_desc_sw128(s_cs + WS_XB_HI + kb * 4096);
-        const uint64_t xl = smem_desc_sw128(s_cs + WS_XB_LO + kb * 4096);
+        const uint64_t xs = smem_desc_sw128(s_cs + WS_XB + kb * 8192);     // [X hi | X lo], N = 64
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tD1, ah + 2 * ks, xh + 2 * ks, idesc_top, acc);
+          mma_ss(tD1, ah + 2 * ks, xs + 2 * ks, idesc_top, acc);           // W1hi.(Xhi | Xlo)
           acc = 1;
-          mma_ss(tD1, al + 2 * ks, xh + 2 * ks, idesc_top, 1);
-          mma_ss(tD1, ah + 2 * ks, xl + 2 * ks, idesc_top, 1);
+          mma_ss(tD1, al + 2 * ks, xs + 2 * ks, idesc_top, 1);             // W1lo.(Xhi | Xlo)
         }
       }
       mma_commit(&cbar);
@@ -467,27 +468,28 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     tc_fence_after();
     TC_TRACE(30);
     {
-      uint32_t d[8];
-      tmem_ld8(tD1 + 8 * wg + lane_base, d);
+      uint32_t d[8], d2[8];
+      tmem_ld8(tD1 + 8 * wg + lane_base, d);             // W1 . X hi
+      tmem_ld8(tD1 + 32 + 8 * wg + lane_base, d2);       // W1 . X lo
       tmem_ld_wait();
-      // layer-1 epilogue: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo), which
-      // overlays the X operand (its MMAs have completed)
-      const uint32_t koff = (uint32_t)(tw >> 6) * 4096u;
+      // layer-1 epilogue: bias + numerics (fp32) + PReLU -> H1 operand (bf16 hi/lo, N-stacked),
+      // which overlays the X operand (its MMAs have completed)
+      const uint32_t koff = (uint32_t)(tw >> 6) * 8192u;
       const uint32_t chunk = (tw & 63) >> 3, within = (tw & 7) * 2;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int xr = wg * kTcG + r;
         const float4 n0 = *reinterpret_cast<const float4*>(nums + xr * 8);
         const float4 n1 = *reinterpret_cast<const float4*>(nums + xr * 8 + 4);
-        float v = __uint_as_float(d[r]) + b1;
+        float v = (__uint_as_float(d[r]) + __uint_as_float(d2[r])) + b1;
         v = fmaf(n0.x, w1n[0], v); v = fmaf(n0.y, w1n[1], v); v = fmaf(n0.z, w1n[2], v);
         v = fmaf(n0.w, w1n[3], v); v = fmaf(n1.x, w1n[4], v); v = fmaf(n1.y, w1n[5], v);
         v = fmaf(n1.z, w1n[6], v);
         v = v > 0.f ? v : a1 * v;
         const uint32_t off = koff + sw128_offset(xr, chunk) + within;
         const __nv_bfloat16 vh = __float2bfloat16_rn(v);
-        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1_HI + off) = vh;
-        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1_LO + off) = __float2bfloat16_rn(v - __bfloat162float(vh));
+        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1 + off) = vh;
+        *reinterpret_cast<__nv_bfloat16*>(cs_base + WS_H1 + off + 4096u) = __float2bfloat16_rn(v - __bfloat162float(vh));
       }
     }
     fence_async_smem();
@@ -499,13 +501,11 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         const uint64_t a = smem_desc_sw128(s_img + IMG_W2 + kb * 16384);
-        const uint64_t hh = smem_desc_sw128(s_cs + WS_H1_HI + kb * 4096);
-        const uint64_t hl = smem_desc_sw128(s_cs + WS_H1_LO + kb * 4096);
+        const uint64_t hs = smem_desc_sw128(s_cs + WS_H1 + kb * 8192);      // [H1 hi | H1 lo], N = 64
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          mma_ss(tD2, a + 2 * ks, hh + 2 * ks, idesc_top, acc);
+          mma_ss(tD2, a + 2 * ks, hs + 2 * ks, idesc_top, acc);            // (W2hi ; W2lo).(H1hi | H1lo)
           acc = 1;
-          mma_ss(tD2, a + 2 * ks, hl + 2 * ks, idesc_top, 1);
         }
       }
       mma_commit(&cbar);
@@ -517,9 +517,12 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     __syncwarp();
     tc_fence_after();
     {
-      uint32_t d[8];
+      uint32_t d[8], d2[8];
       tmem_ld8(tD2 + 8 * wg + lane_base, d);
+      tmem_ld8(tD2 + 32 + 8 * wg + lane_base, d2);
       tmem_ld_wait();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) d[r] = __float_as_uint(__uint_as_float(d[r]) + __uint_as_float(d2[r]));
       float* red = reinterpret_cast<float*>(cs_base + WS_RED);    // [64 units][32 rows]
       float* zp = reinterpret_cast<float*>(cs_base + WS_ZP);      // [16][32]
       if (tw >= 64) {                                              // lo halves of W2 -> smem
@@ -580,9 +583,18 @@ template <int CPR>
 static cudaError_t launch_din_tc_t(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
   const int n_sg = (b.B + kTcSG - 1) / kTcSG;
   const int grid = n_sg < p.num_sms ? n_sg : p.num_sms;
-  din_tc_kernel<CPR><<<grid, kTcWG * 128, din_tc_smem_bytes(CPR), s>>>(p, b);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcWG * 128);
+  cfg.dynamicSmemBytes = din_tc_smem_bytes(CPR);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see the kernel prologue
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ++g_launch_count;
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, din_tc_kernel<CPR>, p, b);
 }
 
 cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s) {
