@@ -324,6 +324,16 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       }
       __syncwarp();
       if (tile == 1) TC_TRACE(23);
+      // ---- the next tile's history rows are requested now: they land while the MMAs run and
+      //      the accumulators are read back
+      float4 hnext[8];
+      {
+        const int idn = fix_id(raw1);
+        valid_nxt = idn >= 0;
+        load_row(tile + 1 < n_tiles ? idn : -1, hnext);
+        raw1 = raw0;
+        raw0 = raw_id(row0, tile + 3);
+      }
       if (tile == 0 && !cst_early) compute_cst();
       if (tile == 1) TC_TRACE(24);
       mbar_wait(my_bar, phase);
@@ -365,15 +375,6 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       const float s = (sa.x + sa.y) + (sb.x + sb.y);
       if (tile == 1) TC_TRACE(26);
       const float w = valid ? 1.f / (1.f + __expf(-s)) : 0.f;
-      // ---- the next tile's history rows are requested now and land during the pooling
-      float4 hnext[8];
-      {
-        const int idn = fix_id(raw1);
-        valid_nxt = idn >= 0;
-        load_row(tile + 1 < n_tiles ? idn : -1, hnext);
-        raw1 = raw0;
-        raw0 = raw_id(row0, tile + 3);
-      }
       // ---- pooling: out[e = lane] = sum over the chunk's 32 positions of w_t * h_t[e]
       float h[32];
       {
