@@ -57,7 +57,9 @@ constexpr uint32_t IMG_AUB_LO = 4096;
 constexpr uint32_t IMG_W1_HI = 8192;                     // 3 K blocks x [128 units][64 k]
 constexpr uint32_t IMG_W1_LO = IMG_W1_HI + 3 * 16384;
 constexpr uint32_t IMG_W2 = IMG_W1_LO + 3 * 16384;       // 2 K blocks x [64 hi | 64 lo units][64 k]
-constexpr uint32_t IMG_PQ = IMG_W2 + 2 * 16384;          // f32 P[32 units][TP], then Q[32][TP]; TP = CPR*32
+constexpr uint32_t IMG_PQ = IMG_W2 + 2 * 16384;          // f32 [TP positions][68]: per position 16 x (P_2m, P_2m+1,
+                                                         // Q_2m, Q_2m+1) + 4 pad floats (conflict-free LDS.128)
+constexpr uint32_t kPqStride = 68;                       // floats per position row
 // CTA scratch (28 KB).  Phase 0/1 view: worker w owns 6 KB at w*6144; phase 2 overlays all 24 KB.
 constexpr uint32_t WS_W_STRIDE = 6144;
 constexpr uint32_t WS_CAND = 0;                          // f32 [8][32]        (worker, phase 0/1)
@@ -81,7 +83,7 @@ __device__ unsigned long long g_din_tc_trace[40];
     if (p.trace && blockIdx.x == 0 && tid == 0) g_din_tc_trace[slot] = clock64();  \
   } while (0)
 
-__host__ __device__ inline uint32_t din_tc_image_bytes(int cpr) { return IMG_PQ + 2u * 32u * cpr * 32u * 4u; }
+__host__ __device__ inline uint32_t din_tc_image_bytes(int cpr) { return IMG_PQ + cpr * 32u * kPqStride * 4u; }
 
 __device__ __forceinline__ void wg_sync(int wg) {
   asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
@@ -131,8 +133,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   uint8_t* ws = cs_base + wg * WS_W_STRIDE;                      // this worker's phase-0/1 view
   constexpr int TP = CPR * 32;
   const int T = p.T;
-  const float* Ptab = reinterpret_cast<const float*>(img + IMG_PQ);
-  const float* Qtab = Ptab + 32 * TP;
+  const float4* PQtab = reinterpret_cast<const float4*>(img + IMG_PQ);
   float* cand = reinterpret_cast<float*>(ws + WS_CAND);
   float* cst = reinterpret_cast<float*>(ws + WS_CST);
   float* part = reinterpret_cast<float*>(ws + WS_PART);
@@ -347,8 +348,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
       {
         const float* cs = cst + rs * 32;
-        const float* pt = Ptab + t;
-        const float* qt = Qtab + t;
+        const float4* pq = PQtab + t * (kPqStride / 4);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t dh[16], dl[16];
@@ -359,16 +359,17 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
           for (int jj = 0; jj < 16; jj += 4) {
             const int j = 16 * half + jj;
             const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
+            const float4 pq0 = pq[j >> 1], pq1 = pq[(j >> 1) + 1];   // (P_j, P_j+1, Q_j, Q_j+1), next pair
             float2 v01 = add2(make_float2(__uint_as_float(dh[jj]), __uint_as_float(dh[jj + 1])),
                               make_float2(__uint_as_float(dl[jj]), __uint_as_float(dl[jj + 1])));
             float2 v23 = add2(make_float2(__uint_as_float(dh[jj + 2]), __uint_as_float(dh[jj + 3])),
                               make_float2(__uint_as_float(dl[jj + 2]), __uint_as_float(dl[jj + 3])));
             v01 = add2(v01, make_float2(c4.x, c4.y));
             v23 = add2(v23, make_float2(c4.z, c4.w));
-            sa = fma2(v01, make_float2(pt[j * TP], pt[(j + 1) * TP]), sa);
-            sb = fma2(v23, make_float2(pt[(j + 2) * TP], pt[(j + 3) * TP]), sb);
-            sa = fma2(make_float2(fabsf(v01.x), fabsf(v01.y)), make_float2(qt[j * TP], qt[(j + 1) * TP]), sa);
-            sb = fma2(make_float2(fabsf(v23.x), fabsf(v23.y)), make_float2(qt[(j + 2) * TP], qt[(j + 3) * TP]), sb);
+            sa = fma2(v01, make_float2(pq0.x, pq0.y), sa);
+            sb = fma2(v23, make_float2(pq1.x, pq1.y), sb);
+            sa = fma2(make_float2(fabsf(v01.x), fabsf(v01.y)), make_float2(pq0.z, pq0.w), sa);
+            sb = fma2(make_float2(fabsf(v23.x), fabsf(v23.y)), make_float2(pq1.z, pq1.w), sb);
           }
         }
       }

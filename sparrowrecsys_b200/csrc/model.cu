@@ -548,7 +548,8 @@ int build_din_tc(Builder& B) {
   // image offsets mirror the constants in din_tc.cu
   const uint32_t IMG_AUB_HI = 0, IMG_AUB_LO = 4096, IMG_W1_HI = 8192, IMG_W1_LO = IMG_W1_HI + 3 * 16384,
                  IMG_W2 = IMG_W1_LO + 3 * 16384, IMG_PQ = IMG_W2 + 2 * 16384;
-  const uint32_t bytes = IMG_PQ + 2u * 32u * TP * 4u;
+  const uint32_t kPqStride = 68;
+  const uint32_t bytes = IMG_PQ + (uint32_t)TP * kPqStride * 4u;
   std::vector<uint8_t> img(bytes, 0);
   // activation unit B operand: row j = [ (Wsub+Wh)[e][j], e<32 | Wp[e][j], e<32 ]
   auto au_get = [&](int j, int k) -> float {
@@ -584,15 +585,16 @@ int build_din_tc(Builder& B) {
             memcpy(img.data() + IMG_W2 + (size_t)kb * 16384 + sw128_off(r, c) + i * 2, &v, 2);
           }
   }
-  // PReLU + Dense(1) folded into two tables, transposed [unit j][position t], zero beyond T:
+  // PReLU + Dense(1) folded into two tables, one 68-float row per position t (zero beyond T):
   //   wout_j max(v,0) + alpha_tj wout_j min(v,0) = v P_tj + |v| Q_tj
-  float* P = reinterpret_cast<float*>(img.data() + IMG_PQ);
-  float* Q = P + (size_t)32 * TP;
-  for (int j = 0; j < A; ++j)
-    for (int t = 0; t < T; ++t) {
+  // stored as 16 x (P_2m, P_2m+1, Q_2m, Q_2m+1) so one 128-bit load feeds two packed FMAs
+  float* PQ = reinterpret_cast<float*>(img.data() + IMG_PQ);
+  for (int t = 0; t < T; ++t)
+    for (int j = 0; j < A; ++j) {
       const float wo = auo[j], aw = alpha[(size_t)t * A + j] * auo[j];
-      P[(size_t)j * TP + t] = 0.5f * (wo + aw);
-      Q[(size_t)j * TP + t] = 0.5f * (wo - aw);
+      float* cell = PQ + (size_t)t * kPqStride + (j >> 1) * 4 + (j & 1);
+      cell[0] = 0.5f * (wo + aw);
+      cell[2] = 0.5f * (wo - aw);
     }
   uint8_t* d_img = nullptr;
   cudaError_t e = cudaMalloc(&d_img, bytes);
