@@ -70,7 +70,8 @@ __device__ __forceinline__ int checked_id(int id, int limit, int* err_flag) {
 //        than staged)
 // Thread (cx, ry) owns TM rows x TN columns; lanes of a warp sweep the columns so W
 // loads are contiguous 128-bit loads and xs loads are broadcasts.
-template <int R, int N, int TM, int TN>
+// W_SMEM: W points into shared memory (staged by stage_weights below) instead of global.
+template <int R, int N, int TM, int TN, bool W_SMEM = false>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ldx, int K,
                                             const float* __restrict__ W,
                                             const float* __restrict__ bias, int act,
@@ -96,7 +97,9 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ld
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-    for (int j = 0; j < TN / 4; ++j) wn[kk][j] = ldg4(W + (size_t)kk * N + col0 + 4 * j);
+    for (int j = 0; j < TN / 4; ++j)
+      wn[kk][j] = W_SMEM ? *reinterpret_cast<const float4*>(W + (size_t)kk * N + col0 + 4 * j)
+                         : ldg4(W + (size_t)kk * N + col0 + 4 * j);
   for (int k = 0; k < K; k += 4) {
     float4 xv[TM];
     float4 wc[4][TN / 4];
@@ -108,7 +111,9 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ld
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int j = 0; j < TN / 4; ++j) wn[kk][j] = ldg4(W + (size_t)(k + 4 + kk) * N + col0 + 4 * j);
+        for (int j = 0; j < TN / 4; ++j)
+          wn[kk][j] = W_SMEM ? *reinterpret_cast<const float4*>(W + (size_t)(k + 4 + kk) * N + col0 + 4 * j)
+                             : ldg4(W + (size_t)(k + 4 + kk) * N + col0 + 4 * j);
     }
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -140,6 +145,18 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ xs, int ld
       ys[r * ldy + col0 + j] = v;
     }
   }
+}
+
+// Asynchronous global -> shared copy of a dense weight array (floats multiple of 4, 16-byte
+// aligned both sides) by the whole CTA: the per-K-step L2 latency of reading weights in place
+// becomes one bulk latency that overlaps the embedding gathers.  Pair with stage_wait().
+__device__ __forceinline__ void stage_weights(float* dst_smem, const float* __restrict__ src, int n_floats) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  for (int i = threadIdx.x * 4; i < n_floats; i += kThreads * 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // z[r] = sum_k xs[r][k] * w[k]   one warp per row, rows strided over the 8 warps.

@@ -39,8 +39,12 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
   float* H1 = Fs + R * LDF;            // [R][LDH]
   float* H2 = H1 + R * LDH;            // [R][LDH]
   float* Ds = H2 + R * LDH;            // [R][4]    the four FM dots
+  float* W1s = Ds + R * 4;             // [KP][64] staged deep kernels
+  float* W2s = W1s + KP * 64;          // [64][64]
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * R;
+  stage_weights(W1s, p.W1, KP * 64);
+  stage_weights(W2s, p.W2, 64 * 64);
 
   for (int i = tid; i < R * 6 * Q; i += kThreads) {
     const int q = i % Q;
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
     if (j < kNumNumerics && row < b.B) v = __ldg(b.numerics + row * kNumNumerics + j);
     Xs[r * LDX + 2 * EP + j] = v;
   }
+  stage_wait();
   __syncthreads();
   if (tid < R * 4) {  // four dots per row (DeepFM.py:100-103): <item,user> <ig,ug> <ig,user> <item,ug>
     const int r = tid >> 2, d = tid & 3;
@@ -85,9 +90,9 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
     for (int k = 0; k < EP; ++k) s = fmaf(a[k], c[k], s);
     Ds[r * 4 + d] = s;
   }
-  dense_layer<R, 64, 1, 8>(Xs, LDX, KP, p.W1, p.b1, ACT_RELU, nullptr, H1, LDH);
+  dense_layer<R, 64, 1, 8, true>(Xs, LDX, KP, W1s, p.b1, ACT_RELU, nullptr, H1, LDH);
   __syncthreads();
-  dense_layer<R, 64, 1, 8>(H1, LDH, 64, p.W2, p.b2, ACT_RELU, nullptr, H2, LDH);
+  dense_layer<R, 64, 1, 8, true>(H1, LDH, 64, W2s, p.b2, ACT_RELU, nullptr, H2, LDH);
   __syncthreads();
   row_dot<R>(H2, LDH, 64, p.wdeep, [&](int r, float s) {
     const int row = row0 + r;
@@ -113,7 +118,8 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
 
 template <int EP>
 static size_t deepfm_smem() {
-  return (size_t)kFm1Rows * ((2 * EP + kNumPad + 4) + (4 * EP + 4) + 68 + 68 + 4) * sizeof(float);
+  return ((size_t)kFm1Rows * ((2 * EP + kNumPad + 4) + (4 * EP + 4) + 68 + 68 + 4) +
+          (size_t)(2 * EP + kNumPad) * 64 + 64 * 64) * sizeof(float);
 }
 
 template <int EP>
@@ -154,8 +160,12 @@ __global__ void __launch_bounds__(kThreads) deepfm2_kernel(DeepFm2Params p, Batc
   float* Fs = Xs + R * LDX;         // [R][LDF]  five projected fields (DeepFM_v2.py:121)
   float* D1 = Fs + R * LDF;         // [R][LD1]
   float* D2 = D1 + R * LD1;         // [R][LD2]
+  float* Wds = D2 + R * LD2;        // [320][32] staged deep kernel
+  float* Wd1s = Wds + 5 * kProj * 32;   // [32][16]
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * R;
+  stage_weights(Wds, p.Wd, 5 * kProj * 32);
+  stage_weights(Wd1s, p.Wd1, 32 * 16);
 
   for (int i = tid; i < R * 4 * Q; i += kThreads) {
     const int q = i % Q;
@@ -190,9 +200,11 @@ __global__ void __launch_bounds__(kThreads) deepfm2_kernel(DeepFm2Params p, Batc
   dense_layer<R, kProj, 2, 8>(Xs + 4 * EP, LDX, kNumPad, p.proj_num, p.proj_num_b, ACT_NONE,
                               nullptr, Fs + 4 * kProj, LDF);
   __syncthreads();
-  dense_layer<R, 32, 1, 8>(Fs, LDF, 5 * kProj, p.Wd, p.bd, ACT_RELU, nullptr, D1, LD1);
+  stage_wait();
   __syncthreads();
-  dense_layer<R, 16, 1, 4>(D1, LD1, 32, p.Wd1, p.bd1, ACT_RELU, nullptr, D2, LD2);
+  dense_layer<R, 32, 1, 8, true>(Fs, LDF, 5 * kProj, Wds, p.bd, ACT_RELU, nullptr, D1, LD1);
+  __syncthreads();
+  dense_layer<R, 16, 1, 4, true>(D1, LD1, 32, Wd1s, p.bd1, ACT_RELU, nullptr, D2, LD2);
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -239,7 +251,8 @@ __global__ void __launch_bounds__(kThreads) deepfm2_kernel(DeepFm2Params p, Batc
 
 template <int EP>
 static size_t deepfm2_smem() {
-  return (size_t)kFmRows * ((4 * EP + kNumPad + 4) + (5 * kProj + 4) + 36 + 20) * sizeof(float);
+  return ((size_t)kFmRows * ((4 * EP + kNumPad + 4) + (5 * kProj + 4) + 36 + 20) + 5 * kProj * 32 + 32 * 16) *
+         sizeof(float);
 }
 
 template <int EP>

@@ -53,7 +53,7 @@ constexpr uint32_t TM_D = 64;            // 64 cols: accumulators, N-stacked: [A
 
 // shared-memory image (bulk-copied from global; built by build_din_tc in model.cu)
 constexpr uint32_t IMG_AUB_HI = 0;                       // [32 units][64 k] bf16, SW128
-constexpr uint32_t IMG_AUB_LO = 4096;
+// (lo halves follow at +4096: rows 32..63 of the N-stacked operand)
 constexpr uint32_t IMG_W1_HI = 8192;                     // 3 K blocks x [128 units][64 k]
 constexpr uint32_t IMG_W1_LO = IMG_W1_HI + 3 * 16384;
 constexpr uint32_t IMG_W2 = IMG_W1_LO + 3 * 16384;       // 2 K blocks x [64 hi | 64 lo units][64 k]
@@ -131,7 +131,6 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
   const uint32_t img_bytes = din_tc_image_bytes(CPR);
   uint8_t* cs_base = base + ((img_bytes + 1023u) & ~1023u);     // CTA scratch
   uint8_t* ws = cs_base + wg * WS_W_STRIDE;                      // this worker's phase-0/1 view
-  constexpr int TP = CPR * 32;
   const int T = p.T;
   const float4* PQtab = reinterpret_cast<const float4*>(img + IMG_PQ);
   float* cand = reinterpret_cast<float*>(ws + WS_CAND);

@@ -24,11 +24,17 @@ __global__ void __launch_bounds__(kThreads) embmlp_kernel(EmbMlpParams p, BatchV
   constexpr int LDX = KP + 4;
   constexpr int LDH = 128 + 4;
   static_assert(LDX >= LDH, "second hidden tile aliases the input tile");
+  constexpr bool STAGE_W1 = EP == 12;      // 64 KB: fits next to the tiles only for the reference shape
+  constexpr bool STAGE_W2 = EP <= 32;      // 64 KB
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;
   float* H1 = smem + R * LDX;
+  float* W2s = H1 + R * LDH;               // [128][128] if STAGE_W2
+  float* W1s = W2s + (STAGE_W2 ? 128 * 128 : 0);   // [KP][128] if STAGE_W1
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * R;
+  if (STAGE_W1) stage_weights(W1s, p.W1, KP * 128);
+  if (STAGE_W2) stage_weights(W2s, p.W2, 128 * 128);
 
   for (int i = tid; i < R * 10 * Q; i += kThreads) {
     const int q = i % Q;
@@ -65,11 +71,14 @@ __global__ void __launch_bounds__(kThreads) embmlp_kernel(EmbMlpParams p, BatchV
     if (j < kNumNumerics && row < b.B) v = __ldg(b.numerics + row * kNumNumerics + j);
     Xs[r * LDX + 10 * EP + j] = v;
   }
+  if (STAGE_W1 || STAGE_W2) stage_wait();
   __syncthreads();
-  dense_layer<R, 128, 4, 8>(Xs, LDX, KP, p.W1, p.b1, ACT_RELU, nullptr, H1, LDH);
+  if (STAGE_W1) dense_layer<R, 128, 4, 8, true>(Xs, LDX, KP, W1s, p.b1, ACT_RELU, nullptr, H1, LDH);
+  else dense_layer<R, 128, 4, 8>(Xs, LDX, KP, p.W1, p.b1, ACT_RELU, nullptr, H1, LDH);
   __syncthreads();
   float* H2 = Xs;
-  dense_layer<R, 128, 4, 8>(H1, LDH, 128, p.W2, p.b2, ACT_RELU, nullptr, H2, LDX);
+  if (STAGE_W2) dense_layer<R, 128, 4, 8, true>(H1, LDH, 128, W2s, p.b2, ACT_RELU, nullptr, H2, LDX);
+  else dense_layer<R, 128, 4, 8>(H1, LDH, 128, p.W2, p.b2, ACT_RELU, nullptr, H2, LDX);
   __syncthreads();
   row_dot<R>(H2, LDX, 128, p.w3, [&](int r, float s) {
     const int row = row0 + r;
@@ -88,7 +97,10 @@ __global__ void __launch_bounds__(kThreads) embmlp_kernel(EmbMlpParams p, BatchV
 
 template <int EP>
 static size_t embmlp_smem() {
-  return (size_t)kEmbRows * ((10 * EP + kNumPad + 4) + 132) * sizeof(float);
+  size_t floats = (size_t)kEmbRows * ((10 * EP + kNumPad + 4) + 132);
+  if (EP <= 32) floats += 128 * 128;                         // staged W2
+  if (EP == 12) floats += (size_t)(10 * EP + kNumPad) * 128;  // staged W1
+  return floats * sizeof(float);
 }
 
 template <int EP>

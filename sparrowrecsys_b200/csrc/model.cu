@@ -509,8 +509,6 @@ int build_din(Builder& B) {
 // ---- tensor-core DIN: shared-memory image ------------------------------------------------
 inline uint32_t f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 inline float u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
-inline uint16_t bf16_trunc_bits(float x) { return (uint16_t)(f2u(x) >> 16); }
-inline float bf16_trunc_val(float x) { return u2f(f2u(x) & 0xFFFF0000u); }
 inline uint16_t bf16_rn_bits(float x) {
   const uint32_t u = f2u(x);
   return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
