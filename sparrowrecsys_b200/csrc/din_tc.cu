@@ -98,6 +98,14 @@ __device__ __forceinline__ void store_x4(uint8_t* tile, int block, int row, int 
   *reinterpret_cast<uint2*>(tile + off + 4096u) = make_uint2(s0.lo, s1.lo);   // row + 32: same swizzle phase
 }
 
+// 256-bit read-only global load (sm_100 LDG.256): a 128-byte embedding row in 4 instructions,
+// half the L1 tag passes of 8 x LDG.128 for a gather in which every lane reads a different row
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 __device__ __forceinline__ int f32_roundtrip_id(int id) {   // DIN.py:95,125: ids pass through float32
   return __float2int_rz(__int2float_rn(id));
 }
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     if (id >= 0) {
       const float* src = p.movie + (size_t)id * 32;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] = ldg4(src + 4 * q);
+      for (int q = 0; q < 8; q += 2) ldg8(src + 4 * q, h[q], h[q + 1]);
     } else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
