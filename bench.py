@@ -459,8 +459,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {
                 "workload": workload_desc(args.workload, spec, B), "batch_per_gpu": B, "global_batch": world * B,
-                "parallelism": "dp%d: rows sharded by user-batch, weights replicated, no data-path "
-                               "collective%s" % (world, " + all-gather of scores" if gather_buf is not None else ""),
+                "parallelism": "dp%d: rows sharded by user-batch, weights replicated, %s"
+                               % (world, "NCCL all-gather of the scores after every step (--gather)"
+                                  if gather_buf is not None else "no data-path collective"),
                 "kernel": model.kernel_name, "launch": launch_mode,
                 "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB > 126 MB L2): ids/"
                       "numerics are read from HBM every step; embedding tables total %.1f MB (%s)"
