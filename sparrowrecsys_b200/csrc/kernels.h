@@ -46,6 +46,22 @@ struct EmbMlpParams {
   int EP;
 };
 
+// ---- EmbeddingMLP / Wide&Deep on tensor cores (embmlp_tc.cu): E <= 12 ------------------------
+struct EmbMlpTcParams {
+  const float* genre[8];   // [19][12]
+  const float* movie;      // [n_movies][12]
+  const float* user;       // [n_users][12]
+  const uint8_t* image;    // 128 KB: W1^T hi/lo, W2^T hi/lo as bf16 SW128 operand tiles
+  const float* b1;         // [128]
+  const float* w1num;      // [8][128] rows of dense/kernel that multiply the 7 numerics
+  const float* b2;         // [128]
+  const float* w3;         // [128]
+  const float* wide;       // [cross_buckets] or nullptr
+  float b3;
+  int n_movies, n_users, n_genres, cross_buckets;
+  int num_sms;
+};
+
 // ---- DeepFM (DeepFM.py:91-113) -----------------------------------------------------
 struct DeepFmParams {
   const float* fm_movie;   // [n_movies][EP]
@@ -149,6 +165,7 @@ cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t
 cudaError_t read_din_tc_trace(unsigned long long* out40);
 cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_embmlp(const EmbMlpParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_embmlp_tc(const EmbMlpTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm2(const DeepFm2Params& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_din(const DinParams& p, const BatchView& b, cudaStream_t s);

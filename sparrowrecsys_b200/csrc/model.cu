@@ -19,6 +19,7 @@ cudaError_t setup_embmlp_attributes();
 cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
 cudaError_t setup_din_tc_attributes();
+cudaError_t setup_embmlp_tc_attributes();
 }  // namespace srs
 
 using namespace srs;
@@ -73,6 +74,8 @@ struct srs_model {
   DinParams din{};
   DinTcParams din_tc{};
   bool use_din_tc = false;
+  EmbMlpTcParams emb_tc{};
+  bool use_emb_tc = false;
   const char* kernel_name = "";
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
@@ -622,6 +625,55 @@ int build_din_tc(Builder& B) {
   return B.status;
 }
 
+// Tensor-core EmbeddingMLP / W&D (E <= 12): operand images from the tensors build_embmlp validated.
+int build_embmlp_tc(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, h0 = s.hidden[0], h1 = s.hidden[1];
+  const float* k1 = B.host("dense/kernel", 7 + 10 * E, h0);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  if (B.status != SRS_OK) return B.status;
+  // K = slot * 12 + e; slot order of the kernel's gather: movieGenre1..3, movieId, userGenre1..5, userId
+  int slot_start[10];
+  for (int k = 0; k < 3; ++k) slot_start[k] = 1 + k * E;
+  slot_start[3] = 1 + 3 * E;
+  for (int k = 0; k < 5; ++k) slot_start[4 + k] = 5 + 4 * E + k * E;
+  slot_start[9] = 5 + 9 * E;
+  auto w1_get = [&](int j, int k) -> float {
+    const int slot = k / 12, e = k - slot * 12;
+    if (j >= h0 || slot >= 10 || e >= E) return 0.f;
+    return k1[(size_t)(slot_start[slot] + e) * h0 + j];
+  };
+  auto w2_get = [&](int j, int k) -> float { return (j < h1 && k < h0) ? k2[(size_t)k * h1 + j] : 0.f; };
+  std::vector<uint8_t> img(131072, 0);
+  write_sw128(img.data() + 0, 128, 2, false, w1_get);
+  write_sw128(img.data() + 32768, 128, 2, true, w1_get);
+  write_sw128(img.data() + 65536, 128, 2, false, w2_get);
+  write_sw128(img.data() + 98304, 128, 2, true, w2_get);
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, img.size());
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  m->owned.push_back(d_img);
+  e = cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+  const int nrows[7] = {0, 1 + 4 * E, 2 + 4 * E, 3 + 4 * E, 4 + 4 * E, 5 + 10 * E, 6 + 10 * E};
+  std::vector<float> w1num(8 * 128, 0.f);
+  for (int n = 0; n < 7; ++n)
+    for (int j = 0; j < h0; ++j) w1num[(size_t)n * 128 + j] = k1[(size_t)nrows[n] * h0 + j];
+  EmbMlpTcParams& p = m->emb_tc;
+  const EmbMlpParams& v1 = m->emb;
+  for (int k = 0; k < 8; ++k) p.genre[k] = v1.genre[k];
+  p.movie = v1.movie; p.user = v1.user;
+  p.image = d_img;
+  p.b1 = v1.b1; p.b2 = v1.b2; p.w3 = v1.w3; p.wide = v1.wide; p.b3 = v1.b3;
+  p.w1num = B.upload(w1num);
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres; p.cross_buckets = s.cross_buckets;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  p.num_sms = sms > 0 ? sms : 148;
+  return B.status;
+}
+
 int64_t bytes_per_inference(const srs_spec& s) {
   const int64_t E = s.emb_dim, T = s.hist_len;
   switch (s.kind) {
@@ -659,7 +711,9 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_NEURALCF:
     case SRS_TWOTOWERS: e = launch_ncf(m->ncf, v, stream); break;
     case SRS_EMBEDDINGMLP:
-    case SRS_WIDENDEEP: e = launch_embmlp(m->emb, v, stream); break;
+    case SRS_WIDENDEEP:
+      e = m->use_emb_tc ? launch_embmlp_tc(m->emb_tc, v, stream) : launch_embmlp(m->emb, v, stream);
+      break;
     case SRS_DEEPFM: e = launch_deepfm(m->fm, v, stream); break;
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
@@ -813,6 +867,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_deepfm_attributes());
   CUDA_TRY(setup_din_attributes());
   CUDA_TRY(setup_din_tc_attributes());
+  CUDA_TRY(setup_embmlp_tc_attributes());
 
   srs_model* m = new srs_model();
   m->spec = *spec;
@@ -828,7 +883,26 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     case SRS_NEURALCF:
     case SRS_TWOTOWERS: rc = build_ncf(B); break;
     case SRS_EMBEDDINGMLP:
-    case SRS_WIDENDEEP: rc = build_embmlp(B); break;
+    case SRS_WIDENDEEP: {
+      rc = build_embmlp(B);
+      // tensor-core path for the reference shape (E <= 12); SRS_EMBMLP_IMPL=cudacore|tc overrides
+      const char* impl = getenv("SRS_EMBMLP_IMPL");
+      const bool fits = m->EP == 12;
+      bool want = fits;
+      if (impl && !strcmp(impl, "cudacore")) want = false;
+      if (impl && !strcmp(impl, "tc")) {
+        if (!fits && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_EMBMLP_IMPL=tc needs emb_dim <= 12");
+        want = true;
+      }
+      if (rc == SRS_OK && want) {
+        rc = build_embmlp_tc(B);
+        if (rc == SRS_OK) {
+          m->use_emb_tc = true;
+          m->kernel_name = spec->kind == SRS_WIDENDEEP ? "embmlp_tc_kernel<wide&deep>" : "embmlp_tc_kernel";
+        }
+      }
+      break;
+    }
     case SRS_DEEPFM: rc = build_deepfm(B); break;
     case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
     default: {

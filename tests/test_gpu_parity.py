@@ -416,3 +416,34 @@ def test_predict_batches_packed_and_unpacked_agree():
         m.predict_batches(scattered, outs2)
         assert np.array_equal(np.concatenate(outs2), ref)
         assert np.array_equal(m.predict(feats, batch_size=12 * 50)[:, 0], ref)
+
+
+# ---- EmbeddingMLP / Wide&Deep tensor-core kernel (csrc/embmlp_tc.cu) ----------------------
+@pytest.mark.parametrize("model", ["embeddingmlp", "widendeep"])
+@pytest.mark.parametrize("B", [1, 63, 64, 65, 129, 8192])
+def test_embmlp_tensor_core_kernel(model, B, monkeypatch):
+    spec = default_spec(model)
+    W = init_weights(spec, 31 + B)
+    feats = synthetic_features(spec, B, seed=B)
+    monkeypatch.setenv("SRS_EMBMLP_IMPL", "tc")
+    with _model(spec, W) as m:
+        assert m.kernel_name.startswith("embmlp_tc_kernel")
+        p_tc, z_tc = m.predict_with_logits(feats)
+        assert np.array_equal(m.predict(feats), p_tc)
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(z_tc - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z_tc - zo).max()
+    assert np.abs(p_tc - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p_tc - po).max()
+    monkeypatch.setenv("SRS_EMBMLP_IMPL", "cudacore")
+    with _model(spec, W) as m:
+        assert m.kernel_name.startswith("embmlp_kernel")
+        p_cc = m.predict(feats)
+    assert np.abs(p_cc - po).max() <= PROB_ATOL
+
+
+def test_embmlp_tensor_core_narrow_hidden_and_small_emb(monkeypatch):
+    monkeypatch.setenv("SRS_EMBMLP_IMPL", "tc")
+    for E, hidden in ((10, (64, 32)), (8, (128, 128)), (12, (100, 77))):
+        spec = default_spec("widendeep", emb_dim=E, hidden=hidden, n_movies=2000, n_users=3000)
+        W = init_weights(spec, E)
+        feats = synthetic_features(spec, 700, seed=E)
+        _compare(spec, W, feats)
