@@ -82,6 +82,26 @@ struct DeepFmParams {
   int EP;
 };
 
+// ---- DeepFM with the deep MLP on tensor cores (deepfm_tc.cu): emb_dim 13..16 --------------------
+struct DeepFmTcParams {
+  const float* fm_movie;   // [n_movies][16]
+  const float* fm_user;
+  const float* fm_mgenre;
+  const float* fm_ugenre;
+  const float* deep_movie;
+  const float* deep_user;
+  const uint8_t* image;    // 64 KB: W1^T hi/lo, W2^T hi/lo as [128][64] bf16 SW128 tiles
+  const float* b1;         // [64]
+  const float* w1num;      // [8][64]
+  const float* b2;         // [64]
+  const float* first;      // [fm1_width]
+  const float* wdeep;      // [64]
+  float wdot[4];
+  float bout;
+  int n_movies, n_users, n_genres;
+  int num_sms;
+};
+
 // ---- DeepFM_v2 (DeepFM_v2.py:98-155) -----------------------------------------------
 struct DeepFm2Params {
   const float* mgenre;     // [19][EP]
@@ -167,6 +187,7 @@ cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_embmlp(const EmbMlpParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_embmlp_tc(const EmbMlpTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_deepfm_tc(const DeepFmTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm2(const DeepFm2Params& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_din(const DinParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, float hi,

@@ -20,6 +20,7 @@ cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_embmlp_tc_attributes();
+cudaError_t setup_deepfm_tc_attributes();
 }  // namespace srs
 
 using namespace srs;
@@ -76,6 +77,8 @@ struct srs_model {
   bool use_din_tc = false;
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
+  DeepFmTcParams fm_tc{};
+  bool use_fm_tc = false;
   const char* kernel_name = "";
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
@@ -674,6 +677,52 @@ int build_embmlp_tc(Builder& B) {
   return B.status;
 }
 
+// Tensor-core DeepFM (emb_dim 13..16): operand images from the tensors build_deepfm validated.
+int build_deepfm_tc(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, h0 = s.hidden[0], h1 = s.hidden[1];
+  const float* k1 = B.host("dense/kernel", 7 + 2 * E, h0);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  if (B.status != SRS_OK) return B.status;
+  auto w1_get = [&](int j, int k) -> float {        // K = [deep movieId emb (16) | deep userId emb (16) | 0]
+    if (j >= h0 || k >= 32) return 0.f;
+    const int e = k & 15;
+    if (e >= E) return 0.f;
+    return k1[(size_t)((k < 16 ? 1 : 5 + E) + e) * h0 + j];
+  };
+  auto w2_get = [&](int j, int k) -> float { return (j < h1 && k < h0) ? k2[(size_t)k * h1 + j] : 0.f; };
+  std::vector<uint8_t> img(65536, 0);
+  write_sw128(img.data() + 0, 128, 1, false, w1_get);
+  write_sw128(img.data() + 16384, 128, 1, true, w1_get);
+  write_sw128(img.data() + 32768, 128, 1, false, w2_get);
+  write_sw128(img.data() + 49152, 128, 1, true, w2_get);
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, img.size());
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  m->owned.push_back(d_img);
+  e = cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+  const int nrows[7] = {0, 1 + E, 2 + E, 3 + E, 4 + E, 5 + 2 * E, 6 + 2 * E};
+  std::vector<float> w1num(8 * 64, 0.f);
+  for (int n = 0; n < 7; ++n)
+    for (int j = 0; j < h0; ++j) w1num[(size_t)n * 64 + j] = k1[(size_t)nrows[n] * h0 + j];
+  DeepFmTcParams& p = m->fm_tc;
+  const DeepFmParams& v1 = m->fm;
+  p.fm_movie = v1.fm_movie; p.fm_user = v1.fm_user; p.fm_mgenre = v1.fm_mgenre; p.fm_ugenre = v1.fm_ugenre;
+  p.deep_movie = v1.deep_movie; p.deep_user = v1.deep_user;
+  p.image = d_img;
+  p.b1 = v1.b1; p.b2 = v1.b2; p.first = v1.first; p.wdeep = v1.wdeep;
+  p.w1num = B.upload(w1num);
+  for (int d = 0; d < 4; ++d) p.wdot[d] = v1.wdot[d];
+  p.bout = v1.bout;
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  p.num_sms = sms > 0 ? sms : 148;
+  return B.status;
+}
+
 int64_t bytes_per_inference(const srs_spec& s) {
   const int64_t E = s.emb_dim, T = s.hist_len;
   switch (s.kind) {
@@ -714,7 +763,9 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_WIDENDEEP:
       e = m->use_emb_tc ? launch_embmlp_tc(m->emb_tc, v, stream) : launch_embmlp(m->emb, v, stream);
       break;
-    case SRS_DEEPFM: e = launch_deepfm(m->fm, v, stream); break;
+    case SRS_DEEPFM:
+      e = m->use_fm_tc ? launch_deepfm_tc(m->fm_tc, v, stream) : launch_deepfm(m->fm, v, stream);
+      break;
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
       e = m->use_din_tc ? launch_din_tc(m->din_tc, v, stream) : launch_din(m->din, v, stream);
@@ -868,6 +919,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_din_attributes());
   CUDA_TRY(setup_din_tc_attributes());
   CUDA_TRY(setup_embmlp_tc_attributes());
+  CUDA_TRY(setup_deepfm_tc_attributes());
 
   srs_model* m = new srs_model();
   m->spec = *spec;
@@ -903,7 +955,23 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
       }
       break;
     }
-    case SRS_DEEPFM: rc = build_deepfm(B); break;
+    case SRS_DEEPFM: {
+      rc = build_deepfm(B);
+      // tensor-core deep MLP when emb_dim pads to 16; SRS_DEEPFM_IMPL=cudacore|tc overrides
+      const char* impl = getenv("SRS_DEEPFM_IMPL");
+      const bool fits = m->EP == 16;
+      bool want = fits;
+      if (impl && !strcmp(impl, "cudacore")) want = false;
+      if (impl && !strcmp(impl, "tc")) {
+        if (!fits && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DEEPFM_IMPL=tc needs 12 < emb_dim <= 16");
+        want = true;
+      }
+      if (rc == SRS_OK && want) {
+        rc = build_deepfm_tc(B);
+        if (rc == SRS_OK) { m->use_fm_tc = true; m->kernel_name = "deepfm_tc_kernel"; }
+      }
+      break;
+    }
     case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
     default: {
       rc = build_din(B);

@@ -447,3 +447,23 @@ def test_embmlp_tensor_core_narrow_hidden_and_small_emb(monkeypatch):
         W = init_weights(spec, E)
         feats = synthetic_features(spec, 700, seed=E)
         _compare(spec, W, feats)
+
+
+# ---- DeepFM tensor-core kernel (csrc/deepfm_tc.cu) ---------------------------------------
+@pytest.mark.parametrize("E,B", [(16, 4096), (16, 1), (16, 31), (16, 33), (14, 700), (16, 9000)])
+def test_deepfm_tensor_core_kernel(E, B, monkeypatch):
+    spec = default_spec("deepfm", emb_dim=E, n_movies=27279, n_users=20000)
+    W = init_weights(spec, 50 + E + B)
+    feats = synthetic_features(spec, B, seed=B + E)
+    monkeypatch.setenv("SRS_DEEPFM_IMPL", "tc")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "deepfm_tc_kernel"
+        p_tc, z_tc = m.predict_with_logits(feats)
+        assert np.array_equal(m.predict(feats), p_tc)
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(z_tc - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z_tc - zo).max()
+    assert np.abs(p_tc - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p_tc - po).max()
+    monkeypatch.setenv("SRS_DEEPFM_IMPL", "cudacore")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "deepfm_kernel"
+        assert np.abs(m.predict(feats) - po).max() <= PROB_ATOL
