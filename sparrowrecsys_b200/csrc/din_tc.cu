@@ -262,9 +262,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
     }
     wg_sync(wg);
     // cst[rs][j] = au_b[j] + sum_e cand[rs][e] * (Wc - Wsub)[e][j]; warp w: rows w and w+4.
-    // First needed by the first epilogue.  Workers 0/1 compute it while their first MMAs run,
-    // workers 2/3 before their first tile: that skews the two pairs by one cst time, so the
-    // pairs' tensor-core phases and CUDA-core phases interleave instead of colliding.
+    // First needed by the first epilogue: computed while the first tile's MMAs run.
     auto compute_cst = [&]() {
       float acc0 = __ldg(p.au_b + lane), acc1 = acc0;
 #pragma unroll 8
@@ -276,8 +274,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
       cst[warp_w * 32 + lane] = acc0;
       cst[(warp_w + 4) * 32 + lane] = acc1;
     };
-    const bool cst_early = wg >= 2;
-    if (cst_early) compute_cst();
+    const bool cst_early = false;
     TC_TRACE(2);
     if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
     TC_TRACE(3);
@@ -457,7 +454,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         const uint64_t al = smem_desc_sw128(s_img + IMG_W1_LO + kb * 16384);
         const uint64_t xs = smem_desc_sw128(s_cs + WS_XB + kb * 8192);     // [X hi | X lo], N = 64
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks = 0; ks < (kb == 2 ? 2 : 4); ++ks) {                   // K block 2: columns 32..63 are zero
           mma_ss(tD1, ah + 2 * ks, xs + 2 * ks, idesc_top, acc);           // W1hi.(Xhi | Xlo)
           acc = 1;
           mma_ss(tD1, al + 2 * ks, xs + 2 * ks, idesc_top, 1);             // W1lo.(Xhi | Xlo)
