@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Phase timeline (SM cycles, CTA 0) of the row-tile DIN kernel (csrc/din_rt.cu).
+Run on the GPU box:  python profiles/trace_din_rt.py [batch]"""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sparrowrecsys_b200 import _lib
+from sparrowrecsys_b200.features import synthetic_features
+from sparrowrecsys_b200.model import CTRModel
+from sparrowrecsys_b200.spec import baseline_spec
+from sparrowrecsys_b200.weights import init_weights
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+spec = baseline_spec("cfg3_din")
+m = CTRModel(spec, init_weights(spec, 2), 0)
+assert m.kernel_name == "din_rt_kernel", m.kernel_name
+db = m.to_device(synthetic_features(spec, B, seed=1))
+out = torch.empty(B, dtype=torch.float32, device="cuda:0")
+lib = _lib.load()
+for _ in range(5):
+    m.predict_device(db, out)
+torch.cuda.synchronize()
+lib.srs_debug_din_trace(m._h, 1, None)
+buf = (C.c_uint64 * 40)()
+names = {0: "entry", 1: "prologue", 2: "phase0", 3: "first_d1_ready", 4: "first_tile_pooled", 5: "tiles_done",
+         6: "layer1", 7: "group", 8: "exit"}
+for rep in range(3):
+    m.predict_device(db, out)
+    _lib.check(lib.srs_debug_din_trace(m._h, 1, buf))
+    t = np.array(buf[:], dtype=np.int64)
+    prev = t[0]
+    line = []
+    for i in sorted(names):
+        if t[i] == 0:
+            continue
+        line.append("%s=%d(+%d)" % (names[i], t[i] - t[0], t[i] - prev))
+        prev = t[i]
+    print(" ".join(line))
+    fine = {10: "c.d1_ready", 11: "c.gate", 12: "c.synced", 13: "c.mma2_issued", 14: "c.mma1_next_issued",
+            15: "c.d2_ready", 16: "c.pooled", 20: "p.tile0_full", 21: "p.tile2_full", 22: "p.tile4_full",
+            23: "p.tile2_built", 17: "c.d2_ready(warp1)", 18: "c.synced(warp1)", 24: "x_built", 25: "l1_issued"}
+    print("   second tile of consumer 0 / producer 0 (cycles since entry): " +
+          " ".join("%s=%d" % (fine[i], t[i] - t[0]) for i in sorted(fine) if t[i]))

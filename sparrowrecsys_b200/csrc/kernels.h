@@ -180,7 +180,39 @@ struct DinTcParams {
   int trace;               // debug: record phase timestamps of worker 0 (srs_debug_din_trace)
 };
 
+// din_rt.cu: history rows gathered by cp.async into tcgen05 operand tiles (E padded to 32, T <= 64)
+struct DinRtParams {
+  const float* movie;        // [n_movies][32] fp32 (candidate rows)
+  const uint8_t* movie_split;// [n_movies][32 bf16 hi | 32 bf16 lo]  (history rows)
+  const float* user;         // [n_users][32]
+  const float* ugenre;       // [19][32]
+  const float* mgenre;       // [19][32]
+  const uint8_t* image;      // W2 | W1 hi | W1 lo operand images (131072 bytes)
+  const float* waT;          // [32 units][32 e]  (Wsub + Wh)^T
+  const float* wpT;          // [32 units][32 e]  Wp^T
+  const float* pq;           // [T][64]: P_t[0..31] | Q_t[0..31]
+  const float* au_wc;        // [32][32]  W_c - W_sub
+  const float* au_b;         // [32]
+  const float* b1;           // [128]
+  const float* a1;           // [128]
+  const float* w1num;        // [8][128]
+  const float* b2;           // [64]
+  const float* a2;           // [64]
+  const float* w3;           // [64]
+  float au_bout;
+  float b3;
+  int n_movies, n_users, n_genres;
+  int T;
+  int rows_per_group;        // set by the launcher
+  int num_sms;
+  int trace;
+};
+
 // launchers (defined next to their kernels); return cudaGetLastError()
+cudaError_t launch_din_rt(const DinRtParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_split_table(const float* src, void* dst, int64_t rows, cudaStream_t s);
+cudaError_t read_din_rt_trace(unsigned long long* out40);
+cudaError_t setup_din_rt_attributes();
 cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t read_din_tc_trace(unsigned long long* out40);
 cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);

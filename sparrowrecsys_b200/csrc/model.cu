@@ -19,6 +19,7 @@ cudaError_t setup_embmlp_attributes();
 cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
 cudaError_t setup_din_tc_attributes();
+cudaError_t setup_din_rt_attributes();
 cudaError_t setup_embmlp_tc_attributes();
 cudaError_t setup_deepfm_tc_attributes();
 }  // namespace srs
@@ -75,6 +76,8 @@ struct srs_model {
   DinParams din{};
   DinTcParams din_tc{};
   bool use_din_tc = false;
+  DinRtParams din_rt{};
+  bool use_din_rt = false;
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
   DeepFmTcParams fm_tc{};
@@ -628,6 +631,91 @@ int build_din_tc(Builder& B) {
   return B.status;
 }
 
+// Row-tile DIN kernel (din_rt.cu): pre-split movie table, transposed activation-unit weights,
+// P/Q gate tables and the top-MLP operand images, from the tensors build_din validated.
+int build_din_rt(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, T = s.hist_len, A = 32;
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  const float* au = B.host("au_dense/kernel", 4 * E, A);
+  const float* alpha = B.host("au_prelu/alpha", T, A);
+  const float* auo = B.host("au_out/kernel", A, 1);
+  const float* k1 = B.host("dense/kernel", 5 * E + 7, h0);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  if (B.status != SRS_OK) return B.status;
+  const uint32_t RI_W2 = 0, RI_W1_HI = 32768, RI_W1_LO = RI_W1_HI + 49152, RI_BYTES = RI_W1_LO + 49152;
+  std::vector<uint8_t> img(RI_BYTES, 0);
+  const int base = 3 + 4 * E;
+  const int slot_start[6] = {1, 1 + E, 3 + 2 * E, 3 + 3 * E, base + 1, -1};
+  auto w1_get = [&](int j, int k) -> float {
+    const int slot = k >> 5, e = k & 31;
+    if (j >= h0 || slot >= 5 || e >= E) return 0.f;
+    return k1[(size_t)(slot_start[slot] + e) * h0 + j];
+  };
+  write_sw128(img.data() + RI_W1_HI, 128, 3, false, w1_get);
+  write_sw128(img.data() + RI_W1_LO, 128, 3, true, w1_get);
+  auto w2_raw = [&](int i, int k) -> float { return (i < h1 && k < h0) ? k2[(size_t)k * h1 + i] : 0.f; };
+  for (int kb = 0; kb < 2; ++kb)
+    for (int r = 0; r < 128; ++r)
+      for (int c = 0; c < 8; ++c)
+        for (int i = 0; i < 8; ++i) {
+          const float x = w2_raw(r & 63, kb * 64 + c * 8 + i);
+          const uint16_t hb = bf16_rn_bits(x);
+          const uint16_t v = (r < 64) ? hb : bf16_rn_bits(x - u2f((uint32_t)hb << 16));
+          memcpy(img.data() + RI_W2 + (size_t)kb * 16384 + sw128_off(r, c) + i * 2, &v, 2);
+        }
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, RI_BYTES);
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc(%u) failed: %s", RI_BYTES, cudaGetErrorString(e));
+  m->owned.push_back(d_img);
+  e = cudaMemcpy(d_img, img.data(), RI_BYTES, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+  // activation unit: (Wsub + Wh)^T and Wp^T, [unit j][e], zero beyond E
+  std::vector<float> waT(32 * 32, 0.f), wpT(32 * 32, 0.f);
+  for (int j = 0; j < A; ++j)
+    for (int ee = 0; ee < E; ++ee) {
+      waT[(size_t)j * 32 + ee] = au[(size_t)ee * A + j] + au[(size_t)(E + ee) * A + j];
+      wpT[(size_t)j * 32 + ee] = au[(size_t)(3 * E + ee) * A + j];
+    }
+  // PReLU + Dense(1) folded: wout_j max(v,0) + alpha_tj wout_j min(v,0) = v P_tj + |v| Q_tj
+  std::vector<float> pq((size_t)T * 64, 0.f);
+  for (int t = 0; t < T; ++t)
+    for (int j = 0; j < A; ++j) {
+      const float wo = auo[j], aw = alpha[(size_t)t * A + j] * auo[j];
+      pq[(size_t)t * 64 + j] = 0.5f * (wo + aw);
+      pq[(size_t)t * 64 + 32 + j] = 0.5f * (wo - aw);
+    }
+  const int nrows[7] = {base, base + 1 + E, base + 2 + E, base + 3 + E, 0, 1 + 2 * E, 2 + 2 * E};
+  std::vector<float> w1num(8 * 128, 0.f);
+  for (int n = 0; n < 7; ++n)
+    for (int j = 0; j < h0; ++j) w1num[(size_t)n * 128 + j] = k1[(size_t)nrows[n] * h0 + j];
+  DinRtParams& p = m->din_rt;
+  const DinParams& v1 = m->din;                 // tables / vectors uploaded by build_din
+  // history rows: [n_movies][32 bf16 hi | 32 bf16 lo]
+  void* d_split = nullptr;
+  const size_t split_bytes = (size_t)s.n_movies * 128;
+  e = cudaMalloc(&d_split, split_bytes);
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", split_bytes, cudaGetErrorString(e));
+  m->owned.push_back(d_split);
+  e = launch_split_table(v1.movie, d_split, s.n_movies, nullptr);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "table split failed: %s", cudaGetErrorString(e));
+  p.movie = v1.movie; p.movie_split = static_cast<const uint8_t*>(d_split);
+  p.user = v1.user; p.ugenre = v1.ugenre; p.mgenre = v1.mgenre;
+  p.image = d_img;
+  p.waT = B.upload(waT); p.wpT = B.upload(wpT); p.pq = B.upload(pq);
+  p.au_wc = v1.au_wc; p.au_b = v1.au_b;
+  p.b1 = v1.b1; p.a1 = v1.a1; p.w1num = B.upload(w1num);
+  p.b2 = v1.b2; p.a2 = v1.a2; p.w3 = v1.w3;
+  p.au_bout = v1.au_bout; p.b3 = v1.b3;
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.T = T; p.rows_per_group = 32;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  p.num_sms = sms > 0 ? sms : 148;
+  return B.status;
+}
+
 // Tensor-core EmbeddingMLP / W&D (E <= 12): operand images from the tensors build_embmlp validated.
 int build_embmlp_tc(Builder& B) {
   srs_model* m = B.m;
@@ -768,7 +856,9 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
       break;
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
-      e = m->use_din_tc ? launch_din_tc(m->din_tc, v, stream) : launch_din(m->din, v, stream);
+      e = m->use_din_rt   ? launch_din_rt(m->din_rt, v, stream)
+          : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
+                          : launch_din(m->din, v, stream);
       break;
     default: return fail(SRS_ERR_INVALID, "unknown model kind");
   }
@@ -918,6 +1008,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_deepfm_attributes());
   CUDA_TRY(setup_din_attributes());
   CUDA_TRY(setup_din_tc_attributes());
+  CUDA_TRY(setup_din_rt_attributes());
   CUDA_TRY(setup_embmlp_tc_attributes());
   CUDA_TRY(setup_deepfm_tc_attributes());
 
@@ -975,19 +1066,30 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
     default: {
       rc = build_din(B);
-      // kernel selection: tensor-core path when the shape fits it (E padded to 32, T in 9..128);
-      // SRS_DIN_IMPL=cudacore|tc overrides (tc fails loudly if the shape is unsupported)
+      // kernel selection (SRS_DIN_IMPL=cudacore|tc|rt overrides; tc / rt fail loudly on an unsupported shape):
+      //   rt  row-tile kernel, E padded to 32 and T in 9..64
+      //   tc  per-pair tensor-core kernel, E padded to 32 and T in 9..128
       const char* impl = getenv("SRS_DIN_IMPL");
-      const bool fits = m->EP == 32 && spec->hist_len <= 128;
-      bool want = fits && spec->hist_len > 8;
-      if (impl && !strcmp(impl, "cudacore")) want = false;
+      const bool fits_tc = m->EP == 32 && spec->hist_len <= 128;
+      const bool fits_rt = m->EP == 32 && spec->hist_len <= 64;
+      bool want_rt = fits_rt && spec->hist_len > 8;
+      bool want_tc = !want_rt && fits_tc && spec->hist_len > 8;
+      if (impl && !strcmp(impl, "cudacore")) want_rt = want_tc = false;
       if (impl && !strcmp(impl, "tc")) {
-        if (!fits && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=tc needs 16 < emb_dim <= 32 and hist_len <= 128");
-        want = true;
+        if (!fits_tc && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=tc needs 16 < emb_dim <= 32 and hist_len <= 128");
+        want_tc = true; want_rt = false;
       }
-      if (rc == SRS_OK && want) {
+      if (impl && !strcmp(impl, "rt")) {
+        if (!fits_rt && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rt needs 16 < emb_dim <= 32 and hist_len <= 64");
+        want_rt = true; want_tc = false;
+      }
+      if (rc == SRS_OK && want_tc) {
         rc = build_din_tc(B);
         if (rc == SRS_OK) { m->use_din_tc = true; m->kernel_name = "din_tc_kernel"; }
+      }
+      if (rc == SRS_OK && want_rt) {
+        rc = build_din_rt(B);
+        if (rc == SRS_OK) { m->use_din_rt = true; m->kernel_name = "din_rt_kernel"; }
       }
       break;
     }
@@ -1130,9 +1232,11 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   if (!m) return fail(SRS_ERR_INVALID, "null model");
   CUDA_TRY(cudaSetDevice(m->device));
   m->din_tc.trace = enable;
+  m->din_rt.trace = enable;
   if (out40) {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
+    if (m->use_din_rt) CUDA_TRY(read_din_rt_trace(reinterpret_cast<unsigned long long*>(out40)));
+    else CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
   }
   return SRS_OK;
 }

@@ -328,7 +328,10 @@ def test_launch_counter_counts_kernels():
         assert launch_count() == before + 1
 
 
-# ---- DIN tensor-core kernel (csrc/din_tc.cu) vs CUDA-core kernel vs oracle ----------------
+# ---- DIN tensor-core kernels (csrc/din_tc.cu per-pair, csrc/din_rt.cu row tiles) vs CUDA-core
+#      kernel vs oracle ----------------------------------------------------------------------
+KERNEL_OF = {"tc": "din_tc_kernel", "rt": "din_rt_kernel"}
+
 @pytest.fixture
 def din_impl(monkeypatch):
     def set_impl(name):
@@ -339,13 +342,16 @@ def din_impl(monkeypatch):
 @pytest.mark.parametrize("E,T,B", [(32, 50, 4096), (32, 9, 100), (32, 31, 17), (32, 32, 16),
                                    (32, 33, 15), (20, 64, 333), (32, 65, 129), (32, 128, 257),
                                    (24, 100, 1), (32, 50, 4097)])
-def test_din_tensor_core_kernel(E, T, B, din_impl):
+@pytest.mark.parametrize("impl", ["tc", "rt"])
+def test_din_tensor_core_kernel(E, T, B, impl, din_impl):
+    if impl == "rt" and T > 64:
+        pytest.skip("row-tile kernel covers hist_len <= 64")
     spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=27279, n_users=5000)
     W = init_weights(spec, E * 1000 + T)
     feats = synthetic_features(spec, B, seed=T)
-    din_impl("tc")
+    din_impl(impl)
     with _model(spec, W) as m:
-        assert m.kernel_name == "din_tc_kernel"
+        assert m.kernel_name == KERNEL_OF[impl]
         p_tc, z_tc = m.predict_with_logits(feats)
         p_tc2 = m.predict(feats)
     assert np.array_equal(p_tc, p_tc2)                       # deterministic
@@ -360,8 +366,9 @@ def test_din_tensor_core_kernel(E, T, B, din_impl):
     assert np.abs(p_cc - p_tc).max() <= 2 * PROB_ATOL
 
 
-def test_din_tensor_core_row_independence(din_impl):
-    din_impl("tc")
+@pytest.mark.parametrize("impl", ["tc", "rt"])
+def test_din_tensor_core_row_independence(impl, din_impl):
+    din_impl(impl)
     spec = baseline_spec("cfg3_din")
     W = init_weights(spec, 3)
     B = 8192 + 5
@@ -371,15 +378,17 @@ def test_din_tensor_core_row_independence(din_impl):
         p = m.predict(feats)[:, 0]
         pp = m.predict({k: v[perm] for k, v in feats.items()})[:, 0]
         assert np.array_equal(pp, p[perm])                   # bit-exact under row permutation
+        assert m.kernel_name == KERNEL_OF[impl]
         lo = m.predict({k: v[:4099] for k, v in feats.items()})[:, 0]
         hi = m.predict({k: v[4099:] for k, v in feats.items()})[:, 0]
         assert np.array_equal(np.concatenate([lo, hi]), p)   # sharding invariant
 
 
-def test_din_tensor_core_large_magnitudes(din_impl):
+@pytest.mark.parametrize("impl", ["tc", "rt"])
+def test_din_tensor_core_large_magnitudes(impl, din_impl):
     """Trained-scale weights: embeddings O(0.5), logits up to ~10 - the bf16x3 split must hold
     the 1e-4 target with margin where plain TF32/bf16 would not."""
-    din_impl("tc")
+    din_impl(impl)
     spec = baseline_spec("cfg3_din")
     W = init_weights(spec, 5)
     W["embedding"] = (W["embedding"] * 10).astype(np.float32)
