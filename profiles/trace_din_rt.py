@@ -39,6 +39,6 @@ for rep in range(3):
     print(" ".join(line))
     fine = {10: "c.d1_ready", 11: "c.gate", 12: "c.synced", 13: "c.mma2_issued", 14: "c.mma1_next_issued",
             15: "c.d2_ready", 16: "c.pooled", 20: "p.tile0_full", 21: "p.tile2_full", 22: "p.tile4_full",
-            23: "p.tile2_built", 17: "c.d2_ready(warp1)", 18: "c.synced(warp1)", 24: "x_built", 25: "l1_issued"}
+            23: "p.tile2_built", 17: "c.d2_ready(warp1)", 18: "c.synced(warp1)", 24: "x_built", 25: "l1_issued", 30: "p0.rows_requested", 31: "p0.ids_stored", 32: "p0.pads_zeroed", 33: "p0.sync1", 34: "p0.gathers_issued", 35: "p0.cand_stored"}
     print("   second tile of consumer 0 / producer 0 (cycles since entry): " +
           " ".join("%s=%d" % (fine[i], t[i] - t[0]) for i in sorted(fine) if t[i]))

@@ -13,15 +13,18 @@
 //   * gate: v = D_hi + D_lo + cst_r, s = sum_j v_j P_tj + |v_j| Q_tj, w = sigmoid(s)  (CUDA cores,
 //     thread = position, P/Q of its position in registers);
 //   * pooling: sum_t w_t h_t is a second MMA on the SAME tile read MN-major:
-//         D2[64 = hi e | lo e][8] = tile^T[64 x 64 positions] * [w_hi | w_lo | 0 ...]
+//         D2[64 = hi e | lo e][8] = tile^T[64 x 64 positions] * [w_hi | w_lo | ...]
 //     so h is never loaded into registers at all;
-//   * top MLP: unchanged from din_tc.cu (transposed, rows of the group are the MMA N).
+//   * top MLP: as in din_tc.cu (transposed, rows of the group are the MMA N); its weight images
+//     are copied over the ring when the group's tiles are done.
 //
-// CTA = 512 threads, one per SM, persistent over groups of up to 32 batch rows:
-//   warpgroups 0,1  producers: tile K (global counter) belongs to producer K & 1; cp.async the
-//                   100 history rows of the tile into ring slot K % 3, build the two W_r
-//   warpgroups 2,3  consumers: tile K belongs to consumer K & 1; issue MMAs, gate epilogue,
-//                   pooling MMA, pooled read-back
+// CTA = 512 threads, one per SM, persistent over groups of up to 32 batch rows; tile K (a
+// CTA-global counter) lives in ring slot K % 8.  Warp roles during the tiles:
+//   warps 0-3    gatherers: cp.async the 100 history rows of tile K into the slot, 5 tiles ahead
+//   warp  4      issuer: every tcgen05.mma / commit of the tile phase
+//   warps 5-6    builders: the B operand (two W_r) of tile K
+//   warps 8-15   consumers: tile K belongs to consumer K & 1: gate epilogue -> pooling weights,
+//                pooled accumulators of its previous tile -> shared memory
 // Precision: bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) everywhere, as in din_tc.cu.
 #include <climits>
 
@@ -33,40 +36,39 @@ using namespace umma;
 
 constexpr int kRtThreads = 512;
 constexpr int kRtRows = 32;                 // row slots per group = N/2 of the top-MLP MMAs
-constexpr int kRtSlots = 7;                 // ring slots (history tiles in flight or being consumed)
-constexpr int kRtAhead = 3;                 // tiles a producer keeps in flight ahead of the one it delivers
+constexpr int kRtSlots = 8;                 // ring slots (history tiles in flight or being consumed)
+constexpr int kRtAhead = 5;                 // tiles the gatherers keep in flight ahead of the one they deliver
 constexpr int kRtIdsLd = 64;                // ints per row of the staged history ids
+constexpr int kRtHistPerThread = kRtRows * kRtIdsLd / kRtThreads;
 
-// weight image in global memory (built by build_din_rt in model.cu): W2 | W1 hi | W1 lo.
-// W2 is resident in shared memory for the whole launch; W1 (96 KB) is copied over ring slots 0..3
-// when a group's tiles are done - during the tiles that space buys four more slots.
-constexpr uint32_t RI_W2 = 0;                        // 2 K blocks x [64 hi | 64 lo units][64 k], SW128
-constexpr uint32_t RI_W2_BYTES = 32768;
-constexpr uint32_t RI_W1 = 32768;                    // image offset of W1 hi; W1 lo follows
-constexpr uint32_t RI_W1_BYTES = 98304;              // 2 x 3 K blocks x [128 units][64 k]
-constexpr uint32_t RW1_HI = 0, RW1_LO = 49152;       // ring offsets of the W1 halves in phase 2
+// weight image in global memory (built by build_din_rt in model.cu): W2 | W1 hi | W1 lo.  It is
+// copied over the ring when a group's tiles are done - during the tiles that space is ring slots.
+constexpr uint32_t RI_BYTES = 131072;
+constexpr uint32_t RW2 = 0;                          // ring offsets in phase 2: 2 K blocks x [64 hi | 64 lo units][64 k]
+constexpr uint32_t RW1_HI = 32768;                   // 3 K blocks x [128 units][64 k]
+constexpr uint32_t RW1_LO = RW1_HI + 49152;
 // ring slot: A = [2 rows x 64 positions][hi 32 | lo 32] bf16, SW128 K-major (16 KB)
 //            B = [hi: row0 32 units, row1 32 units | lo: same][32 k] bf16, SWIZZLE_64B K-major (8 KB)
 constexpr uint32_t RS_A = 16384, RS_B = 8192, RS_SLOT = RS_A + RS_B;
-constexpr uint32_t RING_BYTES = kRtSlots * RS_SLOT;  // 172032
+constexpr uint32_t RING_BYTES = kRtSlots * RS_SLOT;  // 196608
+// phase-2 scratch behind the weight images
+constexpr uint32_t P2_XB = RI_BYTES;                 // 3 K blocks x [32 rows hi | 32 rows lo][64 k]  (24 KB)
+constexpr uint32_t P2_H1 = P2_XB;                    // 2 K blocks, after layer 1
+constexpr uint32_t P2_RED = P2_XB + 24576;           // f32 [64][32]
+constexpr uint32_t P2_ZP = P2_XB + 32768;            // f32 [16][32]
+static_assert(P2_ZP + 2048 <= RING_BYTES, "phase-2 scratch must fit in the ring");
 // scratch behind the ring
 constexpr uint32_t RX_IDS = 0;                       // int [32][64]
 constexpr uint32_t RX_CAND = 8192;                   // f32 [32][32]
 constexpr uint32_t RX_CST = 12288;                   // f32 [32][32]
 constexpr uint32_t RX_POOL = 16384;                  // f32 [32][32]
-constexpr uint32_t RX_B2 = 20480;                    // 2 consumers x 2 K blocks x [8 n][64 positions] bf16, SW128
-constexpr uint32_t RX_NUMS = 24576;                  // f32 [32][8]
-constexpr uint32_t RX_BYTES = 25600;
-// phase-2 overlays of the (then idle) ring
-constexpr uint32_t P2_XB = RI_W1_BYTES;              // 3 K blocks x [32 rows hi | 32 rows lo][64 k]  (24 KB)
-constexpr uint32_t P2_H1 = P2_XB;                    // 2 K blocks, after layer 1
-constexpr uint32_t P2_RED = P2_XB + 24576;           // f32 [64][32]
-constexpr uint32_t P2_ZP = P2_XB + 32768;            // f32 [16][32]
-static_assert(P2_ZP + 2048 <= RING_BYTES, "phase-2 scratch must fit behind the W1 image");
+constexpr uint32_t RX_B2 = 20480;                    // [consumer][buffer] x 2 K blocks x [8 n][64 positions] bf16, SW128
+constexpr uint32_t RX_NUMS = 28672;                  // f32 [32][8]
+constexpr uint32_t RX_BYTES = 29696;
 // tensor memory columns
 constexpr uint32_t TMC_D1 = 0;                       // consumer q: [128 q, 128 q + 128)
-constexpr uint32_t TMC_D2 = 256;                     // consumer q, tile row r: 256 + 16 q + 8 r, 8 columns
-constexpr uint32_t TMC_TOP1 = 320, TMC_TOP2 = 384;   // top-MLP accumulators, 64 columns each
+constexpr uint32_t TMC_D2 = 256;                     // consumer q, buffer u, tile row r: 256 + 32 q + 16 u + 8 r
+constexpr uint32_t TMC_TOP1 = 384, TMC_TOP2 = 448;   // top-MLP accumulators, 64 columns each
 
 __device__ unsigned long long g_din_rt_trace[40];
 #define RT_TRACE(slot, cond)                                                     \
@@ -127,16 +129,23 @@ __device__ __forceinline__ int rt_f32_roundtrip_id(int id) {   // DIN.py:95,125:
   return __float2int_rz(__int2float_rn(id));
 }
 
+// inputs of a group a thread requests from HBM before it needs them
+struct RtGroupLoads {
+  int id_a, id_b;                  // which 0: (movieId, userId) raw; which 1: (userGenre1, movieGenre1)
+  float nv;                        // which 1: numeric sq of the row
+  int hraw[kRtHistPerThread];      // raw history ids of cells tid + u * 512
+};
+
 __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_constant__ DinRtParams p,
                                                                BatchView b) {
   extern __shared__ uint8_t raw[];
-  __shared__ uint64_t wbar;                 // W2 image landed (once per launch)
-  __shared__ uint64_t w1bar;                // W1 image landed (once per group)
+  __shared__ uint64_t wbar;                 // top-MLP weight image landed (once per group)
   __shared__ uint64_t cbar;                 // top-MLP MMAs complete
-  __shared__ uint64_t full[kRtSlots];       // tile operands in place (128 producer arrivals)
+  __shared__ uint64_t full[kRtSlots];       // tile operands in place (128 gatherer + 64 builder arrivals)
   __shared__ uint64_t empty[kRtSlots];      // both MMAs of the tile in the slot have completed
   __shared__ uint64_t d1_full[2];           // consumer q: activation-unit accumulators ready
-  __shared__ uint64_t d2_full[2];           // consumer q: pooled accumulators ready
+  __shared__ uint64_t w_ready[2];           // consumer q: pooling weights written (128 arrivals)
+  __shared__ uint64_t d2_full[2][2];        // consumer q, buffer u: pooled accumulators ready
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
@@ -146,8 +155,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   const int warp_w = __shfl_sync(0xffffffffu, (tid >> 5) & 3, 0);
   const int tw = tid & 127;
   uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
-  uint8_t* img = base;
-  uint8_t* ring = base + RI_W2_BYTES;
+  uint8_t* ring = base;
   uint8_t* xs = ring + RING_BYTES;
   int* ids_s = reinterpret_cast<int*>(xs + RX_IDS);
   float* cand = reinterpret_cast<float*>(xs + RX_CAND);
@@ -158,55 +166,108 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   const int T = p.T;
   const int RPG = p.rows_per_group;
   const int n_groups = (b.B + RPG - 1) / RPG;
+  const bool is_gather = wg == 0, is_issuer = wg == 1 && warp_w == 0;
+  const bool is_builder = wg == 1 && (warp_w == 1 || warp_w == 2), is_consumer = wg >= 2;
+  const bool is_loader = wg == 1 && warp_w == 3;
+  // phase-0 / phase-2 role: row slot, feature pair, float4 index
+  const int xr = tid >> 4, which = (tid >> 3) & 1, sq = tid & 7;
 
-  // ---- prologue (nothing here depends on the previous launch) ---------------------------
+  auto issue_group_loads = [&](int g) -> RtGroupLoads {
+    RtGroupLoads L;
+    L.id_a = L.id_b = -1; L.nv = 0.f;
+#pragma unroll
+    for (int u = 0; u < kRtHistPerThread; ++u) L.hraw[u] = 0;
+    if (g >= n_groups) return L;
+    const int row0 = g * RPG;
+    const int nrows = min(RPG, b.B - row0);
+    if (xr < nrows) {
+      const int row = row0 + xr;
+      if (which == 0) {
+        L.id_a = __ldg(b.movie_id + row);
+        L.id_b = __ldg(b.user_id + row);
+      } else {
+        L.id_a = __ldg(b.user_genre + row * 5);
+        L.id_b = __ldg(b.movie_genre + row * 3);
+        if (sq < kNumNumerics) L.nv = __ldg(b.numerics + row * kNumNumerics + sq);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRtHistPerThread; ++u) {
+      const int i = tid + u * kRtThreads;
+      const int r = i >> 6, t = i & 63;
+      if (r < nrows && t < T) L.hraw[u] = __ldg(b.hist + (size_t)(row0 + r) * b.hist_stride + t);
+    }
+    return L;
+  };
+
+  // ---- prologue (nothing before griddepcontrol.wait depends on the previous launch) ----------
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid < 32) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&wbar, 1);
-    mbar_init(&w1bar, 1);
     mbar_init(&cbar, 1);
-    for (int i = 0; i < kRtSlots; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d2_full[i], 1); }
-    fence_mbar_init();
-    mbar_arrive_expect_tx(&wbar, RI_W2_BYTES);
-    bulk_g2s(img, p.image + RI_W2, RI_W2_BYTES, &wbar);
-  }
-  // pooling weights operand: rows n >= 2 stay zero for the whole launch
-  for (int i = tid; i < 4096 / 16; i += kRtThreads) reinterpret_cast<uint4*>(b2s)[i] = make_uint4(0, 0, 0, 0);
-  // per-thread constants of the two roles
-  // producers: rc[0..7] = (Wsub+Wh)[8 cq .. 8 cq + 7][j], rc[8..15] = Wp[..][j]  (j = tw >> 2, cq = tw & 3)
-  // consumers: rc[0..31] = P_t[j], rc[32..63] = Q_t[j] of position t = tw & 63
-  float rc[64];
-  if (wg < 2) {
-    const int j = tw >> 2, cq = tw & 3;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 v = (i < 2)   ? ldg4(p.waT + j * 32 + 8 * cq + 4 * i)
-                       : (i < 4) ? ldg4(p.wpT + j * 32 + 8 * cq + 4 * (i - 2))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
+    for (int i = 0; i < kRtSlots; ++i) { mbar_init(&full[i], 192); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&w_ready[i], 128);
+      mbar_init(&d2_full[i][0], 1); mbar_init(&d2_full[i][1], 1);
     }
-  } else {
+    fence_mbar_init();
+  }
+  // per-thread constants of the roles
+  //   builders : rc[16 c + 0..7] = (Wsub+Wh)[8 cq .. 8 cq + 7][j], rc[16 c + 8..15] = Wp[..][j],
+  //              j = bt >> 1, cq = 2 (bt & 1) + c, c = 0, 1
+  //   consumers: rc[0..31] = P_t[j], rc[32..63] = Q_t[j] of position t = tw & 63
+  float rc[64];
+  if (is_consumer) {
     const int t = tw & 63;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float4 v = (t < T) ? ldg4(p.pq + (size_t)t * 64 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
     }
+  } else {
+    const int bt = tid & 63, j = bt >> 1, cq0 = 2 * (bt & 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i >> 2, part = (i >> 1) & 1, h = i & 1;          // 16 c + 8 part + 4 h
+      const float* src = (part ? p.wpT : p.waT) + j * 32 + 8 * (cq0 + (c & 1)) + 4 * h;
+      const float4 v = (is_builder && i < 8) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
+    }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
+  RtGroupLoads pre = issue_group_loads(blockIdx.x);     // ids come from HBM: in flight during the sync
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   RT_TRACE(1, tid == 0);
   const uint32_t tbase = tmem_slot;
   const uint32_t lane_base = (uint32_t)(warp_w * 32) << 16;
-  const uint32_t s_img = smem_u32(img), s_ring = smem_u32(ring);
+  const uint32_t s_ring = smem_u32(ring);
   const uint32_t idesc_top = idesc_bf16(128, 2 * kRtRows);
-  uint32_t cphase = 0, w1phase = 0;
-  bool weights_ready = false;
+  uint32_t cphase = 0, wphase = 0;
   int kbase = 0;                                        // tiles of earlier groups of this CTA
+
+  // gatherer constants: chunk c8 of position (16 j + prow)
+  const int c8 = tw & 7, prow = tw >> 3;
+  const uint32_t dst_thread = (uint32_t)prow * 128u + (uint32_t)((c8 ^ (prow & 7)) << 4);
+  auto gather = [&](int k) {                            // local tile k -> slot of global tile kbase + k
+    const int K = kbase + k, slot = K % kRtSlots;
+    if (K >= kRtSlots) mbar_wait(&empty[slot], ((K / kRtSlots) + 1) & 1);
+    uint8_t* A = ring + slot * RS_SLOT;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int* idrow = ids_s + (2 * k + r) * kRtIdsLd;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pos = 16 * j + prow;
+        if (pos < T) {
+          const int id = idrow[pos];
+          cp_async16(A + (r * 64 + 16 * j) * 128 + dst_thread, p.movie_split + (size_t)id * 128 + c8 * 16);
+        }
+      }
+    }
+  };
 
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int row0 = g * RPG;
@@ -214,119 +275,161 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
     const int n_tiles = (nrows + 1) >> 1;
 
     // ================= phase 0: ids, side rows, candidate rows =============================
-    // thread (xr, which, sq): row slot, feature pair, float4 index
-    const int xr = tid >> 4, which = (tid >> 3) & 1, sq = tid & 7;
     float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;     // which 0: (candidate, user); 1: (userGenre1, movieGenre1)
     {
-      const int row = row0 + xr;
       const bool live = xr < nrows;
       if (which == 0) {
         if (live) {
-          const int cid = checked_id(rt_f32_roundtrip_id(__ldg(b.movie_id + row)), p.n_movies, b.err_flag);
-          const int uid = checked_id(__ldg(b.user_id + row), p.n_users, b.err_flag);
+          const int cid = checked_id(rt_f32_roundtrip_id(pre.id_a), p.n_movies, b.err_flag);
+          const int uid = checked_id(pre.id_b, p.n_users, b.err_flag);
           fa = ldg4(p.movie + (size_t)cid * 32 + 4 * sq);
           fb = ldg4(p.user + (size_t)uid * 32 + 4 * sq);
         }
-        *reinterpret_cast<float4*>(cand + xr * 32 + 4 * sq) = fa;
-      } else {
-        float nv = 0.f;
-        if (live) {
-          int ug = __ldg(b.user_genre + row * 5), mg = __ldg(b.movie_genre + row * 3);
-          if (sq < kNumNumerics) nv = __ldg(b.numerics + row * kNumNumerics + sq);
-          if (ug >= p.n_genres) { atomicExch(b.err_flag, 1); ug = -1; }
-          if (mg >= p.n_genres) { atomicExch(b.err_flag, 1); mg = -1; }
-          if (ug >= 0) fa = ldg4(p.ugenre + ug * 32 + 4 * sq);
-          if (mg >= 0) fb = ldg4(p.mgenre + mg * 32 + 4 * sq);
-        }
-        nums[xr * 8 + sq] = nv;
+      } else if (live) {
+        int ug = pre.id_a, mg = pre.id_b;
+        if (ug >= p.n_genres) { atomicExch(b.err_flag, 1); ug = -1; }
+        if (mg >= p.n_genres) { atomicExch(b.err_flag, 1); mg = -1; }
+        if (ug >= 0) fa = ldg4(p.ugenre + ug * 32 + 4 * sq);
+        if (mg >= 0) fb = ldg4(p.mgenre + mg * 32 + 4 * sq);
       }
-      // history ids (float32 round trip, range check) of the whole group: 4 independent loads per thread
-      {
-        int rawv[kRtRows * kRtIdsLd / kRtThreads];
+      RT_TRACE(30, tid == 0);
+      // history ids (float32 round trip, range check) of the whole group
 #pragma unroll
-        for (int u = 0; u < kRtRows * kRtIdsLd / kRtThreads; ++u) {
-          const int i = tid + u * kRtThreads;
-          const int r = i >> 6, t = i & 63;
-          rawv[u] = (r < nrows && t < T) ? __ldg(b.hist + (size_t)(row0 + r) * b.hist_stride + t) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kRtRows * kRtIdsLd / kRtThreads; ++u)
-          ids_s[tid + u * kRtThreads] = checked_id(rt_f32_roundtrip_id(rawv[u]), p.n_movies, b.err_flag);
-      }
+      for (int u = 0; u < kRtHistPerThread; ++u)
+        ids_s[tid + u * kRtThreads] = checked_id(rt_f32_roundtrip_id(pre.hraw[u]), p.n_movies, b.err_flag);
+      RT_TRACE(31, tid == 0);
       for (int i = tid; i < kRtRows * 32; i += kRtThreads) pooled[i] = 0.f;
       // tile rows of positions >= T are read by both MMAs: keep them zero (phase 2 of the previous
-      // group used the ring as scratch)
+      // group used the ring for the weight images and as scratch)
       const int pad = 64 - T;
       for (int i = tid; i < kRtSlots * 2 * pad * 8; i += kRtThreads) {
         const int c = i & 7, rest = i >> 3;
         const int pr = rest % pad, sr = rest / pad;               // sr = slot * 2 + row
-        const int pos = T + pr;
-        *reinterpret_cast<uint4*>(ring + (sr >> 1) * RS_SLOT + ((sr & 1) * 64 + pos) * 128 + (c << 4)) =
+        *reinterpret_cast<uint4*>(ring + (sr >> 1) * RS_SLOT + ((sr & 1) * 64 + T + pr) * 128 + (c << 4)) =
             make_uint4(0, 0, 0, 0);
       }
     }
-    __syncthreads();
-    RT_TRACE(2, tid == 0);
-    // ================= phase 1: tiles ====================================================
-    if (wg < 2) {
-      // ---------------- producers ----------------
-      const int pj = tw >> 2, cq = tw & 3, c8 = tw & 7, prow = tw >> 3;
-      const uint32_t dst_thread = (uint32_t)prow * 128u + (uint32_t)((c8 ^ (prow & 7)) << 4);
-      auto gather = [&](int k) {                            // local tile k -> slot of global tile kbase + k
-        const int K = kbase + k, slot = K % kRtSlots;
-        if (K >= kRtSlots) mbar_wait(&empty[slot], ((K / kRtSlots) + 1) & 1);
-        uint8_t* A = ring + slot * RS_SLOT;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int* idrow = ids_s + (2 * k + r) * kRtIdsLd;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int pos = 16 * j + prow;
-            if (pos < T) {
-              const int id = idrow[pos];
-              cp_async16(A + (r * 64 + 16 * j) * 128 + dst_thread, p.movie_split + (size_t)id * 128 + c8 * 16);
-            }
-          }
-        }
-      };
-      const int first = (wg - kbase) & 1;                   // local tiles k with (kbase + k) & 1 == wg
+    RT_TRACE(32, tid == 0);
+    __syncthreads();                                        // history ids staged
+    RT_TRACE(33, tid == 0);
+    if (is_gather) {
 #pragma unroll
       for (int a = 0; a < kRtAhead; ++a) {
-        if (first + 2 * a < n_tiles) gather(first + 2 * a);
+        if (a < n_tiles) gather(a);
         cp_async_commit();
       }
-      for (int k = first; k < n_tiles; k += 2) {
-        const int K = kbase + k, slot = K % kRtSlots;
-        // ---- B operand of the tile: W_r = (Wsub+Wh) + diag(c_r) Wp, bf16 hi / lo
-        uint8_t* Bt = ring + slot * RS_SLOT + RS_A;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const float* c = cand + (2 * k + r) * 32 + 8 * cq;
-          const float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + 4);
-          const float2 v0 = fma2(make_float2(c0.x, c0.y), make_float2(rc[8], rc[9]), make_float2(rc[0], rc[1]));
-          const float2 v1 = fma2(make_float2(c0.z, c0.w), make_float2(rc[10], rc[11]), make_float2(rc[2], rc[3]));
-          const float2 v2 = fma2(make_float2(c1.x, c1.y), make_float2(rc[12], rc[13]), make_float2(rc[4], rc[5]));
-          const float2 v3 = fma2(make_float2(c1.z, c1.w), make_float2(rc[14], rc[15]), make_float2(rc[6], rc[7]));
-          const Split2 s0 = split_pack(v0.x, v0.y), s1 = split_pack(v1.x, v1.y);
-          const Split2 s2 = split_pack(v2.x, v2.y), s3 = split_pack(v3.x, v3.y);
-          const uint32_t n = r * 32 + pj;
-          *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
-          *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
-        }
-        if (k == first + 2) RT_TRACE(23, tid == 0);
+    }
+    RT_TRACE(34, tid == 0);
+    if (which == 0) *reinterpret_cast<float4*>(cand + xr * 32 + 4 * sq) = fa;
+    else nums[xr * 8 + sq] = pre.nv;
+    RT_TRACE(35, tid == 0);
+    __syncthreads();                                        // candidate rows staged
+    RT_TRACE(2, tid == 0);
+
+    // ================= phase 1: tiles ====================================================
+    if (is_gather) {
+      for (int k = 0; k < n_tiles; ++k) {
+        const int slot = (kbase + k) % kRtSlots;
         cp_async_wait<kRtAhead - 1>();                      // this tile's rows have landed (later tiles' may be in flight)
         fence_async_smem();
         mbar_arrive(&full[slot]);
-        if (k == first) RT_TRACE(20, tid == 0);
-        if (k == first + 2) RT_TRACE(21, tid == 0);
-        if (k == first + 4) RT_TRACE(22, tid == 0);
-        // ---- keep kRtAhead tiles in flight: the slot of tile k + 2 kRtAhead frees when tile K - 1 retires
-        if (k + 2 * kRtAhead < n_tiles) gather(k + 2 * kRtAhead);
+        if (k == 0) RT_TRACE(20, tid == 0);
+        if (k == 2) RT_TRACE(21, tid == 0);
+        if (k == 4) RT_TRACE(22, tid == 0);
+        if (k + kRtAhead < n_tiles) gather(k + kRtAhead);   // its slot frees when tile K + kRtAhead - kRtSlots retires
         cp_async_commit();
       }
       cp_async_wait<0>();
-    } else {
-      // ---------------- consumers ----------------
+    } else if (is_builder) {
+      // ---- B operand of every tile: W_r = (Wsub+Wh) + diag(c_r) Wp, bf16 hi / lo
+      const int bt = tid & 63, pj = bt >> 1, cq0 = 2 * (bt & 1);
+      for (int k = 0; k < n_tiles; ++k) {
+        const int K = kbase + k, slot = K % kRtSlots;
+        if (K >= kRtSlots) mbar_wait(&empty[slot], ((K / kRtSlots) + 1) & 1);
+        uint8_t* Bt = ring + slot * RS_SLOT + RS_A;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int cq = cq0 + c;
+            const float* cv = cand + (2 * k + r) * 32 + 8 * cq;
+            const float4 c0 = *reinterpret_cast<const float4*>(cv), c1 = *reinterpret_cast<const float4*>(cv + 4);
+            const float* wa = rc + 16 * c;
+            const float* wp = rc + 16 * c + 8;
+            const float2 v0 = fma2(make_float2(c0.x, c0.y), make_float2(wp[0], wp[1]), make_float2(wa[0], wa[1]));
+            const float2 v1 = fma2(make_float2(c0.z, c0.w), make_float2(wp[2], wp[3]), make_float2(wa[2], wa[3]));
+            const float2 v2 = fma2(make_float2(c1.x, c1.y), make_float2(wp[4], wp[5]), make_float2(wa[4], wa[5]));
+            const float2 v3 = fma2(make_float2(c1.z, c1.w), make_float2(wp[6], wp[7]), make_float2(wa[6], wa[7]));
+            const Split2 s0 = split_pack(v0.x, v0.y), s1 = split_pack(v1.x, v1.y);
+            const Split2 s2 = split_pack(v2.x, v2.y), s3 = split_pack(v3.x, v3.y);
+            const uint32_t n = r * 32 + pj;
+            *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
+            *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
+          }
+        fence_async_smem();
+        mbar_arrive(&full[slot]);
+      }
+    } else if (is_issuer) {
+      // ---- every MMA of the tile phase, in the order the operands become ready
+      auto mma1 = [&](int k) {
+        const int K = kbase + k, slot = K % kRtSlots, q = K & 1;
+        mbar_wait(&full[slot], (K / kRtSlots) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tD1 = tbase + TMC_D1 + 128u * q;
+          const uint64_t ad = smem_desc_sw128(s_ring + slot * RS_SLOT);
+          const uint64_t bd = smem_desc_sw64(s_ring + slot * RS_SLOT + RS_A);
+          mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
+          mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
+          mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
+          mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
+          mma_commit(&d1_full[q]);
+        }
+        __syncwarp();
+      };
+      if (0 < n_tiles) mma1(0);
+      if (1 < n_tiles) mma1(1);
+      for (int k = 0; k < n_tiles; ++k) {
+        const int K = kbase + k, slot = K % kRtSlots, q = K & 1, u = (K >> 1) & 1;
+        mbar_wait(&w_ready[q], (K >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tD2 = tbase + TMC_D2 + 32u * q + 16u * u;
+          const uint32_t s_b2 = smem_u32(b2s) + (q * 2 + u) * 2048;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ring + slot * RS_SLOT + r * 8192 + ks * 2048),
+                     smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
+          mma_commit(&d2_full[q][u]);
+          mma_commit(&empty[slot]);
+        }
+        __syncwarp();
+        if (k + 2 < n_tiles) mma1(k + 2);                   // D1 of consumer q was read before w_ready
+      }
+    } else if (is_loader) {
+      // ---- top-MLP weight images: each ring slot receives its part as soon as its last tile retires
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&wbar, RI_BYTES);
+        const int tail = n_tiles < kRtSlots ? n_tiles : kRtSlots;      // the last `tail` tiles hold distinct slots
+        auto load_slot = [&](int slot) {
+          const uint32_t off = slot * RS_SLOT;
+          if (off < RI_BYTES) bulk_g2s(ring + off, p.image + off, min(RS_SLOT, RI_BYTES - off), &wbar);
+        };
+        for (int sl = 0; sl < kRtSlots; ++sl) {                         // slots no tile of this group uses
+          bool used = false;
+          for (int j = 0; j < tail; ++j) used |= ((kbase + n_tiles - tail + j) % kRtSlots) == sl;
+          if (!used) load_slot(sl);
+        }
+        for (int j = 0; j < tail; ++j) {
+          const int K = kbase + n_tiles - tail + j, slot = K % kRtSlots;
+          mbar_wait(&empty[slot], (K / kRtSlots) & 1);
+          load_slot(slot);
+        }
+      }
+      __syncwarp();
+    } else if (is_consumer) {
       const int q = wg - 2;
       const int r_t = warp_w >> 1, t = tw & 63;             // this thread's tile row and position
       // cst[xr][j] = au_b[j] + sum_e cand[xr][e] (Wc - Wsub)[e][j]: 256 threads x 4 outputs
@@ -344,30 +447,29 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       }
       named_sync(5, 256);
       const uint32_t tD1 = tbase + TMC_D1 + 128u * q;
-      const uint32_t tD2 = tbase + TMC_D2 + 16u * q;
-      uint8_t* myb2 = b2s + q * 2048;
-      const uint32_t s_b2 = smem_u32(myb2);
-      auto issue_mma1 = [&](int k) {
-        const int K = kbase + k, slot = K % kRtSlots;
-        if (warp_w == 0) {
-          mbar_wait(&full[slot], (K / kRtSlots) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = smem_desc_sw128(s_ring + slot * RS_SLOT);
-            const uint64_t bd = smem_desc_sw64(s_ring + slot * RS_SLOT + RS_A);
-            mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
-            mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
-            mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
-            mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
-            mma_commit(&d1_full[q]);
-          }
-          __syncwarp();
+      // pooled accumulators of local tile k -> shared memory
+      auto pool_out = [&](int k) {
+        const int K = kbase + k, u = (K >> 1) & 1;
+        mbar_wait(&d2_full[q][u], (K >> 2) & 1);
+        tc_fence_after();
+        // D2 row m = 16 warp_w + lane (lane < 16): m < 32 -> hi e = m, else lo e = m - 32;
+        // columns 8 r + {0: . w_hi, 1: . w_lo}
+        uint32_t d[16];
+        tmem_ld16(tbase + TMC_D2 + 32u * q + 16u * u + lane_base, d);
+        tmem_ld_wait();
+        if (lane < 16) {
+          const int e = (16 * warp_w + lane) & 31;
+          const bool hi = warp_w < 2;
+          const float p0 = hi ? __uint_as_float(d[0]) + __uint_as_float(d[1]) : __uint_as_float(d[0]);
+          const float p1 = hi ? __uint_as_float(d[8]) + __uint_as_float(d[9]) : __uint_as_float(d[8]);
+          atomicAdd(pooled + (2 * k) * 32 + e, p0);          // two addends per cell: order-independent
+          atomicAdd(pooled + (2 * k + 1) * 32 + e, p1);
         }
+        tc_fence_before();
       };
-      const int first = (q - kbase) & 1;
-      if (first < n_tiles) issue_mma1(first);
+      const int first = (q - kbase) & 1;                    // local tiles k with (kbase + k) & 1 == q
       for (int k = first; k < n_tiles; k += 2) {
-        const int K = kbase + k, slot = K % kRtSlots;
+        const int K = kbase + k, u = (K >> 1) & 1;
         mbar_wait(&d1_full[q], (K >> 1) & 1);
         tc_fence_after();
         if (k == first) RT_TRACE(3, tid == 256);
@@ -401,77 +503,40 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         }
         const float s = (sa.x + sa.y) + (sb.x + sb.y);
         const float w = (t < T) ? 1.f / (1.f + __expf(-s)) : 0.f;
-        if (k == first + 2) RT_TRACE(11, tid == 256);
         {
           // pooling weights operand: K block r_t, row 0 = w hi, row 1 = w lo, column = position
+          // (rows 2..7 feed accumulator columns nobody reads)
           const __nv_bfloat16 wh = __float2bfloat16_rn(w);
           const __nv_bfloat16 wl = __float2bfloat16_rn(w - __bfloat162float(wh));
-          uint8_t* dstw = myb2 + r_t * 1024 + (t & 7) * 2;
+          uint8_t* dstw = b2s + (q * 2 + u) * 2048 + r_t * 1024 + (t & 7) * 2;
           *reinterpret_cast<__nv_bfloat16*>(dstw + sw128_offset(0, t >> 3)) = wh;
           *reinterpret_cast<__nv_bfloat16*>(dstw + sw128_offset(1, t >> 3)) = wl;
         }
         fence_async_smem();
         tc_fence_before();
-        named_sync(1 + wg, 128);
-        if (k == first + 2) RT_TRACE(12, tid == 256);
-        if (k == first + 2) RT_TRACE(18, tid == 288);
-        if (warp_w == 0) {
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ring + slot * RS_SLOT + r * 8192 + ks * 2048),
-                       smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
-            mma_commit(&d2_full[q]);
-            mma_commit(&empty[slot]);
-          }
-          __syncwarp();
-        }
-        if (k == first + 2) RT_TRACE(13, tid == 256);
-        if (k + 2 < n_tiles) issue_mma1(k + 2);
-        if (k == first + 2) RT_TRACE(14, tid == 256);
-        mbar_wait(&d2_full[q], (K >> 1) & 1);
-        tc_fence_after();
-        if (k == first + 2) RT_TRACE(15, tid == 256);
-        if (k == first + 2) RT_TRACE(17, tid == 288);
-        {
-          // D2 row m = 16 warp_w + lane (lane < 16): m < 32 -> hi e = m, else lo e = m - 32;
-          // columns 8 r + {0: . w_hi, 1: . w_lo}
-          uint32_t d[16];
-          tmem_ld16(tD2 + lane_base, d);
-          tmem_ld_wait();
-          if (lane < 16) {
-            const int e = (16 * warp_w + lane) & 31;
-            const bool hi = warp_w < 2;
-            const float p0 = hi ? __uint_as_float(d[0]) + __uint_as_float(d[1]) : __uint_as_float(d[0]);
-            const float p1 = hi ? __uint_as_float(d[8]) + __uint_as_float(d[9]) : __uint_as_float(d[8]);
-            atomicAdd(pooled + (2 * k) * 32 + e, p0);          // two addends per cell: order-independent
-            atomicAdd(pooled + (2 * k + 1) * 32 + e, p1);
-          }
-        }
+        mbar_arrive(&w_ready[q]);
+        if (k == first + 2) RT_TRACE(11, tid == 256);
+        if (k - 2 >= 0) pool_out(k - 2);                    // the previous tile's pooling MMAs finished long ago
         if (k == first + 2) RT_TRACE(16, tid == 256);
-        tc_fence_before();
-        if (k == first) RT_TRACE(4, tid == 256);
       }
+      {
+        const int last = first + ((n_tiles - 1 - first) & ~1);
+        if (first < n_tiles) pool_out(last);
+      }
+      RT_TRACE(4, tid == 256);
     }
     kbase += n_tiles;
     tc_fence_before();
     __syncthreads();
     RT_TRACE(5, tid == 0);
-    if (tid == 0) {   // every MMA that read ring slots 0..3 has completed: the W1 image may land there
-      mbar_arrive_expect_tx(&w1bar, RI_W1_BYTES);
-      for (uint32_t off = 0; off < RI_W1_BYTES; off += 32768u) bulk_g2s(ring + off, p.image + RI_W1 + off, 32768u, &w1bar);
-    }
+    pre = issue_group_loads(g + gridDim.x);               // next group's ids: request from HBM now
 
     // ================= phase 2: top MLP on the group's 32 row slots, whole CTA ===============
     {
       uint8_t* xb = ring + P2_XB;
       if (which == 0) {
-        const float4 c4s = *reinterpret_cast<const float4*>(cand + xr * 32 + 4 * sq);
         rt_store_x4(xb, 0, xr, 32 + 4 * sq, fb);             // K block 0: [userGenre1 | userId]
-        rt_store_x4(xb, 1, xr, 32 + 4 * sq, c4s);            // K block 1: [pooled | candidate]
+        rt_store_x4(xb, 1, xr, 32 + 4 * sq, fa);             // K block 1: [pooled | candidate]
         const uint32_t zoff = 2 * 8192u + sw128_offset(xr, 4 + (sq >> 1)) + ((sq & 1) ? 8u : 0u);
         *reinterpret_cast<uint2*>(xb + zoff) = make_uint2(0u, 0u);          // K block 2: [movieGenre1 | 0]
         *reinterpret_cast<uint2*>(xb + zoff + 4096u) = make_uint2(0u, 0u);
@@ -488,7 +553,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
     const uint32_t tT1 = tbase + TMC_TOP1, tT2 = tbase + TMC_TOP2;
     RT_TRACE(24, tid == 0);
     if (wg == 0 && warp_w == 0) {
-      mbar_wait(&w1bar, w1phase);
+      mbar_wait(&wbar, wphase);
       tc_fence_after();
       if (elect_one()) {
         uint32_t acc = 0;
@@ -509,18 +574,17 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       __syncwarp();
     }
     RT_TRACE(25, tid == 0);
+    wphase ^= 1;
     // this thread is unit `tw` of layer 1 for row slots 8*wg .. 8*wg+7
     const float b1 = __ldg(p.b1 + tw), a1 = __ldg(p.a1 + tw);
     float w1n[kNumNumerics];
 #pragma unroll
     for (int n = 0; n < kNumNumerics; ++n) w1n[n] = __ldg(p.w1num + n * 128 + tw);
-    w1phase ^= 1;
     mbar_wait(&cbar, cphase);
     cphase ^= 1;
     __syncwarp();
     tc_fence_after();
     RT_TRACE(6, tid == 0);
-    if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
     {
       uint32_t d[8], d2[8];
       tmem_ld8(tT1 + 8 * wg + lane_base, d);               // W1 . X hi
@@ -553,7 +617,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         uint32_t acc = 0;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t a = smem_desc_sw128(s_img + RI_W2 + kb * 16384);
+          const uint64_t a = smem_desc_sw128(s_ring + RW2 + kb * 16384);
           const uint64_t hs = smem_desc_sw128(s_ring + P2_H1 + kb * 8192);      // [H1 hi | H1 lo], N = 64
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -597,10 +661,10 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       __syncthreads();
       {  // 32 rows x 16 partial sums of 4 units
         const int r = tid & 31, pt = tid >> 5;
-        float s = 0.f;
+        float sum = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) s += red[(pt * 4 + u) * 32 + r];
-        zp[pt * 32 + r] = s;
+        for (int uu = 0; uu < 4; ++uu) sum += red[(pt * 4 + uu) * 32 + r];
+        zp[pt * 32 + r] = sum;
       }
       __syncthreads();
       if (tid < kRtRows) {
@@ -617,7 +681,6 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
     __syncthreads();                                     // ring and scratch are reused by the next group
     RT_TRACE(7, tid == 0);
   }
-  if (!weights_ready) mbar_wait(&wbar, 0);               // never exit with the bulk copy in flight
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_slot, 512);
@@ -649,7 +712,7 @@ cudaError_t read_din_rt_trace(unsigned long long* out40) {
   return cudaMemcpyFromSymbol(out40, g_din_rt_trace, sizeof(unsigned long long) * 40);
 }
 
-size_t din_rt_smem_bytes() { return 1024 + RI_W2_BYTES + RING_BYTES + RX_BYTES; }
+size_t din_rt_smem_bytes() { return 1024 + RING_BYTES + RX_BYTES; }
 
 cudaError_t launch_din_rt(const DinRtParams& p, const BatchView& b, cudaStream_t s) {
   if (b.B <= 0) return cudaSuccess;
