@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <vector>
 #include "umma.cuh"
 using namespace srs::umma;
@@ -58,6 +59,21 @@ __global__ void __launch_bounds__(128) gather_kernel(const __grid_constant__ CUt
       }
       for (int i = max(0, tiles_per_cta - DEPTH); i < tiles_per_cta; ++i) mbar_wait(&full[i % DEPTH], (i / DEPTH) & 1);
     }
+  } else if (method == 4) {
+    for (int i = 0; i < tiles_per_cta; ++i) {
+      const int slot = i % DEPTH;
+      uint8_t* tile = base + slot * (TILE_POS * 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pos = 16 * j + (tid >> 3), c = tid & 7;
+        const int id = min(max(__ldg(my_ids + i * TILE_POS + pos), 0), vmax);
+        const uint8_t* src = table + (size_t)id * 128 + c * 16;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile + sw128_offset(pos, c))), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (method == 3) {
     for (int i = 0; i < tiles_per_cta; ++i) {
       const int slot = i % DEPTH;
@@ -107,12 +123,13 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
 
 int main(int argc, char** argv) {
   const int box_rows = argc > 1 ? atoi(argv[1]) : 1;
+  const int zipf = argc > 2 ? atoi(argv[2]) : 0;
   EncodeTiled encode = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres));
   if (!encode) { printf("no cuTensorMapEncodeTiled\n"); return 1; }
   const int n_sms = 148;
-  for (int big = 0; big < 2; ++big) {
+  for (int big = 0; big < (zipf ? 1 : 2); ++big) {
     const size_t V = big ? (size_t)1 << 25 : 27279;        // rows of 128 B: 4 GB or 3.5 MB
     uint8_t* table; CK(cudaMalloc(&table, V * 128));
     std::vector<uint16_t> host;
@@ -135,7 +152,13 @@ int main(int argc, char** argv) {
     const size_t n_ids = (size_t)n_sms * tiles_per_cta * TILE_POS;
     std::vector<int> ids(n_ids);
     srand(7);
-    for (auto& v : ids) v = (int)(((size_t)rand() * 32768u + rand()) % V);
+    for (auto& v : ids) {
+      if (zipf) {   // ~Zipf(1): id = floor(V^u) - 1, half of the cells are padding id 0
+        const double u = (double)rand() / RAND_MAX;
+        v = (rand() & 1) ? 0 : (int)(pow((double)V, u)) - 1;
+        if (v < 0) v = 0; if (v >= (int)V) v = (int)V - 1;
+      } else v = (int)(((size_t)rand() * 32768u + rand()) % V);
+    }
     ids[n_ids - 1] = -1; ids[(size_t)(tiles_per_cta - 1) * TILE_POS + 5] = -1; ids[(size_t)(tiles_per_cta - 1) * TILE_POS + 6] = (int)V;  // out of bounds -> zeros?
     int* dids; CK(cudaMalloc(&dids, n_ids * 4));
     CK(cudaMemcpy(dids, ids.data(), n_ids * 4, cudaMemcpyHostToDevice));
@@ -144,10 +167,10 @@ int main(int argc, char** argv) {
     const int smem = 1024 + DEPTH * TILE_POS * 128;
     CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int method = 0; method < 4; ++method) {
+    for (int method = 2; method < 5; method += 2) {
       if (method != 0 && false) continue;
       for (int grid : {1, n_sms, 2 * n_sms, 3 * n_sms}) {
-        if (grid > n_sms && method != 2 && method != 3) continue;
+        
         float best = 1e9f;
         for (int rep = 0; rep < 3; ++rep) {
           CK(cudaEventRecord(e0));

@@ -20,9 +20,10 @@
 //
 // CTA = 512 threads, one per SM, persistent over groups of up to 32 batch rows; tile K (a
 // CTA-global counter) lives in ring slot K % 8.  Warp roles during the tiles:
-//   warps 0-3    gatherers: cp.async the 100 history rows of tile K into the slot, 5 tiles ahead
+//   warps 0-3,7  gatherers: cp.async the 100 history rows of tile K into the slot, 3 tiles ahead
 //   warp  4      issuer: every tcgen05.mma / commit of the tile phase
-//   warps 5-6    builders: the B operand (two W_r) of tile K
+//   warps 5-6    builders: the B operand (two W_r) of tile K; afterwards warp 5 streams the top-MLP
+//                weight images into ring slots as their last tiles retire
 //   warps 8-15   consumers: tile K belongs to consumer K & 1: gate epilogue -> pooling weights,
 //                pooled accumulators of its previous tile -> shared memory
 // Precision: bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) everywhere, as in din_tc.cu.
@@ -37,7 +38,9 @@ using namespace umma;
 constexpr int kRtThreads = 512;
 constexpr int kRtRows = 32;                 // row slots per group = N/2 of the top-MLP MMAs
 constexpr int kRtSlots = 8;                 // ring slots (history tiles in flight or being consumed)
-constexpr int kRtAhead = 5;                 // tiles the gatherers keep in flight ahead of the one they deliver
+constexpr int kRtAhead = 3;                 // tiles the gatherers keep in flight ahead of the one they deliver
+constexpr int kRtGatherThreads = 160;       // warps 0-3 and 7
+constexpr int kRtCopiesPerThread = 7;       // ceil(2 * 64 positions * 8 chunks / 160)
 constexpr int kRtIdsLd = 64;                // ints per row of the staged history ids
 constexpr int kRtHistPerThread = kRtRows * kRtIdsLd / kRtThreads;
 
@@ -61,14 +64,14 @@ static_assert(P2_ZP + 2048 <= RING_BYTES, "phase-2 scratch must fit in the ring"
 constexpr uint32_t RX_IDS = 0;                       // int [32][64]
 constexpr uint32_t RX_CAND = 8192;                   // f32 [32][32]
 constexpr uint32_t RX_CST = 12288;                   // f32 [32][32]
-constexpr uint32_t RX_POOL = 16384;                  // f32 [32][32]
-constexpr uint32_t RX_B2 = 20480;                    // [consumer][buffer] x 2 K blocks x [8 n][64 positions] bf16, SW128
-constexpr uint32_t RX_NUMS = 28672;                  // f32 [32][8]
-constexpr uint32_t RX_BYTES = 29696;
+constexpr uint32_t RX_POOL = 16384;                  // f32 [32][hi | lo][32]
+constexpr uint32_t RX_B2 = 24576;                    // [consumer][buffer] x 2 K blocks x [8 n][64 positions] bf16, SW128
+constexpr uint32_t RX_NUMS = 32768;                  // f32 [32][8]
+constexpr uint32_t RX_BYTES = 33792;
 // tensor memory columns
-constexpr uint32_t TMC_D1 = 0;                       // consumer q: [128 q, 128 q + 128)
-constexpr uint32_t TMC_D2 = 256;                     // consumer q, buffer u, tile row r: 256 + 32 q + 16 u + 8 r
-constexpr uint32_t TMC_TOP1 = 384, TMC_TOP2 = 448;   // top-MLP accumulators, 64 columns each
+constexpr uint32_t TMC_D1 = 0;                       // tile K: [128 (K % 3), + 128)
+constexpr uint32_t TMC_D2 = 384;                     // consumer q, buffer u, tile row r: 384 + 32 q + 16 u + 8 r
+constexpr uint32_t TMC_TOP1 = 0, TMC_TOP2 = 64;      // top-MLP accumulators (phase 2), 64 columns each
 
 __device__ unsigned long long g_din_rt_trace[40];
 #define RT_TRACE(slot, cond)                                                     \
@@ -141,9 +144,9 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   extern __shared__ uint8_t raw[];
   __shared__ uint64_t wbar;                 // top-MLP weight image landed (once per group)
   __shared__ uint64_t cbar;                 // top-MLP MMAs complete
-  __shared__ uint64_t full[kRtSlots];       // tile operands in place (128 gatherer + 64 builder arrivals)
+  __shared__ uint64_t full[kRtSlots];       // tile operands in place (160 gatherer + 64 builder arrivals)
   __shared__ uint64_t empty[kRtSlots];      // both MMAs of the tile in the slot have completed
-  __shared__ uint64_t d1_full[2];           // consumer q: activation-unit accumulators ready
+  __shared__ uint64_t d1_full[3];           // tile K: activation-unit accumulators in buffer K % 3 ready
   __shared__ uint64_t w_ready[2];           // consumer q: pooling weights written (128 arrivals)
   __shared__ uint64_t d2_full[2][2];        // consumer q, buffer u: pooled accumulators ready
   __shared__ uint32_t tmem_slot;
@@ -166,9 +169,8 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   const int T = p.T;
   const int RPG = p.rows_per_group;
   const int n_groups = (b.B + RPG - 1) / RPG;
-  const bool is_gather = wg == 0, is_issuer = wg == 1 && warp_w == 0;
+  const bool is_gather = wg == 0 || (wg == 1 && warp_w == 3), is_issuer = wg == 1 && warp_w == 0;
   const bool is_builder = wg == 1 && (warp_w == 1 || warp_w == 2), is_consumer = wg >= 2;
-  const bool is_loader = wg == 1 && warp_w == 3;
   // phase-0 / phase-2 role: row slot, feature pair, float4 index
   const int xr = tid >> 4, which = (tid >> 3) & 1, sq = tid & 7;
 
@@ -206,13 +208,16 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   if (tid == 0) {
     mbar_init(&wbar, 1);
     mbar_init(&cbar, 1);
-    for (int i = 0; i < kRtSlots; ++i) { mbar_init(&full[i], 192); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kRtSlots; ++i) { mbar_init(&full[i], kRtGatherThreads + 64); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 3; ++i) mbar_init(&d1_full[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&d1_full[i], 1); mbar_init(&w_ready[i], 128);
+      mbar_init(&w_ready[i], 128);
       mbar_init(&d2_full[i][0], 1); mbar_init(&d2_full[i][1], 1);
     }
     fence_mbar_init();
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
+  RtGroupLoads pre = issue_group_loads(blockIdx.x);     // ids come from HBM: requested first, in flight during the sync
   // per-thread constants of the roles
   //   builders : rc[16 c + 0..7] = (Wsub+Wh)[8 cq .. 8 cq + 7][j], rc[16 c + 8..15] = Wp[..][j],
   //              j = bt >> 1, cq = 2 (bt & 1) + c, c = 0, 1
@@ -235,8 +240,6 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
     }
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
-  RtGroupLoads pre = issue_group_loads(blockIdx.x);     // ids come from HBM: in flight during the sync
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -248,25 +251,27 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   uint32_t cphase = 0, wphase = 0;
   int kbase = 0;                                        // tiles of earlier groups of this CTA
 
-  // gatherer constants: chunk c8 of position (16 j + prow)
-  const int c8 = tw & 7, prow = tw >> 3;
-  const uint32_t dst_thread = (uint32_t)prow * 128u + (uint32_t)((c8 ^ (prow & 7)) << 4);
+  // gatherer constants: copy n of this thread moves chunk (i & 7) of history cell (i >> 3), i = gt + 160 n,
+  // cells counted row 0 positions 0..T-1, then row 1
+  const int gt = tid < 128 ? tid : tid - 96;            // warp 7 (tid 224..255) -> 128..159
+  uint32_t g_dst[kRtCopiesPerThread];                   // byte offset in the A tile
+  int g_ids[kRtCopiesPerThread];                        // index into the tile's two id rows, -1: no copy
+#pragma unroll
+  for (int n = 0; n < kRtCopiesPerThread; ++n) {
+    const int i = gt + kRtGatherThreads * n, cell = i >> 3, c = i & 7;
+    const int r = cell >= T ? 1 : 0, pos = cell - r * T;
+    g_ids[n] = cell < 2 * T ? r * kRtIdsLd + pos : -1;
+    g_dst[n] = (uint32_t)(r * 64 + pos) * 128u + (uint32_t)((c ^ (pos & 7)) << 4) ;
+  }
+  const uint32_t g_src = (uint32_t)(gt & 7) * 16u;
   auto gather = [&](int k) {                            // local tile k -> slot of global tile kbase + k
     const int K = kbase + k, slot = K % kRtSlots;
     if (K >= kRtSlots) mbar_wait(&empty[slot], ((K / kRtSlots) + 1) & 1);
     uint8_t* A = ring + slot * RS_SLOT;
+    const int* idrow = ids_s + 2 * k * kRtIdsLd;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int* idrow = ids_s + (2 * k + r) * kRtIdsLd;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pos = 16 * j + prow;
-        if (pos < T) {
-          const int id = idrow[pos];
-          cp_async16(A + (r * 64 + 16 * j) * 128 + dst_thread, p.movie_split + (size_t)id * 128 + c8 * 16);
-        }
-      }
-    }
+    for (int n = 0; n < kRtCopiesPerThread; ++n)
+      if (g_ids[n] >= 0) cp_async16(A + g_dst[n], p.movie_split + (size_t)idrow[g_ids[n]] * 128 + g_src);
   };
 
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -298,36 +303,31 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       for (int u = 0; u < kRtHistPerThread; ++u)
         ids_s[tid + u * kRtThreads] = checked_id(rt_f32_roundtrip_id(pre.hraw[u]), p.n_movies, b.err_flag);
       RT_TRACE(31, tid == 0);
-      for (int i = tid; i < kRtRows * 32; i += kRtThreads) pooled[i] = 0.f;
       // tile rows of positions >= T are read by both MMAs: keep them zero (phase 2 of the previous
       // group used the ring for the weight images and as scratch)
-      const int pad = 64 - T;
-      for (int i = tid; i < kRtSlots * 2 * pad * 8; i += kRtThreads) {
-        const int c = i & 7, rest = i >> 3;
-        const int pr = rest % pad, sr = rest / pad;               // sr = slot * 2 + row
-        *reinterpret_cast<uint4*>(ring + (sr >> 1) * RS_SLOT + ((sr & 1) * 64 + T + pr) * 128 + (c << 4)) =
-            make_uint4(0, 0, 0, 0);
+      const int pad = 64 - T;                                     // thread -> (pad row tid >> 3, chunk tid & 7)
+      if (tid < pad * 8) {
+#pragma unroll
+        for (int sr = 0; sr < kRtSlots * 2; ++sr)                 // sr = slot * 2 + row
+          *reinterpret_cast<uint4*>(ring + (sr >> 1) * RS_SLOT + ((sr & 1) * 64 + T + (tid >> 3)) * 128 +
+                                    ((tid & 7) << 4)) = make_uint4(0, 0, 0, 0);
       }
     }
     RT_TRACE(32, tid == 0);
-    __syncthreads();                                        // history ids staged
+    if (which == 0) *reinterpret_cast<float4*>(cand + xr * 32 + 4 * sq) = fa;
+    else nums[xr * 8 + sq] = pre.nv;
     RT_TRACE(33, tid == 0);
+    __syncthreads();                                        // history ids, candidate rows staged
+    RT_TRACE(2, tid == 0);
+
+    // ================= phase 1: tiles ====================================================
     if (is_gather) {
 #pragma unroll
       for (int a = 0; a < kRtAhead; ++a) {
         if (a < n_tiles) gather(a);
         cp_async_commit();
       }
-    }
-    RT_TRACE(34, tid == 0);
-    if (which == 0) *reinterpret_cast<float4*>(cand + xr * 32 + 4 * sq) = fa;
-    else nums[xr * 8 + sq] = pre.nv;
-    RT_TRACE(35, tid == 0);
-    __syncthreads();                                        // candidate rows staged
-    RT_TRACE(2, tid == 0);
-
-    // ================= phase 1: tiles ====================================================
-    if (is_gather) {
+      RT_TRACE(34, tid == 0);
       for (int k = 0; k < n_tiles; ++k) {
         const int slot = (kbase + k) % kRtSlots;
         cp_async_wait<kRtAhead - 1>();                      // this tile's rows have landed (later tiles' may be in flight)
@@ -369,26 +369,49 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         fence_async_smem();
         mbar_arrive(&full[slot]);
       }
+      // ---- top-MLP weight images: each ring slot receives its part as soon as its last tile retires
+      if (warp_w == 1) {
+    if (lane == 0) {
+          mbar_arrive_expect_tx(&wbar, RI_BYTES);
+          const int tail = n_tiles < kRtSlots ? n_tiles : kRtSlots;      // the last `tail` tiles hold distinct slots
+          auto load_slot = [&](int slot) {
+            const uint32_t off = slot * RS_SLOT;
+            if (off < RI_BYTES) bulk_g2s(ring + off, p.image + off, min(RS_SLOT, RI_BYTES - off), &wbar);
+          };
+          for (int sl = 0; sl < kRtSlots; ++sl) {                         // slots no tile of this group uses
+            bool used = false;
+            for (int j = 0; j < tail; ++j) used |= ((kbase + n_tiles - tail + j) % kRtSlots) == sl;
+            if (!used) load_slot(sl);
+          }
+          for (int j = 0; j < tail; ++j) {
+            const int K = kbase + n_tiles - tail + j, slot = K % kRtSlots;
+            mbar_wait(&empty[slot], (K / kRtSlots) & 1);
+            load_slot(slot);
+          }
+        }
+        __syncwarp();
+      }
     } else if (is_issuer) {
       // ---- every MMA of the tile phase, in the order the operands become ready
       auto mma1 = [&](int k) {
-        const int K = kbase + k, slot = K % kRtSlots, q = K & 1;
+        const int K = kbase + k, slot = K % kRtSlots, db = K % 3;
         mbar_wait(&full[slot], (K / kRtSlots) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tD1 = tbase + TMC_D1 + 128u * q;
+          const uint32_t tD1 = tbase + TMC_D1 + 128u * db;
           const uint64_t ad = smem_desc_sw128(s_ring + slot * RS_SLOT);
           const uint64_t bd = smem_desc_sw64(s_ring + slot * RS_SLOT + RS_A);
           mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
           mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
           mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
           mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
-          mma_commit(&d1_full[q]);
+          mma_commit(&d1_full[db]);
         }
         __syncwarp();
       };
       if (0 < n_tiles) mma1(0);
       if (1 < n_tiles) mma1(1);
+      if (2 < n_tiles) mma1(2);
       for (int k = 0; k < n_tiles; ++k) {
         const int K = kbase + k, slot = K % kRtSlots, q = K & 1, u = (K >> 1) & 1;
         mbar_wait(&w_ready[q], (K >> 1) & 1);
@@ -406,29 +429,8 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
           mma_commit(&empty[slot]);
         }
         __syncwarp();
-        if (k + 2 < n_tiles) mma1(k + 2);                   // D1 of consumer q was read before w_ready
+        if (k + 3 < n_tiles) mma1(k + 3);                   // accumulator buffer K % 3 was read before w_ready
       }
-    } else if (is_loader) {
-      // ---- top-MLP weight images: each ring slot receives its part as soon as its last tile retires
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&wbar, RI_BYTES);
-        const int tail = n_tiles < kRtSlots ? n_tiles : kRtSlots;      // the last `tail` tiles hold distinct slots
-        auto load_slot = [&](int slot) {
-          const uint32_t off = slot * RS_SLOT;
-          if (off < RI_BYTES) bulk_g2s(ring + off, p.image + off, min(RS_SLOT, RI_BYTES - off), &wbar);
-        };
-        for (int sl = 0; sl < kRtSlots; ++sl) {                         // slots no tile of this group uses
-          bool used = false;
-          for (int j = 0; j < tail; ++j) used |= ((kbase + n_tiles - tail + j) % kRtSlots) == sl;
-          if (!used) load_slot(sl);
-        }
-        for (int j = 0; j < tail; ++j) {
-          const int K = kbase + n_tiles - tail + j, slot = K % kRtSlots;
-          mbar_wait(&empty[slot], (K / kRtSlots) & 1);
-          load_slot(slot);
-        }
-      }
-      __syncwarp();
     } else if (is_consumer) {
       const int q = wg - 2;
       const int r_t = warp_w >> 1, t = tw & 63;             // this thread's tile row and position
@@ -446,7 +448,6 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         *reinterpret_cast<float4*>(cst + cr * 32 + j0) = acc;
       }
       named_sync(5, 256);
-      const uint32_t tD1 = tbase + TMC_D1 + 128u * q;
       // pooled accumulators of local tile k -> shared memory
       auto pool_out = [&](int k) {
         const int K = kbase + k, u = (K >> 1) & 1;
@@ -458,19 +459,18 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         tmem_ld16(tbase + TMC_D2 + 32u * q + 16u * u + lane_base, d);
         tmem_ld_wait();
         if (lane < 16) {
-          const int e = (16 * warp_w + lane) & 31;
+          const int m = 16 * warp_w + lane;                  // pooled[row][m]: hi part (m < 32) or lo part
           const bool hi = warp_w < 2;
-          const float p0 = hi ? __uint_as_float(d[0]) + __uint_as_float(d[1]) : __uint_as_float(d[0]);
-          const float p1 = hi ? __uint_as_float(d[8]) + __uint_as_float(d[9]) : __uint_as_float(d[8]);
-          atomicAdd(pooled + (2 * k) * 32 + e, p0);          // two addends per cell: order-independent
-          atomicAdd(pooled + (2 * k + 1) * 32 + e, p1);
+          pooled[(2 * k) * 64 + m] = hi ? __uint_as_float(d[0]) + __uint_as_float(d[1]) : __uint_as_float(d[0]);
+          pooled[(2 * k + 1) * 64 + m] = hi ? __uint_as_float(d[8]) + __uint_as_float(d[9]) : __uint_as_float(d[8]);
         }
         tc_fence_before();
       };
       const int first = (q - kbase) & 1;                    // local tiles k with (kbase + k) & 1 == q
       for (int k = first; k < n_tiles; k += 2) {
         const int K = kbase + k, u = (K >> 1) & 1;
-        mbar_wait(&d1_full[q], (K >> 1) & 1);
+        const uint32_t tD1 = tbase + TMC_D1 + 128u * (K % 3);
+        mbar_wait(&d1_full[K % 3], (K / 3) & 1);
         tc_fence_after();
         if (k == first) RT_TRACE(3, tid == 256);
         if (k == first + 2) RT_TRACE(10, tid == 256);
@@ -541,7 +541,12 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         *reinterpret_cast<uint2*>(xb + zoff) = make_uint2(0u, 0u);          // K block 2: [movieGenre1 | 0]
         *reinterpret_cast<uint2*>(xb + zoff + 4096u) = make_uint2(0u, 0u);
       } else {
-        const float4 pl = *reinterpret_cast<const float4*>(pooled + xr * 32 + 4 * sq);
+        float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xr < nrows) {
+          const float4 ph = *reinterpret_cast<const float4*>(pooled + xr * 64 + 4 * sq);
+          const float4 pw = *reinterpret_cast<const float4*>(pooled + xr * 64 + 32 + 4 * sq);
+          pl = make_float4(ph.x + pw.x, ph.y + pw.y, ph.z + pw.z, ph.w + pw.w);
+        }
         rt_store_x4(xb, 0, xr, 4 * sq, fa);
         rt_store_x4(xb, 1, xr, 4 * sq, pl);
         rt_store_x4(xb, 2, xr, 4 * sq, fb);
