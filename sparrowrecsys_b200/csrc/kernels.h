@@ -180,7 +180,8 @@ struct DinTcParams {
   int trace;               // debug: record phase timestamps of worker 0 (srs_debug_din_trace)
 };
 
-// din_rt.cu: history rows gathered by cp.async into tcgen05 operand tiles (E padded to 32, T <= 64)
+// din_rt.cu (E padded to 32, T <= 64) and din_rt64.cu (E padded to 64, T <= 256): history rows gathered
+// by cp.async into tcgen05 operand tiles; table pitches and the P/Q row length follow the padded E
 struct DinRtParams {
   const float* movie;        // [n_movies][32] fp32 (candidate rows)
   const uint8_t* movie_split;// [n_movies][32 bf16 hi | 32 bf16 lo]  (history rows)
@@ -204,6 +205,7 @@ struct DinRtParams {
   int n_movies, n_users, n_genres;
   int T;
   int rows_per_group;        // set by the launcher
+  int nch;                   // din_rt64: 128-position chunks per row (1 or 2)
   int num_sms;
   int trace;
 };
@@ -213,6 +215,9 @@ cudaError_t launch_din_rt(const DinRtParams& p, const BatchView& b, cudaStream_t
 cudaError_t launch_split_table(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t read_din_rt_trace(unsigned long long* out40);
 cudaError_t setup_din_rt_attributes();
+cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cudaStream_t s);
+cudaError_t setup_din_rt64_attributes();
 cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t read_din_tc_trace(unsigned long long* out40);
 cudaError_t launch_ncf(const NcfParams& p, const BatchView& b, cudaStream_t s);

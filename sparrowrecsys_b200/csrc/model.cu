@@ -20,6 +20,7 @@ cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_din_rt_attributes();
+cudaError_t setup_din_rt64_attributes();
 cudaError_t setup_embmlp_tc_attributes();
 cudaError_t setup_deepfm_tc_attributes();
 }  // namespace srs
@@ -78,6 +79,7 @@ struct srs_model {
   bool use_din_tc = false;
   DinRtParams din_rt{};
   bool use_din_rt = false;
+  bool use_din_rt64 = false;         // din_rt holds the parameters of din_rt64_kernel
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
   DeepFmTcParams fm_tc{};
@@ -716,6 +718,88 @@ int build_din_rt(Builder& B) {
   return B.status;
 }
 
+// Row-tile DIN kernel for E padded to 64 (din_rt64.cu): pre-split movie table (256-byte rows),
+// transposed activation-unit weights, P/Q gate tables, top-MLP images with one K block per feature.
+int build_din_rt64(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, T = s.hist_len, A = 32;
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  const float* au = B.host("au_dense/kernel", 4 * E, A);
+  const float* alpha = B.host("au_prelu/alpha", T, A);
+  const float* auo = B.host("au_out/kernel", A, 1);
+  const float* k1 = B.host("dense/kernel", 5 * E + 7, h0);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  if (B.status != SRS_OK) return B.status;
+  const uint32_t W1HI = 0, W1LO = 81920, W2OFF = 163840, BYTES = 196608;
+  std::vector<uint8_t> img(BYTES, 0);
+  const int base = 3 + 4 * E;
+  const int slot_start[5] = {1, 1 + E, 3 + 2 * E, 3 + 3 * E, base + 1};   // userGenre1, userId, pooled, candidate, movieGenre1
+  auto w1_get = [&](int j, int k) -> float {
+    const int slot = k >> 6, e = k & 63;
+    if (j >= h0 || slot >= 5 || e >= E) return 0.f;
+    return k1[(size_t)(slot_start[slot] + e) * h0 + j];
+  };
+  write_sw128(img.data() + W1HI, 128, 5, false, w1_get);
+  write_sw128(img.data() + W1LO, 128, 5, true, w1_get);
+  auto w2_raw = [&](int i, int k) -> float { return (i < h1 && k < h0) ? k2[(size_t)k * h1 + i] : 0.f; };
+  for (int kb = 0; kb < 2; ++kb)
+    for (int r = 0; r < 128; ++r)
+      for (int c = 0; c < 8; ++c)
+        for (int i = 0; i < 8; ++i) {
+          const float x = w2_raw(r & 63, kb * 64 + c * 8 + i);
+          const uint16_t hb = bf16_rn_bits(x);
+          const uint16_t v = (r < 64) ? hb : bf16_rn_bits(x - u2f((uint32_t)hb << 16));
+          memcpy(img.data() + W2OFF + (size_t)kb * 16384 + sw128_off(r, c) + i * 2, &v, 2);
+        }
+  uint8_t* d_img = nullptr;
+  cudaError_t e = cudaMalloc(&d_img, BYTES);
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc(%u) failed: %s", BYTES, cudaGetErrorString(e));
+  m->owned.push_back(d_img);
+  e = cudaMemcpy(d_img, img.data(), BYTES, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+  std::vector<float> waT(32 * 64, 0.f), wpT(32 * 64, 0.f);
+  for (int j = 0; j < A; ++j)
+    for (int ee = 0; ee < E; ++ee) {
+      waT[(size_t)j * 64 + ee] = au[(size_t)ee * A + j] + au[(size_t)(E + ee) * A + j];
+      wpT[(size_t)j * 64 + ee] = au[(size_t)(3 * E + ee) * A + j];
+    }
+  std::vector<float> pq((size_t)T * 64, 0.f);
+  for (int t = 0; t < T; ++t)
+    for (int j = 0; j < A; ++j) {
+      const float wo = auo[j], aw = alpha[(size_t)t * A + j] * auo[j];
+      pq[(size_t)t * 64 + j] = 0.5f * (wo + aw);
+      pq[(size_t)t * 64 + 32 + j] = 0.5f * (wo - aw);
+    }
+  const int nrows[7] = {base, base + 1 + E, base + 2 + E, base + 3 + E, 0, 1 + 2 * E, 2 + 2 * E};
+  std::vector<float> w1num(8 * 128, 0.f);
+  for (int n = 0; n < 7; ++n)
+    for (int j = 0; j < h0; ++j) w1num[(size_t)n * 128 + j] = k1[(size_t)nrows[n] * h0 + j];
+  DinRtParams& p = m->din_rt;
+  const DinParams& v1 = m->din;                 // tables / vectors uploaded (or borrowed) by build_din, pitch 64
+  void* d_split = nullptr;
+  const size_t split_bytes = (size_t)s.n_movies * 256;
+  e = cudaMalloc(&d_split, split_bytes);
+  if (e != cudaSuccess) return fail(SRS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", split_bytes, cudaGetErrorString(e));
+  m->owned.push_back(d_split);
+  e = launch_split_table64(v1.movie, d_split, s.n_movies, nullptr);
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "table split failed: %s", cudaGetErrorString(e));
+  p.movie = v1.movie; p.movie_split = static_cast<const uint8_t*>(d_split);
+  p.user = v1.user; p.ugenre = v1.ugenre; p.mgenre = v1.mgenre;
+  p.image = d_img;
+  p.waT = B.upload(waT); p.wpT = B.upload(wpT); p.pq = B.upload(pq);
+  p.au_wc = v1.au_wc; p.au_b = v1.au_b;
+  p.b1 = v1.b1; p.a1 = v1.a1; p.w1num = B.upload(w1num);
+  p.b2 = v1.b2; p.a2 = v1.a2; p.w3 = v1.w3;
+  p.au_bout = v1.au_bout; p.b3 = v1.b3;
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.T = T; p.rows_per_group = 32; p.nch = T > 128 ? 2 : 1;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  p.num_sms = sms > 0 ? sms : 148;
+  return B.status;
+}
+
 // Tensor-core EmbeddingMLP / W&D (E <= 12): operand images from the tensors build_embmlp validated.
 int build_embmlp_tc(Builder& B) {
   srs_model* m = B.m;
@@ -856,7 +940,8 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
       break;
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
-      e = m->use_din_rt   ? launch_din_rt(m->din_rt, v, stream)
+      e = m->use_din_rt64 ? launch_din_rt64(m->din_rt, v, stream)
+          : m->use_din_rt ? launch_din_rt(m->din_rt, v, stream)
           : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
                           : launch_din(m->din, v, stream);
       break;
@@ -1009,6 +1094,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_din_attributes());
   CUDA_TRY(setup_din_tc_attributes());
   CUDA_TRY(setup_din_rt_attributes());
+  CUDA_TRY(setup_din_rt64_attributes());
   CUDA_TRY(setup_embmlp_tc_attributes());
   CUDA_TRY(setup_deepfm_tc_attributes());
 
@@ -1067,11 +1153,13 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     default: {
       rc = build_din(B);
       // kernel selection (SRS_DIN_IMPL=cudacore|tc|rt overrides; tc / rt fail loudly on an unsupported shape):
-      //   rt  row-tile kernel, E padded to 32 and T in 9..64
+      //   rt  row-tile kernels: E padded to 32 and T in 9..64 (din_rt), E padded to 64 and T in 9..256 (din_rt64)
       //   tc  per-pair tensor-core kernel, E padded to 32 and T in 9..128
       const char* impl = getenv("SRS_DIN_IMPL");
       const bool fits_tc = m->EP == 32 && spec->hist_len <= 128;
-      const bool fits_rt = m->EP == 32 && spec->hist_len <= 64;
+      const bool fits_rt32 = m->EP == 32 && spec->hist_len <= 64;
+      const bool fits_rt64 = m->EP == 64 && spec->hist_len <= 256;
+      const bool fits_rt = fits_rt32 || fits_rt64;
       bool want_rt = fits_rt && spec->hist_len > 8;
       bool want_tc = !want_rt && fits_tc && spec->hist_len > 8;
       if (impl && !strcmp(impl, "cudacore")) want_rt = want_tc = false;
@@ -1080,16 +1168,21 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
         want_tc = true; want_rt = false;
       }
       if (impl && !strcmp(impl, "rt")) {
-        if (!fits_rt && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rt needs 16 < emb_dim <= 32 and hist_len <= 64");
+        if (!fits_rt && rc == SRS_OK)
+          rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rt needs 16 < emb_dim <= 32 and hist_len <= 64, or 32 < emb_dim <= 64 and hist_len <= 256");
         want_rt = true; want_tc = false;
       }
       if (rc == SRS_OK && want_tc) {
         rc = build_din_tc(B);
         if (rc == SRS_OK) { m->use_din_tc = true; m->kernel_name = "din_tc_kernel"; }
       }
-      if (rc == SRS_OK && want_rt) {
+      if (rc == SRS_OK && want_rt && fits_rt32) {
         rc = build_din_rt(B);
         if (rc == SRS_OK) { m->use_din_rt = true; m->kernel_name = "din_rt_kernel"; }
+      }
+      if (rc == SRS_OK && want_rt && fits_rt64) {
+        rc = build_din_rt64(B);
+        if (rc == SRS_OK) { m->use_din_rt64 = true; m->kernel_name = "din_rt64_kernel"; }
       }
       break;
     }

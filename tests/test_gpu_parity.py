@@ -366,6 +366,46 @@ def test_din_tensor_core_kernel(E, T, B, impl, din_impl):
     assert np.abs(p_cc - p_tc).max() <= 2 * PROB_ATOL
 
 
+@pytest.mark.parametrize("E,T,B", [(64, 200, 512), (64, 128, 100), (48, 129, 33), (33, 9, 17), (64, 256, 65),
+                                   (40, 64, 4097), (64, 200, 1), (64, 130, 148 * 32 + 5)])
+def test_din_row_tile_kernel_wide_embeddings(E, T, B, din_impl):
+    """din_rt64_kernel (csrc/din_rt64.cu): 32 < E <= 64, T <= 256, one or two 128-position chunks per row."""
+    spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=50_000, n_users=5000)
+    W = init_weights(spec, E * 1000 + T)
+    feats = synthetic_features(spec, B, seed=T, uniform_history=(T == 200))
+    din_impl("rt")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_rt64_kernel"
+        p_rt, z_rt = m.predict_with_logits(feats)
+        p_rt2 = m.predict(feats)
+    assert np.array_equal(p_rt, p_rt2)                       # deterministic
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(z_rt - zo).max() <= 5e-4, "logit err %g" % np.abs(z_rt - zo).max()
+    assert np.abs(p_rt - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p_rt - po).max()
+    din_impl("cudacore")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_kernel"
+        p_cc = m.predict(feats)
+    assert np.abs(p_cc - p_rt).max() <= 2 * PROB_ATOL
+
+
+def test_din_row_tile_kernel_wide_row_independence(din_impl):
+    din_impl("rt")
+    spec = default_spec("din", emb_dim=64, hist_len=200, n_movies=300_000, n_users=5000)
+    W = init_weights(spec, 7)
+    B = 2 * 148 * 32 + 77
+    feats = synthetic_features(spec, B, seed=7, uniform_history=True)
+    perm = np.random.default_rng(2).permutation(B)
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_rt64_kernel"
+        p = m.predict(feats)[:, 0]
+        pp = m.predict({k: v[perm] for k, v in feats.items()})[:, 0]
+        assert np.array_equal(pp, p[perm])                   # bit-exact under row permutation
+        lo = m.predict({k: v[:4099] for k, v in feats.items()})[:, 0]
+        hi = m.predict({k: v[4099:] for k, v in feats.items()})[:, 0]
+        assert np.array_equal(np.concatenate([lo, hi]), p)   # sharding invariant
+
+
 @pytest.mark.parametrize("impl", ["tc", "rt"])
 def test_din_tensor_core_row_independence(impl, din_impl):
     din_impl(impl)
