@@ -164,7 +164,12 @@ int srs_model_status(srs_model* m);
 /* Algorithmic bytes per inference of this model (SURVEY.md section 8d definition). */
 int64_t srs_model_bytes_per_inference(const srs_model* m);
 
-/* Name of the kernel variant srs_predict_* dispatches to for this model. */
+/* Name of the kernel variant srs_predict_* dispatches to for this model.  DIN has four
+ * (din_rt_kernel / din_rt64_kernel: tcgen05 row tiles; din_tc_kernel: tcgen05 per pair;
+ * din_kernel: CUDA cores); the choice follows the shape and can be forced with the environment
+ * variable SRS_DIN_IMPL = rt | tc | cudacore read by srs_model_create (a forced variant that does
+ * not support the shape makes srs_model_create fail).  SRS_EMBMLP_IMPL and SRS_DEEPFM_IMPL
+ * (tc | cudacore) do the same for EmbeddingMLP / Wide&Deep and DeepFM. */
 const char* srs_model_kernel_name(const srs_model* m);
 
 /* Number of kernels this library has launched in this process (all models). */
@@ -183,8 +188,9 @@ int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, 
                              float* scores, int32_t device, void* stream);
 
 /* Debug aid for kernel tuning: enable/disable recording of per-phase SM-clock timestamps
- * in the tensor-core DIN kernel (worker 0 of CTA 0) and, if out40 != NULL, synchronise and
- * copy the 40 recorded values out.  No effect on results. */
+ * in the tensor-core DIN kernels (CTA 0; slot meaning: profiles/trace_din_rt.py,
+ * profiles/trace_din_tc.py) and, if out40 != NULL, synchronise and copy the 40 recorded values
+ * out.  No effect on results. */
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40);
 
 /* Micro-benchmark behind the DIN kernel's MMA shape choice: SM cycles for a chain of n_mma
