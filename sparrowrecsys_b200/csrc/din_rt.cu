@@ -154,43 +154,49 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
     return L;
   };
 
-  // ---- prologue (nothing before griddepcontrol.wait depends on the previous launch) ----------
+  // ---- prologue ---------------------------------------------------------------------------
+  // One CTA per SM fills the machine, so the next launch cannot start before this one ends anyway:
+  // the dependency wait comes first and the ids (HBM) are requested before anything else.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
+  RtGroupLoads pre = issue_group_loads(blockIdx.x);
   if (tid < 32) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    mbar_init(&wbar, 1);
-    mbar_init(&cbar, 1);
-    for (int i = 0; i < kRtSlots; ++i) { mbar_init(&full[i], kRtGatherThreads + 64); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 3; ++i) mbar_init(&d1_full[i], 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&w_ready[i], 128);
-      mbar_init(&d2_full[i][0], 1); mbar_init(&d2_full[i][1], 1);
-    }
+  if (tid >= 32 && tid < 64) {                           // warp 1: one mbarrier per lane
+    const int l = tid - 32;
+    if (l < kRtSlots) mbar_init(&full[l], kRtGatherThreads + 64);
+    else if (l < 2 * kRtSlots) mbar_init(&empty[l - kRtSlots], 1);
+    else if (l < 2 * kRtSlots + 3) mbar_init(&d1_full[l - 2 * kRtSlots], 1);
+    else if (l < 2 * kRtSlots + 5) mbar_init(&w_ready[l - 2 * kRtSlots - 3], 128);
+    else if (l < 2 * kRtSlots + 9) mbar_init(&d2_full[(l - 2 * kRtSlots - 5) >> 1][(l - 2 * kRtSlots - 5) & 1], 1);
+    else if (l == 2 * kRtSlots + 9) mbar_init(&wbar, 1);
+    else if (l == 2 * kRtSlots + 10) mbar_init(&cbar, 1);
     fence_mbar_init();
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
-  RtGroupLoads pre = issue_group_loads(blockIdx.x);     // ids come from HBM: requested first, in flight during the sync
   // per-thread constants of the roles
   //   builders : rc[16 c + 0..7] = (Wsub+Wh)[8 cq .. 8 cq + 7][j], rc[16 c + 8..15] = Wp[..][j],
   //              j = bt >> 1, cq = 2 (bt & 1) + c, c = 0, 1
   //   consumers: rc[0..31] = P_t[j], rc[32..63] = Q_t[j] of position t = tw & 63
   float rc[64];
   if (is_consumer) {
-    const int t = tw & 63;
+    const float* src = p.pq + (size_t)min(tw & 63, T - 1) * 64;      // positions >= T: any finite values do (w is forced to 0)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float4 v = (t < T) ? ldg4(p.pq + (size_t)t * 64 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = ldg4(src + 4 * i);
       rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
     }
-  } else {
+  } else if (is_builder) {
     const int bt = tid & 63, j = bt >> 1, cq0 = 2 * (bt & 1);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = i >> 2, part = (i >> 1) & 1, h = i & 1;          // 16 c + 8 part + 4 h
-      const float* src = (part ? p.wpT : p.waT) + j * 32 + 8 * (cq0 + (c & 1)) + 4 * h;
-      const float4 v = (is_builder && i < 8) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 8; ++i) {                                     // index 4 i = 16 c + 8 part + 4 h
+      const int c = i >> 2, part = (i >> 1) & 1, h = i & 1;
+      const float4 v = ldg4((part ? p.wpT : p.waT) + j * 32 + 8 * (cq0 + c) + 4 * h);
       rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
     }
+#pragma unroll
+    for (int i = 32; i < 64; ++i) rc[i] = 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) rc[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
