@@ -187,6 +187,23 @@ int srs_fill_uniform(float* device_ptr, int64_t n, uint64_t seed, float lo, floa
 int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, int32_t dim,
                              float* scores, int32_t device, void* stream);
 
+/* Ranking tail of both online rankers: order n candidate scores descending and return the
+ * first min(k, n) positions (and, if top_scores != NULL, their scores).  Replaces
+ * `candidateScoreMap.entrySet().stream().sorted(comparingByValue(reverseOrder()))` +
+ * `subList(0, size)` (RecForYouProcess.java:56-59,92-94; SimilarMovieProcess.java:26-31,
+ * 133-135).  Order of Double.compareTo: NaN ranks first, -0.0 after 0.0; equal scores - in
+ * HashMap iteration order in the reference, i.e. unspecified - rank by position, lower
+ * first.  Device pointers; asynchronous on `stream`. */
+int srs_topk_device(const float* scores, int32_t n, int32_t k, int32_t* top_idx,
+                    float* top_scores, int32_t device, void* stream);
+
+/* One ranking call from host buffers: H2D of the candidate batch, forward kernel, ranking
+ * kernel, D2H of the min(k, B) best positions and scores only.  Replaces
+ * RecForYouProcess.ranker (:69-95) with model "nerualcf" followed by getRecList's subList:
+ * the score vector never leaves the device.  Synchronous; SRS_ERR_RANGE as srs_predict_host. */
+int srs_rank_host(srs_model* m, const srs_batch* batch, int32_t k, int32_t* top_idx,
+                  float* top_scores);
+
 /* Debug aid for kernel tuning: enable/disable recording of per-phase SM-clock timestamps
  * in the tensor-core DIN kernels (CTA 0; slot meaning: profiles/trace_din_rt.py,
  * profiles/trace_din_tc.py) and, if out40 != NULL, synchronise and copy the 40 recorded values

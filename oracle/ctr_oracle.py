@@ -391,3 +391,32 @@ def cosine_similarity(query, cands):
     n1 = (q * q).astype(np.float64).sum()
     n2 = (c * c).astype(np.float64).sum(axis=1)
     return dot / (np.sqrt(n1) * np.sqrt(n2))
+
+
+def java_double_compare(a, b):
+    """java.lang.Double.compare, the order `Map.Entry.comparingByValue` sorts boxed Doubles
+    by: numeric order, then -0.0 < 0.0, and NaN (canonicalised) above +infinity."""
+    import struct
+    a, b = float(a), float(b)
+    if a < b:
+        return -1
+    if a > b:
+        return 1
+    bits = lambda x: 0x7FF8000000000000 if x != x else struct.unpack("<q", struct.pack("<d", x))[0]
+    ba, bb = bits(a), bits(b)
+    return 0 if ba == bb else (-1 if ba < bb else 1)
+
+
+def rank_topk(scores, k):
+    """The ranker tail of online/recprocess/RecForYouProcess.java:92-94 (same in
+    SimilarMovieProcess.java:133-135) and the `subList(0, size)` of getRecList (:56-59):
+    candidates sorted by score with `comparingByValue(Comparator.reverseOrder())`, first
+    `size` kept.  The Java stream sort is stable over the HashMap's (unspecified) iteration
+    order; here equal scores keep candidate order.  Returns (positions int32, scores float32).
+    Pure-Python comparison sort: meant for the few thousand candidates a request ranks."""
+    from functools import cmp_to_key
+    s = np.asarray(scores, np.float32).reshape(-1)
+    d = [float(v) for v in s]
+    order = sorted(range(len(d)), key=cmp_to_key(lambda i, j: java_double_compare(d[j], d[i])))
+    order = np.asarray(order[:max(int(k), 0)], np.int32)
+    return order, s[order]

@@ -39,7 +39,7 @@ EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_d
            "srs_predict_device", "srs_predict_host", "srs_predict_host_batches", "srs_num_slots", "srs_predict_host_async",
            "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
            "srs_model_kernel_name", "srs_launch_count", "srs_fill_uniform",
-           "srs_cosine_scores_device", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
+           "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
 
 _lib = None
 
@@ -99,6 +99,12 @@ def load():
     lib.srs_cosine_scores_device.restype = C.c_int
     lib.srs_cosine_scores_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_int32, C.c_void_p]
+    lib.srs_topk_device.restype = C.c_int
+    lib.srs_topk_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_void_p]
+    lib.srs_rank_host.restype = C.c_int
+    lib.srs_rank_host.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_int32, C.c_void_p,
+                                  C.c_void_p]
     lib.srs_debug_din_trace.restype = C.c_int
     lib.srs_debug_din_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.srs_debug_umma_bench.restype = C.c_int

@@ -58,6 +58,8 @@ struct Slot {
   uint8_t* d_block = nullptr;       // one allocation: [movie|user|hist|movie_genre|user_genre|numerics]
   float* d_probs = nullptr;
   float* d_logits = nullptr;
+  int rank_capacity = 0;            // srs_rank_host only: rows d_rank can rank
+  uint8_t* d_rank = nullptr;        // [top_idx cap | top_scores cap | sort scratch]
   int* h_err = nullptr;             // pinned mirror of the device error flag
 };
 
@@ -990,11 +992,11 @@ int ensure_slot(srs_model* m, Slot& s, int B) {
   return SRS_OK;
 }
 
-int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits,
-                 bool copy_err = true) {
+// H2D of the batch into the slot's staging and the forward kernel, on the slot's stream;
+// the scores are left in s.d_probs (and s.d_logits).
+int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits) {
   int rc = check_batch(m, b);
   if (rc != SRS_OK) return rc;
-  if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
   CUDA_TRY(cudaSetDevice(m->device));
   rc = ensure_slot(m, s, b->B);
   if (rc != SRS_OK) return rc;
@@ -1040,9 +1042,17 @@ int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float*
   v.movie_genre = reinterpret_cast<const int32_t*>(d + L.mg);
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
-  v.probs = s.d_probs; v.logits = logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
-  rc = launch(m, v, s.stream);
+  v.probs = s.d_probs; v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
+  return launch(m, v, s.stream);
+}
+
+int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits,
+                 bool copy_err = true) {
+  if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
+  int rc = stage_and_launch(m, s, b, logits != nullptr);
   if (rc != SRS_OK) return rc;
+  if (b->B == 0) return SRS_OK;
+  const size_t B = (size_t)b->B;
   CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (logits) CUDA_TRY(cudaMemcpyAsync(logits, s.d_logits, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (copy_err)
@@ -1211,7 +1221,7 @@ void srs_model_destroy(srs_model* m) {
   cudaSetDevice(m->device);
   for (Slot& s : m->slots) {
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-    cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits);
+    cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_rank);
     if (s.h_err) cudaFreeHost(s.h_err);
   }
   for (void* p : m->owned) cudaFree(p);
@@ -1319,6 +1329,55 @@ int srs_cosine_scores_device(const float* query, const float* cands, int32_t n, 
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(launch_cosine(query, cands, n, dim, scores, static_cast<cudaStream_t>(stream)));
   return SRS_OK;
+}
+
+int srs_topk_device(const float* scores, int32_t n, int32_t k, int32_t* top_idx,
+                    float* top_scores, int32_t device, void* stream) {
+  if (n < 0 || k < 0) return fail(SRS_ERR_INVALID, "negative n or k");
+  if (n == 0 || k == 0) return SRS_OK;
+  if (!scores || !top_idx) return fail(SRS_ERR_INVALID, "null pointer");
+  if (n > (1 << 30)) return fail(SRS_ERR_INVALID, "at most 2^30 scores");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  const size_t need = topk_scratch_bytes(n);
+  if (need) CUDA_TRY(cudaMallocAsync(&scratch, need, s));
+  cudaError_t e = launch_topk(scores, n, k, top_idx, top_scores, scratch, s);
+  if (scratch) cudaFreeAsync(scratch, s);
+  CUDA_TRY(e);
+  return SRS_OK;
+}
+
+int srs_rank_host(srs_model* m, const srs_batch* b, int32_t k, int32_t* top_idx,
+                  float* top_scores) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (k < 0) return fail(SRS_ERR_INVALID, "negative k");
+  std::lock_guard<std::mutex> lock(m->mu);
+  Slot& s = m->slots[kSlots];
+  int rc = stage_and_launch(m, s, b, false);
+  if (rc != SRS_OK) return rc;
+  if (b->B == 0 || k == 0) return wait_slot(m, s);
+  if (!top_idx) return fail(SRS_ERR_INVALID, "top_idx is null");
+  const int n = b->B;
+  if (k > n) k = n;
+  if (n > s.rank_capacity) {
+    cudaFree(s.d_rank);
+    s.d_rank = nullptr;
+    s.rank_capacity = 0;
+    const int cap = s.capacity;     // >= n after stage_and_launch
+    CUDA_TRY(cudaMalloc(&s.d_rank, (size_t)cap * 8 + topk_scratch_bytes(cap) + 256));
+    s.rank_capacity = cap;
+  }
+  const size_t cap = (size_t)s.rank_capacity;
+  int32_t* d_idx = reinterpret_cast<int32_t*>(s.d_rank);
+  float* d_top = reinterpret_cast<float*>(s.d_rank + cap * 4);
+  void* scratch = s.d_rank + cap * 8;
+  CUDA_TRY(launch_topk(s.d_probs, n, k, d_idx, d_top, scratch, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (top_scores)
+    CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  return wait_slot(m, s);
 }
 
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {

@@ -214,6 +214,22 @@ class CTRModel:
         _lib.check(self._lib.srs_predict_host(self._h, C.byref(b), probs.ctypes.data, lp))
         return probs
 
+    def rank(self, features: Mapping[str, object], size: int):
+        """`RecForYouProcess.getRecList`'s tail for one request: score the candidate rows
+        and return the best `size` (positions int32 [k], scores float32 [k], best first;
+        equal scores by position) - `srs_rank_host`, only k results leave the device."""
+        enc = encode_batch(self.spec, features)
+        k = max(0, min(int(size), enc.B))
+        idx = np.empty(k, np.int32)
+        top = np.empty(k, np.float32)
+        if k == 0:
+            return idx, top
+        keep = []
+        b = _host_struct(enc, keep)
+        _lib.check(self._lib.srs_rank_host(self._h, C.byref(b), k, idx.ctypes.data,
+                                           top.ctypes.data))
+        return idx, top
+
     # ---- pipelined host path -----------------------------------------------------------
     def num_slots(self) -> int:
         return int(self._lib.srs_num_slots())

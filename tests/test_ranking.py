@@ -1,0 +1,136 @@
+"""Ranking tail of the online rankers: the oracle's restatement
+of `sorted(comparingByValue(reverseOrder()))` + `subList(0, size)`
+(online/recprocess/RecForYouProcess.java:56-59,92-94) on CPU, and the device ranking
+(`srs_topk_device`, `srs_rank_host`) against it, bit exact, on the GPU."""
+import numpy as np
+import pytest
+
+from oracle import ctr_oracle as O
+
+
+# ---- oracle (CPU) ------------------------------------------------------------------------
+def test_java_double_compare_total_order():
+    inf, nan = float("inf"), float("nan")
+    chain = [-inf, -1.5, -0.0, 0.0, 1e-30, 2.0, inf, nan]
+    for i, a in enumerate(chain):
+        for j, b in enumerate(chain):
+            assert O.java_double_compare(a, b) == (i > j) - (i < j), (a, b)
+
+
+def test_rank_topk_matches_default_ranker_scores():
+    # RecForYouProcess.java:86-90: the default branch scores candidate i with (n - i),
+    # so the ranked list is the candidate list itself.
+    n = 800
+    idx, top = O.rank_topk(np.arange(n, 0, -1, dtype=np.float32), 10)
+    assert idx.tolist() == list(range(10)) and top.tolist() == list(range(800, 790, -1))
+
+
+def test_rank_topk_ties_nan_and_cut():
+    s = np.array([0.5, np.nan, 0.5, -0.0, 0.0, 1.0, -np.inf, 0.5], np.float32)
+    idx, top = O.rank_topk(s, 100)                  # size > n: the whole list (:56-59)
+    assert idx.tolist() == [1, 5, 0, 2, 7, 4, 3, 6]
+    assert np.isnan(top[0]) and top[1] == 1.0
+    assert O.rank_topk(s, 3)[0].tolist() == [1, 5, 0]
+    assert O.rank_topk(s, 0)[0].size == 0 and O.rank_topk(np.zeros(0, np.float32), 5)[0].size == 0
+
+
+def test_rank_topk_agrees_with_numpy_on_distinct_scores():
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal(3000).astype(np.float32)
+    s = np.unique(s)
+    rng.shuffle(s)
+    idx, _ = O.rank_topk(s, 200)
+    assert np.array_equal(idx, np.argsort(-s.astype(np.float64), kind="stable")[:200])
+
+
+# ---- device (GPU) --------------------------------------------------------------------------
+def _device_topk(s, k):
+    import torch
+    from sparrowrecsys_b200.ranking import topk_device
+    idx, top = topk_device(torch.from_numpy(s).cuda(), k)
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), top.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 5), (31, 31), (33, 7), (800, 10), (800, 800),
+                                 (1000, 1), (4096, 100), (4097, 50), (10000, 10000),
+                                 (70000, 300)])
+def test_topk_device_bit_exact(n, k):
+    rng = np.random.default_rng(n * 7 + k)
+    s = rng.standard_normal(n).astype(np.float32)
+    s[rng.integers(0, n, n // 3)] = np.float32(0.25)          # ties
+    if n > 8:
+        s[3], s[5], s[6], s[7] = np.nan, -0.0, 0.0, np.inf
+        s[n - 1] = -np.inf
+    idx, top = _device_topk(s, k)
+    ridx, rtop = O.rank_topk(s, k)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(top.view(np.uint32), rtop.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_topk_device_large_properties():
+    """Size-independent properties at a size the Python oracle would be slow for."""
+    n, k = 1 << 20, 5000
+    rng = np.random.default_rng(11)
+    s = rng.random(n, dtype=np.float32)                        # many exact ties at 2^-24 grid
+    idx, top = _device_topk(s, k)
+    assert len(np.unique(idx)) == k and np.array_equal(s[idx], top)
+    assert np.all(np.diff(top) <= 0)
+    same = np.diff(top) == 0
+    assert np.all(np.diff(idx.astype(np.int64))[same] > 0)     # ties by position
+    assert top[-1] >= np.partition(s, n - k)[n - k]            # nothing better left out
+    assert np.array_equal(idx, np.lexsort((np.arange(n), -s.astype(np.float64)))[:k])
+
+
+@pytest.mark.gpu
+def test_rank_host_neuralcf_golden_and_oracle():
+    """RecForYouProcess.getRecList with model "nerualcf": one user, 800 candidates, the
+    reference's shipped weights; positions bit exact against the oracle's ranking of the
+    device scores, scores against the oracle forward."""
+    from conftest import load_golden_weights
+    from sparrowrecsys_b200.model import CTRModel
+    from sparrowrecsys_b200.spec import default_spec
+    W = load_golden_weights("neuralcf_002")
+    spec = default_spec("neuralcf")
+    f = {"movieId": np.arange(1, 801, dtype=np.int32), "userId": np.full(800, 10351, np.int32)}
+    with CTRModel(spec, W) as m:
+        p = m.predict(f)[:, 0]
+        idx, top = m.rank(f, 10)
+        idx_all, _ = m.rank(f, 5000)
+    ridx, rtop = O.rank_topk(p, 10)
+    assert np.array_equal(idx, ridx) and np.array_equal(top, rtop)
+    assert np.array_equal(idx_all, O.rank_topk(p, 800)[0])
+    po, _ = O.forward(spec, W, f)
+    assert np.abs(top - po[idx, 0]).max() < 1e-6
+    assert set(idx.tolist()) == set(O.rank_topk(po[:, 0], 10)[0].tolist())
+
+
+@pytest.mark.gpu
+def test_rank_host_din_large_batch():
+    from sparrowrecsys_b200.features import synthetic_features
+    from sparrowrecsys_b200.model import CTRModel
+    from sparrowrecsys_b200.spec import baseline_spec
+    from sparrowrecsys_b200.weights import init_weights
+    spec = baseline_spec("cfg3_din")
+    feats = synthetic_features(spec, 6000, seed=9)            # > 4096: the multi-CTA sort
+    with CTRModel(spec, init_weights(spec, 2)) as m:
+        p = m.predict(feats)[:, 0]
+        idx, top = m.rank(feats, 64)
+    ridx, rtop = O.rank_topk(p, 64)
+    assert np.array_equal(idx, ridx) and np.array_equal(top, rtop)
+
+
+@pytest.mark.gpu
+def test_rank_by_embedding_matches_reference_emb_ranker():
+    """ranker(..., "emb"): Embedding.calculateSimilarity + sort (RecForYouProcess.java:74-78)."""
+    from sparrowrecsys_b200.ranking import rank_by_embedding
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal(10).astype(np.float32)
+    c = rng.standard_normal((800, 10)).astype(np.float32)
+    idx, top = rank_by_embedding(q, c, 20)
+    ref = O.cosine_similarity(q, c)
+    ridx, _ = O.rank_topk(ref.astype(np.float32), 20)
+    assert np.array_equal(idx, ridx)
+    assert np.abs(top - ref[idx]).max() < 1e-6
