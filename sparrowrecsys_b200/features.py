@@ -66,21 +66,15 @@ def genre_to_index(values) -> np.ndarray:
     if arr.dtype.kind in "iu":          # already indexed by the caller
         return arr.astype(np.int32)
     flat = arr.ravel()
-    if flat.shape[0] > 4096:            # vectorised: look up each distinct value once
-        as_str = np.array([v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat[:0]],
-                          dtype=object)
-        uniq, inv = np.unique(flat.astype(str) if flat.dtype != object or not any(
-            isinstance(v, bytes) for v in flat[:64]) else np.array(
-                [v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat], dtype=str),
-            return_inverse=True)
-        lut = np.array([_GENRE_INDEX.get(str(u), -1) for u in uniq], dtype=np.int32)
-        return lut[inv].reshape(arr.shape)
-    out = np.empty(flat.shape[0], dtype=np.int32)
-    for i, v in enumerate(flat):
-        if isinstance(v, bytes):
-            v = v.decode("utf-8", "replace")
-        out[i] = _GENRE_INDEX.get(v, -1)
-    return out.reshape(arr.shape)
+    if flat.dtype.kind == "S":
+        flat = np.char.decode(flat, "utf-8", "replace")
+    elif flat.dtype == object and any(isinstance(v, bytes) for v in flat):
+        flat = np.array([v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat],
+                        dtype=object)
+    # look up each distinct value once (a batch holds at most 20 of them)
+    uniq, inv = np.unique(flat.astype(str), return_inverse=True)
+    lut = np.array([_GENRE_INDEX.get(str(u), -1) for u in uniq], dtype=np.int32)
+    return lut[inv.reshape(-1)].reshape(arr.shape)
 
 
 def _as_1d(features: Mapping[str, object], key: str) -> np.ndarray:

@@ -13,17 +13,30 @@ This module answers exactly that contract, so the unmodified Java server can poi
 
 Row-format instances are turned into the feature dict of `model.predict` (columns by key;
 a key missing from an instance takes the `make_csv_dataset(na_value="0")` defaults: 0 for
-numbers, "" for strings), scored in one library call, and returned in request order.
-Errors use TF-Serving's shape: HTTP 400 `{"error": "..."}`.
+numbers, "" for strings), scored, and returned in request order.  Errors use TF-Serving's
+shape: HTTP 400 `{"error": "..."}`.
+
+Two things sit between the socket and the library call:
+
+* **feature fill** - with `--features <samples.csv>` (or a `FeatureStore` passed to
+  `serve`), model inputs that no instance of a request carries are read from the
+  reference's `uf:<userId>` / `mf:<movieId>` hashes (`featurestore.py`), so the Java
+  server, which posts only `(userId, movieId)`, can be answered by DIN / DeepFM / W&D;
+* **cross-request micro-batching** (`MicroBatcher`) - Jetty runs one blocking POST per
+  worker thread (`online/util/HttpClient.java:21-40`); requests that arrive while a
+  library call is in flight are concatenated into the next call and the scores split back
+  per request, so the GPU sees one batch per round trip instead of one per thread.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import queue
 import re
 import threading
+import time
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
-from typing import Callable, Dict, List, Mapping
+from typing import Callable, Dict, List, Mapping, Optional
 
 import numpy as np
 
@@ -33,12 +46,20 @@ _PATH = re.compile(r"^/v1/models/([^/:]+)(?:/versions/\d+)?:predict$")
 _STRING_KEYS = set(MOVIE_GENRE_KEYS) | set(USER_GENRE_KEYS)
 
 
-def instances_to_features(spec: ModelSpec, instances: List[Mapping[str, object]]) -> Dict[str, np.ndarray]:
-    """TF-Serving row format -> dict of columns for `predict`."""
+def instances_to_features(spec: ModelSpec, instances: List[Mapping[str, object]],
+                          store=None) -> Dict[str, np.ndarray]:
+    """TF-Serving row format -> dict of columns for `predict`.  With a `FeatureStore`,
+    inputs that no instance carries come from the `uf:` / `mf:` hashes."""
     if not isinstance(instances, list) or not instances:
         raise ValueError("'instances' must be a non-empty list")
+    if not all(isinstance(inst, Mapping) for inst in instances):
+        raise ValueError("each instance must be a JSON object (row format)")
     feats: Dict[str, np.ndarray] = {}
+    absent = []
     for key in spec.required_keys():
+        if store is not None and not any(key in inst for inst in instances):
+            absent.append(key)
+            continue
         if key in _STRING_KEYS:
             col = np.array([str(inst.get(key, "")) for inst in instances], dtype=object)
         else:
@@ -48,11 +69,130 @@ def instances_to_features(spec: ModelSpec, instances: List[Mapping[str, object]]
             else:
                 col = col.astype(np.float32)
         feats[key] = col
+    if absent:
+        from .featurestore import fill_instances
+        fill_instances(feats, absent, store, spec.hist_len)
     return feats
 
 
-def make_handler(models: Mapping[str, tuple], lock: threading.Lock):
-    """`models`: name -> (spec, predict_fn); predict_fn(features) -> float32 [N,1]."""
+class MicroBatcher:
+    """Concatenate concurrent requests into one `predict` call.
+
+    `submit(features)` blocks the calling (HTTP worker) thread and returns that request's
+    float32 [n,1] scores.  One dispatcher thread takes the oldest waiting request, adds
+    whatever else is already queued (up to `max_rows` rows; optionally lingering
+    `max_wait_s` for more), scores the concatenation once and splits the result.  With
+    `max_wait_s = 0` batching adds no latency: a lone request is dispatched at once, and
+    requests pile up only while the previous call is running.  If a merged call fails
+    (e.g. one request holds an out-of-range id) its requests are re-run one by one, so an
+    error reaches only the request that caused it."""
+
+    def __init__(self, predict_fn: Callable[[Dict[str, np.ndarray]], np.ndarray],
+                 max_rows: int = 8192, max_wait_s: float = 0.0):
+        self.predict_fn = predict_fn
+        self.max_rows = int(max_rows)
+        self.max_wait_s = float(max_wait_s)
+        self.calls = 0                    # library calls made
+        self.requests = 0                 # requests served
+        self._q: "queue.Queue" = queue.Queue()
+        self._held = None                 # a request taken off the queue that did not fit
+        self._stop = False
+        self._thread = threading.Thread(target=self._run, name="srs-microbatcher", daemon=True)
+        self._thread.start()
+
+    def submit(self, feats: Dict[str, np.ndarray]) -> np.ndarray:
+        if self._stop:
+            raise RuntimeError("batcher is closed")
+        item = {"feats": feats, "n": len(next(iter(feats.values()))), "done": threading.Event(),
+                "out": None, "err": None}
+        self._q.put(item)
+        item["done"].wait()
+        if item["err"] is not None:
+            raise item["err"]
+        return item["out"]
+
+    def close(self):
+        self._stop = True
+        self._q.put(None)
+        self._thread.join(timeout=5)
+
+    # ---- dispatcher thread ----------------------------------------------------------------
+    _EMPTY = object()
+
+    def _take(self, timeout):
+        """Next waiting request, `None` (the close sentinel) or `_EMPTY`."""
+        if self._held is not None:
+            item, self._held = self._held, None
+            return item
+        try:
+            return self._q.get(timeout=timeout) if timeout > 0 else self._q.get_nowait()
+        except queue.Empty:
+            return self._EMPTY
+
+    def _run(self):
+        closing = False
+        while not closing:
+            first = self._held if self._held is not None else self._q.get()
+            self._held = None
+            if first is None:
+                break
+            group, rows = [first], first["n"]
+            deadline = time.monotonic() + self.max_wait_s
+            while rows < self.max_rows:
+                nxt = self._take(deadline - time.monotonic())
+                if nxt is None:
+                    closing = True
+                    break
+                if nxt is self._EMPTY:
+                    if time.monotonic() >= deadline:
+                        break
+                    continue
+                if rows + nxt["n"] > self.max_rows:
+                    self._held = nxt
+                    break
+                group.append(nxt)
+                rows += nxt["n"]
+            self._score(group)
+        leftovers = [] if self._held is None else [self._held]
+        while True:                       # closed: fail whatever is still waiting
+            try:
+                leftovers.append(self._q.get_nowait())
+            except queue.Empty:
+                break
+        for item in leftovers:
+            if item is not None:
+                item["err"] = RuntimeError("batcher is closed")
+                item["done"].set()
+
+    def _score(self, group):
+        try:
+            if len(group) == 1:
+                merged = group[0]["feats"]
+            else:
+                merged = {k: np.concatenate([g["feats"][k] for g in group])
+                          for k in group[0]["feats"]}
+            self.calls += 1
+            out = np.asarray(self.predict_fn(merged), np.float32).reshape(-1, 1)
+            lo = 0
+            for g in group:
+                g["out"] = out[lo:lo + g["n"]]
+                lo += g["n"]
+        except Exception as e:            # noqa: BLE001 - routed to the request(s) below
+            if len(group) == 1:
+                group[0]["err"] = e
+            else:
+                for g in group:
+                    self._score([g])
+                return
+        self.requests += len(group)
+        for g in group:
+            g["done"].set()
+
+
+def make_handler(models: Mapping[str, tuple], lock: threading.Lock, store=None,
+                 batchers: Optional[Mapping[str, MicroBatcher]] = None):
+    """`models`: name -> (spec, predict_fn); predict_fn(features) -> float32 [N,1].
+    `batchers`: name -> MicroBatcher over that predict_fn (else calls serialise on `lock`)."""
 
     class Handler(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
@@ -76,9 +216,12 @@ def make_handler(models: Mapping[str, tuple], lock: threading.Lock):
             try:
                 n = int(self.headers.get("Content-Length", "0"))
                 req = json.loads(self.rfile.read(n) or b"{}")
-                feats = instances_to_features(spec, req.get("instances"))
-                with lock:                       # one GPU stream of work at a time per process
-                    p = predict_fn(feats)
+                feats = instances_to_features(spec, req.get("instances"), store)
+                if batchers and m.group(1) in batchers:
+                    p = batchers[m.group(1)].submit(feats)
+                else:
+                    with lock:                   # one library call at a time per process
+                        p = predict_fn(feats)
                 self._send(200, {"predictions": [[float(v)] for v in np.asarray(p).reshape(-1)]})
             except (ValueError, KeyError, TypeError, json.JSONDecodeError) as e:
                 self._send(400, {"error": str(e)})
@@ -93,10 +236,18 @@ def make_handler(models: Mapping[str, tuple], lock: threading.Lock):
     return Handler
 
 
-def serve(models: Mapping[str, tuple], host: str = "127.0.0.1", port: int = 8501) -> ThreadingHTTPServer:
-    """Start the server in the calling thread's process; returns the server object
-    (call `.serve_forever()`; `.shutdown()` from another thread stops it)."""
-    return ThreadingHTTPServer((host, port), make_handler(models, threading.Lock()))
+def serve(models: Mapping[str, tuple], host: str = "127.0.0.1", port: int = 8501, store=None,
+          micro_batch: bool = True, max_rows: int = 8192,
+          max_wait_s: float = 0.0) -> ThreadingHTTPServer:
+    """Build the server (call `.serve_forever()`; `.shutdown()` from another thread stops
+    it).  `store`: a `FeatureStore` for inputs the requests do not carry.  `micro_batch`:
+    merge concurrent requests per model (`srv.batchers[name]` exposes the counters)."""
+    batchers = {name: MicroBatcher(fn, max_rows, max_wait_s) for name, (_, fn) in models.items()} \
+        if micro_batch else {}
+    srv = ThreadingHTTPServer((host, port), make_handler(models, threading.Lock(), store, batchers))
+    srv.daemon_threads = True
+    srv.batchers = batchers
+    return srv
 
 
 def main():
@@ -108,11 +259,21 @@ def main():
     ap.add_argument("--host", default="127.0.0.1")
     ap.add_argument("--port", type=int, default=8501)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--features", help="sample CSV (trainingSamples.csv layout) to build the "
+                    "uf:/mf: feature store from, for requests that carry only userId/movieId")
+    ap.add_argument("--no-micro-batch", action="store_true")
+    ap.add_argument("--max-wait-us", type=float, default=0.0,
+                    help="linger this long for more requests before a library call")
     args = ap.parse_args()
     from . import tfrecmodel
     mod = getattr(tfrecmodel, args.model)
     model = mod.load(savedmodel=args.savedmodel, seed=args.seed, device=args.device)
-    srv = serve({args.name: (model.spec, model.predict)}, args.host, args.port)
+    store = None
+    if args.features:
+        from .featurestore import FeatureStore
+        store = FeatureStore.from_samples(args.features)
+    srv = serve({args.name: (model.spec, model.predict)}, args.host, args.port, store=store,
+                micro_batch=not args.no_micro_batch, max_wait_s=args.max_wait_us * 1e-6)
     print("serving %s as /v1/models/%s:predict on %s:%d (%s)"
           % (args.model, args.name, args.host, args.port, model.kernel_name))
     srv.serve_forever()

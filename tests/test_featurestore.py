@@ -1,0 +1,128 @@
+"""Serving-side feature assembly: the `uf:` / `mf:` hash layout
+of FeatureEngForRecModel.scala:130-174,208-259 and the request assembly above `predict`."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from sparrowrecsys_b200 import featurestore as FS
+from sparrowrecsys_b200 import serving
+from sparrowrecsys_b200.features import encode_batch, load_samples_csv
+from sparrowrecsys_b200.spec import default_spec
+
+CSV = os.path.join(GOLDEN, "samples_head.csv")
+
+
+@pytest.fixture(scope="module")
+def store():
+    return FS.FeatureStore.from_samples(CSV)
+
+
+@pytest.fixture(scope="module")
+def raw():
+    return FS.read_sample_strings(CSV)
+
+
+def test_hash_layout_matches_the_spark_job(store, raw):
+    # field sets of the two valueMaps (FeatureEngForRecModel.scala:155-161, 237-251)
+    uid = raw["userId"][0]
+    assert set(store.backend.hgetall("uf:" + uid)) == {
+        "userRatedMovie1", "userRatedMovie2", "userRatedMovie3", "userRatedMovie4",
+        "userRatedMovie5", "userGenre1", "userGenre2", "userGenre3", "userGenre4", "userGenre5",
+        "userRatingCount", "userAvgReleaseYear", "userReleaseYearStddev", "userAvgRating",
+        "userRatingStddev"}
+    assert set(store.backend.hgetall("mf:" + raw["movieId"][0])) == {
+        "movieGenre1", "movieGenre2", "movieGenre3", "movieRatingCount", "releaseYear",
+        "movieAvgRating", "movieRatingStddev"}
+    assert store.user_features(999999) == {}                     # absent key: empty map
+    assert len(store.backend.keys("uf:*")) == len(set(raw["userId"]))
+    assert store.movie_ids() == sorted({int(m) for m in raw["movieId"]})
+
+
+def test_latest_row_per_id_wins_and_strings_are_verbatim(store, raw):
+    ts = np.array([int(t) for t in raw["timestamp"]])
+    for id_key, fields, get in (("userId", FS.USER_FIELDS, store.user_features),
+                                ("movieId", FS.MOVIE_FIELDS, store.movie_features)):
+        ids = np.array(raw[id_key])
+        for ident in list(dict.fromkeys(raw[id_key]))[:60]:
+            rows = np.flatnonzero(ids == ident)
+            latest = rows[np.argmax(ts[rows])]                   # first among equal maxima
+            h = get(int(ident))
+            assert h == {f: raw[f][latest] for f in fields}
+    # na.fill(""): an empty CSV cell stays an empty string in the hash
+    empties = [i for i, v in enumerate(raw["userRatedMovie5"]) if v == ""]
+    assert empties, "fixture should contain users with short histories"
+
+
+def test_assemble_reproduces_training_rows(store, raw):
+    """A row that is the latest sample of both its user and its movie must be rebuilt
+    exactly (same encoded batch) from the two hashes."""
+    spec = default_spec("din")
+    cols = load_samples_csv(CSV)
+    table = FS.MovieFeatureTable.from_store(store, spec.n_movies)
+    ts = np.array([int(t) for t in raw["timestamp"]])
+    uid, mid = np.array(raw["userId"]), np.array(raw["movieId"])
+    checked = 0
+    for r in range(len(ts)):
+        ur, mr = np.flatnonzero(uid == uid[r]), np.flatnonzero(mid == mid[r])
+        if ur[np.argmax(ts[ur])] != r or mr[np.argmax(ts[mr])] != r:
+            continue
+        f = FS.assemble(int(uid[r]), store.user_features(int(uid[r])), [int(mid[r])], table)
+        a = encode_batch(spec, f)
+        b = encode_batch(spec, {k: v[r:r + 1] for k, v in cols.items()})
+        for name in ("movie_id", "user_id", "hist", "movie_genre", "user_genre", "numerics"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), (r, name)
+        checked += 1
+    assert checked >= 5
+
+
+def test_assemble_one_user_many_candidates(store, raw):
+    spec = default_spec("widendeep")
+    table = FS.MovieFeatureTable.from_store(store, spec.n_movies)
+    uid = int(raw["userId"][0])
+    cands = store.movie_ids()[:40] + [999]                        # 999: no hash -> defaults
+    f = FS.assemble(uid, store.user_features(uid), cands, table)
+    assert set(spec.required_keys()) <= set(f)
+    n = len(cands)
+    assert all(len(v) == n for v in f.values())
+    assert f["userId"].tolist() == [uid] * n and f["movieId"].tolist() == cands
+    assert len(set(f["userGenre1"].tolist())) == 1                # user side broadcast
+    assert f["movieGenre1"][-1] == "" and f["releaseYear"][-1] == 0 and not table.present[999]
+    h = store.movie_features(cands[3])
+    assert f["movieGenre2"][3] == h["movieGenre2"] and f["releaseYear"][3] == int(h["releaseYear"])
+    assert f["movieAvgRating"].dtype == np.float32 and f["movieRatingCount"].dtype == np.int32
+    enc = encode_batch(spec, f)                                   # goes straight into predict
+    assert enc.B == n and enc.hist.shape == (n, 1)
+    with pytest.raises(ValueError):
+        table.gather(np.array([spec.n_movies]))
+
+
+def test_missing_fields_take_csv_defaults():
+    s = FS.FeatureStore(FS.DictBackend({"uf:7": {"userGenre1": "Drama", "userAvgRating": "",
+                                                 "userRatedMovie1": "12"}}))
+    p = FS.parse_user_features(s.user_features(7), hist_len=8)
+    assert p["userRatedMovie1"] == 12 and p["userRatedMovie2"] == 0 and p["userRatedMovie8"] == 0
+    assert p["userAvgRating"] == 0.0 and p["userGenre1"] == "Drama" and p["userGenre2"] == ""
+    assert FS.parse_int("1995.0") == 1995 and FS.parse_int(b" 3 ") == 3 and FS.parse_float("") == 0.0
+
+
+def test_serving_fills_absent_inputs_from_the_store(store, raw):
+    """The Java server posts only (userId, movieId) (RecForYouProcess.java:118-127); with a
+    store the richer models get the rest from the hashes."""
+    spec = default_spec("din")
+    uid, mids = int(raw["userId"][0]), [int(m) for m in raw["movieId"][:4]]
+    inst = [{"userId": uid, "movieId": m} for m in mids]
+    f = serving.instances_to_features(spec, inst, store)
+    table = FS.MovieFeatureTable.from_store(store, spec.n_movies)
+    g = FS.assemble(uid, store.user_features(uid), mids, table)
+    a, b = encode_batch(spec, f), encode_batch(spec, g)
+    for name in ("movie_id", "user_id", "hist", "movie_genre", "user_genre", "numerics"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    # a key carried by the request wins over the store
+    inst[0]["userGenre1"] = "Western"
+    f2 = serving.instances_to_features(spec, inst, store)
+    assert f2["userGenre1"].tolist() == ["Western", "", "", ""]
+    # without a store: plain defaults, as before
+    f3 = serving.instances_to_features(spec, [{"userId": uid, "movieId": mids[0]}])
+    assert f3["userGenre1"].tolist() == [""] and f3["releaseYear"].tolist() == [0.0]

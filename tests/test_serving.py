@@ -1,6 +1,7 @@
 """TF-Serving-compatible front: wire contract of RecForYouProcess.callNeuralCFTFServing."""
 import json
 import threading
+import time
 import urllib.error
 import urllib.request
 
@@ -83,3 +84,128 @@ def test_http_front_on_the_cuda_model():
     finally:
         srv.shutdown()
         model.close()
+
+
+# ---- cross-request micro-batching (host logic, stand-in scorer) ---------------------------
+def _feats(ids):
+    ids = np.asarray(ids, np.int64)
+    return {"movieId": ids, "userId": ids * 10}
+
+
+def test_micro_batcher_merges_requests_that_wait_behind_a_call():
+    gate, first_in = threading.Event(), threading.Event()
+    seen = []
+
+    def scorer(f):
+        seen.append(f["movieId"].tolist())
+        if len(seen) == 1:
+            first_in.set()
+            gate.wait(10)
+        return (f["movieId"] + f["userId"] * 0.001).astype(np.float32).reshape(-1, 1)
+
+    mb = serving.MicroBatcher(scorer, max_rows=1000)
+    out = {}
+    worker = lambda name, ids: out.__setitem__(name, mb.submit(_feats(ids)))
+    t0 = threading.Thread(target=worker, args=("a", [1, 2]))
+    t0.start()
+    assert first_in.wait(10)                        # call 1 is running with request a alone
+    rest = [threading.Thread(target=worker, args=(n, ids))
+            for n, ids in (("b", [3]), ("c", [4, 5, 6]), ("d", [7]))]
+    for t in rest:
+        t.start()
+    deadline = time.monotonic() + 10
+    while mb._q.qsize() < 3 and time.monotonic() < deadline:
+        time.sleep(0.005)
+    gate.set()
+    for t in [t0] + rest:
+        t.join(10)
+    mb.close()
+    assert seen[0] == [1, 2] and len(seen) == 2 and sorted(seen[1]) == [3, 4, 5, 6, 7]
+    assert mb.calls == 2 and mb.requests == 4
+    for name, ids in (("a", [1, 2]), ("b", [3]), ("c", [4, 5, 6]), ("d", [7])):
+        exp = np.array(ids, np.float32) * np.float32(1.01)
+        assert out[name].shape == (len(ids), 1)
+        np.testing.assert_allclose(out[name][:, 0], exp, rtol=1e-6)
+
+
+def test_micro_batcher_respects_max_rows_and_isolates_errors():
+    gate, first_in = threading.Event(), threading.Event()
+    sizes = []
+
+    def scorer(f):
+        sizes.append(len(f["movieId"]))
+        if len(sizes) == 1:
+            first_in.set()
+            gate.wait(10)
+        if (f["movieId"] < 0).any():
+            raise ValueError("movie id out of range")
+        return f["movieId"].astype(np.float32).reshape(-1, 1)
+
+    mb = serving.MicroBatcher(scorer, max_rows=4)
+    res = {}
+
+    def worker(name, ids):
+        try:
+            res[name] = mb.submit(_feats(ids))
+        except ValueError as e:
+            res[name] = e
+
+    t0 = threading.Thread(target=worker, args=("w", [9]))
+    t0.start()
+    assert first_in.wait(10)
+    ts = []
+    for name, ids in (("x", [1, 2]), ("bad", [-1]), ("y", [3]), ("z", [4, 5, 6])):
+        t = threading.Thread(target=worker, args=(name, ids))
+        t.start()
+        ts.append(t)
+        while mb._q.qsize() < len(ts):              # keep the arrival order deterministic
+            time.sleep(0.002)
+    gate.set()
+    for t in [t0] + ts:
+        t.join(10)
+    mb.close()
+    assert isinstance(res["bad"], ValueError)
+    assert res["x"][:, 0].tolist() == [1, 2] and res["y"][:, 0].tolist() == [3]
+    assert res["z"][:, 0].tolist() == [4, 5, 6] and res["w"][:, 0].tolist() == [9]
+    # call 1: w; call 2: x+bad+y merged (4 rows) fails -> re-run one by one; then z alone
+    assert sizes == [1, 4, 2, 1, 1, 3]
+    with pytest.raises(RuntimeError):
+        mb.submit(_feats([1]))
+
+
+def test_concurrent_http_requests_share_library_calls():
+    """Many Jetty-style blocking POSTs at once: fewer scorer calls than requests, every
+    response in its own request's order."""
+    from oracle import ctr_oracle as O
+    spec = default_spec("neuralcf")
+    W = load_golden_weights("neuralcf_002")
+    lock = threading.Lock()
+
+    def scorer(f):
+        with lock:
+            time.sleep(0.02)          # a call long enough for requests to queue
+            return O.forward(spec, W, f)[0]
+
+    srv, port = _run({"recmodel": (spec, scorer)})
+    try:
+        results = {}
+
+        def client(i):
+            inst = [{"userId": 10351, "movieId": 52 + ((i + j) % 2)} for j in range(3)]
+            results[i] = _post(port, "/v1/models/recmodel:predict", {"instances": inst})
+
+        threads = [threading.Thread(target=client, args=(i,)) for i in range(16)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(30)
+        golden = {52: 0.68536943, 53: 0.17321654}
+        for i in range(16):
+            code, body = results[i]
+            assert code == 200
+            exp = [golden[52 + ((i + j) % 2)] for j in range(3)]
+            np.testing.assert_allclose([p[0] for p in body["predictions"]], exp, atol=1e-6)
+        mb = srv.batchers["recmodel"]
+        assert mb.requests == 16 and mb.calls < 16
+    finally:
+        srv.shutdown()
