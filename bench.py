@@ -56,6 +56,8 @@ WORKLOADS = {
     "cfg4_neuralcf": (8192, "NeuralCF, batch=65536 over 8 GPUs = 8192 per GPU"),
     "cfg4_twotowers": (8192, "two towers, batch=65536 over 8 GPUs = 8192 per GPU"),
     "cfg5_din": (8192, "DIN, 100M-item vocab, emb_dim=64, hist_len=200, batch=8192"),
+    # not a BASELINE.json config: the reference's DIEN.py shape
+    "ref_dien": (4096, "DIEN, MovieLens-1K vocab, emb_dim=10, hist_len=5, batch=4096"),
 }
 
 

@@ -45,7 +45,9 @@ enum srs_model_kind {
   SRS_TWOTOWERS = 3,        /* NeuralCF.py:57-70  (neural_cf_model_2)            */
   SRS_DEEPFM = 4,           /* DeepFM.py:91-113                                  */
   SRS_DEEPFM_V2 = 5,        /* DeepFM_v2.py:98-155                               */
-  SRS_DIN = 6               /* DIN.py:125-167                                    */
+  SRS_DIN = 6,              /* DIN.py:125-167                                    */
+  SRS_DIEN = 7              /* DIEN.py:154-256 (y_pred; AUGRU initial state is the  */
+                            /* stored tensor "augru_h0", emb_dim <= 32)            */
 };
 
 /* Hyper-parameters the reference hard-codes as module constants
@@ -56,10 +58,10 @@ typedef struct srs_spec {
   int32_t n_movies;         /* num_buckets of movieId (valid ids 0..n-1)         */
   int32_t n_users;          /* num_buckets of userId                             */
   int32_t n_genres;         /* 19                                                */
-  int32_t hist_len;         /* T (DIN); W&D reads history slot 0 only            */
+  int32_t hist_len;         /* T (DIN, DIEN); W&D reads history slot 0 only      */
   int32_t n_hidden;         /* entries used in hidden[]                          */
   int32_t hidden[4];        /* MLP widths, model dependent                       */
-  int32_t au_hidden;        /* DIN activation-unit width (32)                    */
+  int32_t au_hidden;        /* DIN activation-unit / DIEN attention width (32)   */
   int32_t cross_buckets;    /* W&D hash_bucket_size (10000)                      */
   int32_t proj_dim;         /* DeepFM_v2 field projection width (64)             */
   int32_t final_dense;      /* two towers: Dense(1,sigmoid) after the dot        */

@@ -338,6 +338,87 @@ def din_forward(spec, W, feats, dtype=np.float32):
     return sigmoid(z), z
 
 
+def dien_forward(spec, W, feats, dtype=np.float32):
+    """DIEN.py:154-256, the `y_pred` output (the auxiliary-loss head, :259-292, only feeds
+    `add_loss` and is not part of the prediction).
+
+    Two things differ from DIN's use of the same `Embedding(mask_zero=True)` layer:
+    * the mask IS consumed here: `GRU(...)(user_behaviors_emb_layer)` (:169) receives the
+      Embedding's mask (`inputs != 0`), and Keras' masked RNN step carries state and output
+      over a masked position (`K.rnn`: `where(mask, new, old)`, previous output = zeros before
+      the first valid step) - so a padded slot repeats the last hidden state;
+    * the AUGRU's initial state is `GlorotUniform()(shape=(1, E))` evaluated inside `call`
+      (:235-236), i.e. a fresh random vector per forward pass: the reference's predictions
+      are not reproducible.  Here that vector is the stored tensor `augru_h0` [1,E].
+
+    GRU: Keras defaults - gate order z | r | h, sigmoid / tanh, `reset_after=True`:
+      mx = x.K + b[0];  mh = h.U + b[1];  z = s(mx_z + mh_z);  r = s(mx_r + mh_r)
+      hh = tanh(mx_h + r * mh_h);  h' = z * h + (1 - z) * hh
+    Attention (:172-195): s_t = sigmoid(Dense1(sigmoid(Dense32(g_t * c)))) per position.
+    AUGRU (:204-245), per step with x = g_t, state u:
+      r = s(Act_r(In_r(x) + Hid_r(u)));  z = s(Act_z(In_z(x) + Hid_z(u)))
+      hn = tanh(Act_h(In_h(x) + Hid_h(u * z)));  a = s_t * r;  u' = (1 - a) * u + a * hn
+    (`In` Dense with bias, `Hid` Dense without, `Act` Dense with bias and the activation).
+    Top (:250-256): [u_T | candidate | user_profile | context] -> 128 PReLU -> 64 PReLU -> 1."""
+    E, T = spec.emb_dim, spec.hist_len
+    cand_f = numeric(feats, "movieId", np.float32)                           # :96,154
+    hist_f = np.concatenate([numeric(feats, k, np.float32) for k in din_history_keys(T)],
+                            axis=1)                                          # :99-105,155
+    cand = cand_f.astype(np.int32)[:, 0]
+    hist = hist_f.astype(np.int32)
+    if cand.min() < 0 or max(cand.max(), hist.max()) >= spec.n_movies or hist.min() < 0:
+        raise ValueError("movie id out of range")
+    mask = hist_f != 0                                                       # Embedding.compute_mask
+    tab = W["embedding"].astype(dtype)
+    X = tab[hist]                                                            # [B,T,E] :163
+    C = tab[cand]                                                            # [B,E]   :164,167
+    B = cand.shape[0]
+    K, U = W["gru/kernel"].astype(dtype), W["gru_recurrent/kernel"].astype(dtype)
+    bx, bh = W["gru/bias"].astype(dtype)
+    h = np.zeros((B, E), dtype)
+    G = np.zeros((B, T, E), dtype)
+    for t in range(T):                                                       # :169
+        mx = X[:, t] @ K + bx
+        mh = h @ U + bh
+        z = sigmoid(mx[:, :E] + mh[:, :E])
+        r = sigmoid(mx[:, E:2 * E] + mh[:, E:2 * E])
+        hh = np.tanh(mx[:, 2 * E:] + r * mh[:, 2 * E:])
+        hn = z * h + (1 - z) * hh
+        h = np.where(mask[:, t, None], hn, h)
+        G[:, t] = h
+    att = dense(dense(G * C[:, None, :], W, "att_dense", "sigmoid"), W, "att_out", "sigmoid")[..., 0]
+
+    def gate(g, x, hid):                                                     # :204-219
+        pre = dense(x, W, "augru_%s_input" % g) + hid @ W["augru_%s_hidden/kernel" % g].astype(dtype)
+        return dense(pre, W, "augru_%s_act" % g)
+    u = np.repeat(W["augru_h0"].astype(dtype), B, axis=0)                    # :235-236 (stored)
+    for t in range(T):                                                       # :237-243
+        x = G[:, t]
+        r = sigmoid(gate("r", x, u))
+        z = sigmoid(gate("z", x, u))
+        hn = np.tanh(gate("h", x, u * z))
+        a = att[:, t, None] * r
+        u = (1 - a) * u + a * hn
+    uid = identity_ids(feats, "userId", spec.n_users)
+    user_profile = np.concatenate([                                          # :124-130,157 sorted
+        numeric(feats, "userAvgRating", dtype),
+        embedding_column(W["userGenre1_embedding"], genre_index(feats, "userGenre1"), dtype),
+        embedding_column(W["userId_embedding"], uid, dtype),
+        numeric(feats, "userRatingCount", dtype),
+        numeric(feats, "userRatingStddev", dtype)], axis=1)
+    context = np.concatenate([                                               # :133-139,158 sorted
+        numeric(feats, "movieAvgRating", dtype),
+        embedding_column(W["movieGenre1_embedding"], genre_index(feats, "movieGenre1"), dtype),
+        numeric(feats, "movieRatingCount", dtype),
+        numeric(feats, "movieRatingStddev", dtype),
+        numeric(feats, "releaseYear", dtype)], axis=1)
+    x = np.concatenate([u, C, user_profile, context], axis=1)                # :250
+    x = prelu(dense(x, W, "dense"), W["prelu/alpha"])                        # :252-253
+    x = prelu(dense(x, W, "dense_1"), W["prelu_1/alpha"])                    # :254-255
+    zlogit = dense(x, W, "dense_2")                                          # :256
+    return sigmoid(zlogit), zlogit
+
+
 FORWARD = {
     "embeddingmlp": embeddingmlp_forward,
     "widendeep": widendeep_forward,
@@ -346,6 +427,7 @@ FORWARD = {
     "deepfm": deepfm_forward,
     "deepfm_v2": deepfm_v2_forward,
     "din": din_forward,
+    "dien": dien_forward,
 }
 
 

@@ -155,6 +155,28 @@ struct DinParams {
   int EP;
 };
 
+// ---- DIEN (DIEN.py:154-256), CUDA-core kernel for E <= 32 -------------------------------------
+struct DienParams {
+  const float* movie;      // shared candidate/history table [n_movies][EP]
+  const float* user;       // [n_users][EP]
+  const float* ugenre;     // [19][EP]
+  const float* mgenre;     // [19][EP]
+  const float* seq;        // GRU + attention + AUGRU weights, layout dien.cu::DienBlob<EP>
+  // top MLP, first kernel permuted to the tile order
+  //   [userGenre1 | userId | augru state | candidate | movieGenre1] x EP, then 7 numerics + pad
+  const float* W1;         // [KP = 5*EP + 8][128]
+  const float* b1;         // [128]
+  const float* a1;         // [128] PReLU alpha
+  const float* W2;         // [128][64]
+  const float* b2;         // [64]
+  const float* a2;         // [64]
+  const float* w3;         // [64]
+  float b3;
+  int n_movies, n_users, n_genres;
+  int T;
+  int EP;
+};
+
 // ---- DIN on tensor cores (din_tc.cu): E padded to 32, T <= 128 -----------------------------
 struct DinTcParams {
   const float* movie;      // [n_movies][32]
@@ -227,6 +249,9 @@ cudaError_t launch_deepfm(const DeepFmParams& p, const BatchView& b, cudaStream_
 cudaError_t launch_deepfm_tc(const DeepFmTcParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_deepfm2(const DeepFm2Params& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_din(const DinParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t launch_dien(const DienParams& p, const BatchView& b, cudaStream_t s);
+int dien_seq_floats(int EP);     // size of DienParams::seq for a padded width, -1 if unsupported
+cudaError_t setup_dien_attributes();
 cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, float hi,
                                 cudaStream_t s);
 cudaError_t launch_umma_selftest(const float* A, const float* B, float* D, int N, int KB,

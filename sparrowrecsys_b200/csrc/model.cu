@@ -18,6 +18,7 @@ namespace srs {
 cudaError_t setup_embmlp_attributes();
 cudaError_t setup_deepfm_attributes();
 cudaError_t setup_din_attributes();
+cudaError_t setup_dien_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_din_rt_attributes();
 cudaError_t setup_din_rt64_attributes();
@@ -77,6 +78,7 @@ struct srs_model {
   DeepFmParams fm{};
   DeepFm2Params fm2{};
   DinParams din{};
+  DienParams dien{};
   DinTcParams din_tc{};
   bool use_din_tc = false;
   DinRtParams din_rt{};
@@ -519,6 +521,107 @@ int build_din(Builder& B) {
   return B.status;
 }
 
+// ---- DIEN (DIEN.py:154-256): sequence-part blob in the layout of dien.cu::DienBlob<EP> ---------
+int build_dien(Builder& B) {
+  srs_model* m = B.m;
+  const srs_spec& s = m->spec;
+  const int E = s.emb_dim, EP = m->EP, T = s.hist_len, A = 32;
+  if (E > 32) return fail(SRS_ERR_INVALID, "DIEN supports emb_dim <= 32");
+  if (s.au_hidden != A) return fail(SRS_ERR_INVALID, "DIEN attention width must be 32");
+  if (s.n_hidden != 2 || s.hidden[0] > 128 || s.hidden[1] > 64 || s.hidden[0] < 1 || s.hidden[1] < 1)
+    return fail(SRS_ERR_INVALID, "DIEN needs hidden widths <= (128, 64)");
+  if (T < 1) return fail(SRS_ERR_INVALID, "hist_len must be >= 1");
+  const int h0 = s.hidden[0], h1 = s.hidden[1];
+  DienParams& p = m->dien;
+  p.movie = B.table("embedding", s.n_movies, E);
+  p.user = B.table("userId_embedding", s.n_users, E);
+  p.ugenre = B.table("userGenre1_embedding", s.n_genres, E);
+  p.mgenre = B.table("movieGenre1_embedding", s.n_genres, E);
+  const float* gk = B.host("gru/kernel", E, 3 * E);
+  const float* gr = B.host("gru_recurrent/kernel", E, 3 * E);
+  const float* gb = B.host("gru/bias", 2, 3 * E);
+  const float* ak = B.host("att_dense/kernel", E, A);
+  const float* ab = B.host("att_dense/bias", A, 1);
+  const float* ao = B.host("att_out/kernel", A, 1);
+  const float* aob = B.host("att_out/bias", 1, 1);
+  const char* gates[3] = {"r", "z", "h"};
+  const float *wi[3], *bi[3], *wh[3], *wa[3], *ba[3];
+  for (int g = 0; g < 3; ++g) {
+    char name[64];
+    snprintf(name, sizeof name, "augru_%s_input/kernel", gates[g]); wi[g] = B.host(name, E, E);
+    snprintf(name, sizeof name, "augru_%s_input/bias", gates[g]); bi[g] = B.host(name, E, 1);
+    snprintf(name, sizeof name, "augru_%s_hidden/kernel", gates[g]); wh[g] = B.host(name, E, E);
+    snprintf(name, sizeof name, "augru_%s_act/kernel", gates[g]); wa[g] = B.host(name, E, E);
+    snprintf(name, sizeof name, "augru_%s_act/bias", gates[g]); ba[g] = B.host(name, E, 1);
+  }
+  const float* u0 = B.host("augru_h0", 1, E);
+  const float* k1 = B.host("dense/kernel", 5 * E + 7, h0);
+  const float* b1 = B.host("dense/bias", h0, 1);
+  const float* a1 = B.host("prelu/alpha", h0, 1);
+  const float* k2 = B.host("dense_1/kernel", h0, h1);
+  const float* b2 = B.host("dense_1/bias", h1, 1);
+  const float* a2 = B.host("prelu_1/alpha", h1, 1);
+  const float* k3 = B.host("dense_2/kernel", h1, 1);
+  const float* b3 = B.host("dense_2/bias", 1, 1);
+  if (B.status != SRS_OK) return B.status;
+  const int total = dien_seq_floats(EP);
+  if (total < 0) return fail(SRS_ERR_INVALID, "DIEN: unsupported padded width %d", EP);
+  std::vector<float> q((size_t)total, 0.f);
+  const int EE = EP * EP;
+  const int GW = 0, GU = 3 * EE, AW = 6 * EE, IW = AW + 32 * EP, HW = IW + 3 * EE, SW = HW + 3 * EE,
+            BX = SW + 3 * EE, BH = BX + 3 * EP, BI = BH + 3 * EP, BA = BI + 3 * EP, H0 = BA + 3 * EP,
+            AB = H0 + EP, AO = AB + 32, ABO = AO + 32;
+  for (int k = 0; k < E; ++k)
+    for (int g = 0; g < 3; ++g)                 // Keras gate blocks z | r | h along the 3E axis
+      for (int e = 0; e < E; ++e) {
+        q[GW + (size_t)k * 3 * EP + g * EP + e] = gk[(size_t)k * 3 * E + g * E + e];
+        q[GU + (size_t)k * 3 * EP + g * EP + e] = gr[(size_t)k * 3 * E + g * E + e];
+      }
+  for (int g = 0; g < 3; ++g)
+    for (int e = 0; e < E; ++e) {
+      q[BX + g * EP + e] = gb[g * E + e];
+      q[BH + g * EP + e] = gb[3 * E + g * E + e];
+      q[BI + g * EP + e] = bi[g][e];
+      q[BA + g * EP + e] = ba[g][e];
+    }
+  for (int k = 0; k < E; ++k)
+    for (int j = 0; j < A; ++j) q[AW + (size_t)k * 32 + j] = ak[(size_t)k * A + j];
+  for (int g = 0; g < 3; ++g)
+    for (int k = 0; k < E; ++k)
+      for (int e = 0; e < E; ++e) {
+        q[IW + (size_t)g * EE + k * EP + e] = wi[g][(size_t)k * E + e];
+        q[HW + (size_t)g * EE + k * EP + e] = wh[g][(size_t)k * E + e];
+        q[SW + (size_t)g * EE + k * EP + e] = wa[g][(size_t)k * E + e];
+      }
+  for (int e = 0; e < E; ++e) q[H0 + e] = u0[e];
+  for (int j = 0; j < A; ++j) { q[AB + j] = ab[j]; q[AO + j] = ao[j]; }
+  q[ABO] = aob[0];
+  p.seq = B.upload(q);
+  // top kernel rows: [augru | candidate | user_profile | context] (DIEN.py:250); the blocks
+  // are DenseFeatures layers, sorted by column name inside (as in DIN)
+  const int up = 2 * E, ctx = 4 * E + 3;
+  std::vector<int> map;
+  append(map, iota_map(up + 1, E, EP));          // userGenre1 emb
+  append(map, iota_map(up + 1 + E, E, EP));      // userId emb
+  append(map, iota_map(0, E, EP));               // AUGRU final state
+  append(map, iota_map(E, E, EP));               // candidate emb
+  append(map, iota_map(ctx + 1, E, EP));         // movieGenre1 emb
+  const int nums[8] = {ctx, ctx + 1 + E, ctx + 2 + E, ctx + 3 + E, up, up + 1 + 2 * E, up + 2 + 2 * E, -1};
+  for (int j = 0; j < 8; ++j) map.push_back(nums[j]);
+  p.W1 = B.upload(B.permute(k1, h0, map, 128));
+  p.b1 = B.upload(B.padvec(b1, h0, 128));
+  p.a1 = B.upload(B.padvec(a1, h0, 128));
+  p.W2 = B.upload(B.permute(k2, h1, iota_map(0, h0, 128), 64));
+  p.b2 = B.upload(B.padvec(b2, h1, 64));
+  p.a2 = B.upload(B.padvec(a2, h1, 64));
+  p.w3 = B.upload(B.padvec(k3, h1, 64));
+  p.b3 = b3[0];
+  p.n_movies = s.n_movies; p.n_users = s.n_users; p.n_genres = s.n_genres;
+  p.T = T; p.EP = EP;
+  m->kernel_name = "dien_kernel";
+  return B.status;
+}
+
 // ---- tensor-core DIN: shared-memory image ------------------------------------------------
 inline uint32_t f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 inline float u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
@@ -906,7 +1009,8 @@ int64_t bytes_per_inference(const srs_spec& s) {
     case SRS_TWOTOWERS: return 2 * 4 * E + 2 * 4 + 4;
     case SRS_DEEPFM: return 6 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4;
     case SRS_DEEPFM_V2: return 4 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4;
-    case SRS_DIN: return (T + 1) * 4 * E + 3 * 4 * E + 28 + 4 * (T + 4) + 4;
+    case SRS_DIN:
+    case SRS_DIEN: return (T + 1) * 4 * E + 3 * 4 * E + 28 + 4 * (T + 4) + 4;
   }
   return 0;
 }
@@ -947,6 +1051,7 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
           : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
                           : launch_din(m->din, v, stream);
       break;
+    case SRS_DIEN: e = launch_dien(m->dien, v, stream); break;
     default: return fail(SRS_ERR_INVALID, "unknown model kind");
   }
   if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1086,7 +1191,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
                      int32_t device, srs_model** out) {
   if (!spec || !out || (n_tensors > 0 && !tensors)) return fail(SRS_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (spec->kind < SRS_EMBEDDINGMLP || spec->kind > SRS_DIN)
+  if (spec->kind < SRS_EMBEDDINGMLP || spec->kind > SRS_DIEN)
     return fail(SRS_ERR_INVALID, "unknown model kind %d", spec->kind);
   if (spec->emb_dim < 1 || spec->emb_dim > 64) return fail(SRS_ERR_INVALID, "emb_dim must be in 1..64");
   if (spec->n_movies < 1 || spec->n_users < 1 || spec->n_genres < 1)
@@ -1102,6 +1207,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   CUDA_TRY(setup_embmlp_attributes());
   CUDA_TRY(setup_deepfm_attributes());
   CUDA_TRY(setup_din_attributes());
+  CUDA_TRY(setup_dien_attributes());
   CUDA_TRY(setup_din_tc_attributes());
   CUDA_TRY(setup_din_rt_attributes());
   CUDA_TRY(setup_din_rt64_attributes());
@@ -1112,7 +1218,8 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   m->spec = *spec;
   m->device = device;
   m->EP = round_ep(spec->emb_dim);
-  m->hist_cols = spec->kind == SRS_DIN ? spec->hist_len : spec->kind == SRS_WIDENDEEP ? 1 : 0;
+  m->hist_cols = (spec->kind == SRS_DIN || spec->kind == SRS_DIEN) ? spec->hist_len
+                 : spec->kind == SRS_WIDENDEEP ? 1 : 0;
   m->bytes_per_inf = bytes_per_inference(*spec);
   Builder B{m};
   for (int i = 0; i < n_tensors; ++i)
@@ -1160,6 +1267,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
       break;
     }
     case SRS_DEEPFM_V2: rc = build_deepfm2(B); break;
+    case SRS_DIEN: rc = build_dien(B); break;
     default: {
       rc = build_din(B);
       // kernel selection (SRS_DIN_IMPL=cudacore|tc|rt overrides; tc / rt fail loudly on an unsupported shape):

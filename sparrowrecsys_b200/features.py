@@ -136,7 +136,8 @@ def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=No
     hist = movie_genre = user_genre = numerics = None
     # one arena in the packed order of include/srs_ctr.h (srs_batch): the library then moves
     # the whole batch host->device with a single copy
-    hist_keys = history_keys(spec.hist_len) if m == "din" else (["userRatedMovie1"] if m == "widendeep" else [])
+    hist_keys = history_keys(spec.hist_len) if m in ("din", "dien") \
+        else (["userRatedMovie1"] if m == "widendeep" else [])
     dense = m not in ("neuralcf", "twotowers")
     words = B * (2 + len(hist_keys) + (15 if dense else 0))
     arena = arena_alloc(words * 4) if arena_alloc is not None else np.empty(words * 4, np.uint8)
@@ -207,7 +208,7 @@ def synthetic_features(spec: ModelSpec, batch: int, seed: int, *, zipf_a: float 
     f: Dict[str, np.ndarray] = {}
     f["movieId"] = movie_ids(B).astype(np.int32)
     f["userId"] = rng.integers(1, spec.n_users, size=B, dtype=np.int64).astype(np.int32)
-    T = spec.hist_len if spec.model == "din" else 5
+    T = spec.hist_len if spec.model in ("din", "dien") else 5
     hist = movie_ids(B * T).reshape(B, T)
     if pad_history:
         lens = rng.integers(1, T + 1, size=B)

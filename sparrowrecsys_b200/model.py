@@ -119,7 +119,8 @@ class CTRModel:
                                         C.byref(handle)))
         self._h = handle
         self._keep = [w for w in self._keep if not isinstance(w, np.ndarray)]  # host copies done
-        self.hist_cols = spec.hist_len if spec.model == "din" else (1 if spec.model == "widendeep" else 0)
+        self.hist_cols = spec.hist_len if spec.model in ("din", "dien") \
+            else (1 if spec.model == "widendeep" else 0)
 
     # ---- constructors ------------------------------------------------------------
     @classmethod

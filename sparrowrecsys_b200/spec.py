@@ -23,6 +23,7 @@ MODEL_KINDS: Dict[str, int] = {
     "deepfm": 4,
     "deepfm_v2": 5,
     "din": 6,
+    "dien": 7,
 }
 
 # Reference genre vocabulary, identical in every model script
@@ -65,7 +66,7 @@ class ModelSpec:
     n_genres: int = len(GENRE_VOCAB)
     hist_len: int = 5            # T: RECENT_MOVIES (DIN); W&D uses slot 1 only
     hidden: Tuple[int, ...] = ()  # model dependent, see default_spec()
-    au_hidden: int = 32          # DIN activation-unit width (DIN.py:149)
+    au_hidden: int = 32          # DIN activation-unit / DIEN attention width (DIN.py:149, DIEN.py:178)
     cross_buckets: int = 10000   # W&D crossed_column hash_bucket_size (WideNDeep.py:73)
     proj_dim: int = 64           # DeepFM_v2 per-field projection width (DeepFM_v2.py:114)
     final_dense: bool = True     # two towers: Dense(1,sigmoid) after Dot (NeuralCF.py:67);
@@ -76,9 +77,11 @@ class ModelSpec:
             raise ValueError("unknown model %r (one of %s)" % (self.model, sorted(MODEL_KINDS)))
         if self.emb_dim < 1 or self.emb_dim > 64:
             raise ValueError("emb_dim must be in 1..64")
+        if self.model == "dien" and self.emb_dim > 32:
+            raise ValueError("dien: emb_dim must be <= 32 (one warp lane per state element)")
         if self.n_genres != len(GENRE_VOCAB):
             raise ValueError("n_genres is fixed by the reference vocabulary (19)")
-        if self.model in ("din", "widendeep") and self.hist_len < 1:
+        if self.model in ("din", "dien", "widendeep") and self.hist_len < 1:
             raise ValueError("hist_len must be >= 1")
         object.__setattr__(self, "hidden", tuple(int(h) for h in self.hidden))
 
@@ -108,7 +111,9 @@ class ModelSpec:
                     *MOVIE_GENRE_KEYS, *USER_GENRE_KEYS]
         if m in ("deepfm", "deepfm_v2"):
             return ["movieId", "userId", *NUMERIC_KEYS, "movieGenre1", "userGenre1"]
-        if m == "din":
+        if m in ("din", "dien"):
+            # DIEN's Keras `inputs` also list label and negtive_userRatedMovie2..5
+            # (DIEN.py:82-87); they feed the auxiliary loss only, not y_pred
             return ["movieId", "userId", *history_keys(self.hist_len), *NUMERIC_KEYS,
                     "movieGenre1", "userGenre1"]
         raise AssertionError(m)
@@ -130,7 +135,7 @@ class ModelSpec:
             return 6 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4
         if m == "deepfm_v2":
             return 4 * 4 * E + 4 * 4 + 4 * 4 + 7 * 4 + 4
-        if m == "din":
+        if m in ("din", "dien"):
             return (T + 1) * 4 * E + 3 * 4 * E + 28 + 4 * (T + 4) + 4
         raise AssertionError(m)
 
@@ -161,6 +166,13 @@ class ModelSpec:
             A = self.au_hidden
             return (T * (2 * 4 * E * A + 2 * A + 2 * A + 3 * E) + 2 * T * E
                     + 2 * (5 * E + 7) * h[0] + 2 * h[0] * h[1] + 2 * h[1])
+        if m == "dien":
+            A = self.au_hidden
+            gru = 2 * 2 * E * 3 * E + 10 * E              # two [E,3E] products + gate math
+            att = E + 2 * E * A + 2 * A                   # product, Dense32, Dense1
+            augru = 9 * 2 * E * E + 12 * E                # 3 gates x (input, hidden, act) Dense
+            return (T * (gru + att + augru)
+                    + 2 * (5 * E + 7) * h[0] + 2 * h[0] * h[1] + 2 * h[1])
         raise AssertionError(m)
 
 
@@ -172,6 +184,7 @@ _DEFAULT_HIDDEN = {
     "deepfm": (64, 64),           # DeepFM.py:107-108
     "deepfm_v2": (32, 16),        # DeepFM_v2.py:125-126
     "din": (128, 64),             # DIN.py:163,165
+    "dien": (128, 64),            # DIEN.py:252,254
 }
 
 
@@ -206,4 +219,6 @@ def baseline_spec(cfg: str) -> ModelSpec:
     if cfg == "cfg5_din":
         return default_spec("din", emb_dim=64, hist_len=200,
                             n_movies=100_000_000, n_users=ML20M_USERS)
+    if cfg == "ref_dien":
+        return default_spec("dien")
     raise KeyError(cfg)

@@ -98,6 +98,26 @@ def weight_shapes(spec: ModelSpec) -> List[Tuple[str, Tuple[int, ...]]]:
         add("dense_1/kernel", h[0], h[1]); add("dense_1/bias", h[1])
         add("prelu_1/alpha", h[1])
         add("dense_2/kernel", h[1], 1); add("dense_2/bias", 1)
+    elif m == "dien":
+        A = spec.au_hidden
+        add("embedding", Vm, E)                 # DIEN.py:161 shared by candidate + history
+        add("userId_embedding", Vu, E)
+        add("userGenre1_embedding", G, E)
+        add("movieGenre1_embedding", G, E)
+        # tf.keras.layers.GRU(E) (DIEN.py:169): gates z | r | h, reset_after=True -> bias [2,3E]
+        add("gru/kernel", E, 3 * E); add("gru_recurrent/kernel", E, 3 * E); add("gru/bias", 2, 3 * E)
+        add("att_dense/kernel", E, A); add("att_dense/bias", A)        # DIEN.py:178
+        add("att_out/kernel", A, 1); add("att_out/bias", 1)           # DIEN.py:179
+        for g in ("r", "z", "h"):               # GRU_gate_parameter x3 (DIEN.py:204-219,229-232)
+            add("augru_%s_input/kernel" % g, E, E); add("augru_%s_input/bias" % g, E)
+            add("augru_%s_hidden/kernel" % g, E, E)
+            add("augru_%s_act/kernel" % g, E, E); add("augru_%s_act/bias" % g, E)
+        add("augru_h0", 1, E)                   # the stored initial state (see oracle dien_forward)
+        add("dense/kernel", 5 * E + 7, h[0]); add("dense/bias", h[0])
+        add("prelu/alpha", h[0])
+        add("dense_1/kernel", h[0], h[1]); add("dense_1/bias", h[1])
+        add("prelu_1/alpha", h[1])
+        add("dense_2/kernel", h[1], 1); add("dense_2/bias", 1)
     else:
         raise AssertionError(m)
     return out
@@ -145,6 +165,12 @@ def numeric_rows(spec: ModelSpec) -> Dict[str, np.ndarray]:
         ctx = 2 * E + 3 + 2 * E
         return {"dense/kernel": np.array([ctx + 0, ctx + 1 + E, ctx + 2 + E, ctx + 3 + E,
                                           up + 0, up + 1 + 2 * E, up + 2 + 2 * E])}
+    if m == "dien":
+        # [augru | candidate | user_profile | context] (DIEN.py:250), blocks sorted as in DIN
+        up = 2 * E
+        ctx = 4 * E + 3
+        return {"dense/kernel": np.array([ctx + 0, ctx + 1 + E, ctx + 2 + E, ctx + 3 + E,
+                                          up + 0, up + 1 + 2 * E, up + 2 + 2 * E])}
     return {}
 
 
@@ -162,8 +188,10 @@ def init_weights(spec: ModelSpec, seed: int = 0, *, for_test: bool = True,
             W[name] = rng.uniform(-0.05, 0.05, size=shape).astype(np.float32)
         elif name.endswith("_embedding"):             # feature_column.embedding_column
             W[name] = _trunc_normal(rng, shape, 1.0 / np.sqrt(E))
-        elif name.endswith("/kernel"):
-            W[name] = _glorot(rng, shape[0], shape[1], shape)
+        elif name == "augru_h0":                      # GlorotUniform()(shape=(1, E)), DIEN.py:235-236
+            W[name] = _glorot(rng, 1, E, shape)
+        elif name.endswith("/kernel"):                # (Keras draws the GRU recurrent kernel
+            W[name] = _glorot(rng, shape[0], shape[1], shape)   # orthogonal; glorot here)
         elif name.endswith("/bias"):
             W[name] = (rng.uniform(-0.1, 0.1, size=shape).astype(np.float32) if for_test
                        else np.zeros(shape, np.float32))

@@ -3,7 +3,7 @@ implementation lives in `sparrowrecsys_b200.tfrecmodel`."""
 import sys
 
 from sparrowrecsys_b200 import tfrecmodel as _impl
-from sparrowrecsys_b200.tfrecmodel import (deepfm, deepfm_v2, din, embeddingmlp,  # noqa: F401
+from sparrowrecsys_b200.tfrecmodel import (deepfm, deepfm_v2, dien, din, embeddingmlp,  # noqa: F401
                                            neuralcf, twotowers, widendeep)
 
 __all__ = list(_impl.__all__)
