@@ -4,8 +4,11 @@ Rows of every reference graph are independent (no batch statistics, no cross-row
 op), so the path shards by user-batch with no data-path
 collective: rank r scores the contiguous slice [r*B/N, (r+1)*B/N).  The only
 exchange is an all-gather of float32 scores, and only when one ranking call needs
-the whole vector on every rank (`gather_scores`).  One process per GPU,
-`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+the whole vector on every rank (`gather_scores`) - or, when the call ends in the rankers'
+sort-and-cut (`RecForYouProcess.java:56-59,92-94`), an all-gather of each rank's best `size`
+(position, score) pairs followed by a merge (`rank_sharded`): size x N values cross NVLink
+instead of B.  One process per GPU, `torch.distributed` (NCCL on GPUs, gloo in the CPU tests)
+is the plumbing.
 """
 from __future__ import annotations
 
@@ -61,3 +64,43 @@ def predict_sharded(score_fn: Callable[[Dict[str, np.ndarray]], object], feature
     if not gather:
         return local
     return gather_scores(local, n, group)
+
+
+def rank_sharded(rank_fn: Callable[[Dict[str, np.ndarray], int], tuple], features, size: int,
+                 group=None, merge_fn: Callable = None):
+    """One ranking call spanning the group's GPUs.  `rank_fn(shard_features, k)` ranks this
+    rank's row shard and returns (local positions int32 [k'], scores float32 [k']) as torch
+    tensors on the rank's device, best first (e.g. `CTRModel` forward + `ranking.topk_device`);
+    every rank receives the global result (positions into the unsharded candidate list, scores).
+
+    Each rank contributes its best min(size, shard rows) candidates - a global top-`size` entry
+    is necessarily in its own shard's top-`size` - in ONE all-gather of `[scores | positions]`;
+    `merge_fn(scores, k)` (default: `ranking.topk_device`) then ranks the gathered candidates.
+    Shards are contiguous and gathered in rank order, so "ties by position in the gathered list"
+    is "ties by global position": the result equals the single-GPU ranking exactly."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = len(np.asarray(features["movieId"]))
+    size = max(0, min(int(size), n))
+    bounds = [shard_bounds(n, world, r) for r in range(world)]
+    counts = [min(size, hi - lo) for lo, hi in bounds]
+    width = max(max(counts), 1)
+    lo, hi = bounds[rank]
+    pos, sc = rank_fn(shard_features(features, world, rank), counts[rank])
+    if pos.numel() != counts[rank] or sc.numel() != counts[rank]:
+        raise ValueError("rank_fn returned %d candidates, expected %d" % (pos.numel(), counts[rank]))
+    mine = torch.zeros(2 * width, dtype=torch.float32, device=sc.device)
+    mine[:counts[rank]] = sc.reshape(-1).to(torch.float32)
+    mine[width:width + counts[rank]] = (pos.reshape(-1).to(torch.int32) + lo).view(torch.float32)
+    buf = torch.empty(world * 2 * width, dtype=torch.float32, device=sc.device)
+    dist.all_gather_into_tensor(buf, mine, group=group)
+    buf = buf.view(world, 2, width)
+    scores = torch.cat([buf[r, 0, :counts[r]] for r in range(world)]).contiguous()
+    positions = torch.cat([buf[r, 1, :counts[r]] for r in range(world)]).contiguous().view(torch.int32)
+    if merge_fn is None:
+        from .ranking import topk_device
+        merge_fn = topk_device
+    idx, top = merge_fn(scores, size)
+    return positions[idx.long()], top

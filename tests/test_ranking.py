@@ -134,3 +134,35 @@ def test_rank_by_embedding_matches_reference_emb_ranker():
     ridx, _ = O.rank_topk(ref.astype(np.float32), 20)
     assert np.array_equal(idx, ridx)
     assert np.abs(top - ref[idx]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_rank_sharded_on_nccl_single_rank_group():
+    """`sharding.rank_sharded` with the real pieces (CUDA model, device top-k, NCCL) on a
+    one-rank group; the two-rank exchange logic is covered on CPU (tests/test_sharding_gloo.py)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from conftest import load_golden_weights
+    from sparrowrecsys_b200.model import CTRModel
+    from sparrowrecsys_b200.ranking import topk_device
+    from sparrowrecsys_b200.sharding import rank_sharded
+    from sparrowrecsys_b200.spec import default_spec
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29700 + os.getpid() % 200))
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        spec = default_spec("neuralcf")
+        f = {"movieId": np.arange(1, 901, dtype=np.int32), "userId": np.full(900, 10351, np.int32)}
+        with CTRModel(spec, load_golden_weights("neuralcf_002")) as m:
+            def local_rank(shard, k):
+                batch = m.to_device(shard)
+                probs = torch.empty(batch.B, dtype=torch.float32, device="cuda:0")
+                m.predict_device(batch, probs)
+                return topk_device(probs, k)
+            pos, top = rank_sharded(local_rank, f, 25)
+            torch.cuda.synchronize()
+            p = m.predict(f)[:, 0]
+        ridx, rtop = O.rank_topk(p, 25)
+        assert np.array_equal(pos.cpu().numpy(), ridx) and np.array_equal(top.cpu().numpy(), rtop)
+    finally:
+        dist.destroy_process_group()

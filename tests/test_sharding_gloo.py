@@ -29,7 +29,25 @@ def _worker(rank, world, port, q):
         full = predict_sharded(score, feats)
         ref = O.forward(spec, W, feats)[0][:, 0]
         lo, hi = shard_bounds(1001, world, rank)
-        q.put((rank, bool(np.array_equal(full.numpy(), ref)), hi - lo))
+        # one ranking call spanning both ranks: local top-k, one all-gather, merge.  Scores are
+        # quantised so that ties straddle the shard boundary; stand-ins: the oracle's ranking.
+        from sparrowrecsys_b200.sharding import rank_sharded
+        coarse = np.round(ref * 50).astype(np.float32) / 50
+
+        def local_rank(f, k):
+            s = np.round(O.forward(spec, W, f)[0][:, 0] * 50).astype(np.float32) / 50
+            i, t = O.rank_topk(s, k)
+            return torch.from_numpy(i), torch.from_numpy(t)
+
+        def merge(scores, k):
+            i, t = O.rank_topk(scores.numpy(), k)
+            return torch.from_numpy(i), torch.from_numpy(t)
+        ok_rank = True
+        for size in (1, 50, 600, 5000):
+            pos, top = rank_sharded(local_rank, feats, size, merge_fn=merge)
+            ridx, rtop = O.rank_topk(coarse, size)
+            ok_rank &= bool(np.array_equal(pos.numpy(), ridx) and np.array_equal(top.numpy(), rtop))
+        q.put((rank, bool(np.array_equal(full.numpy(), ref)), hi - lo, ok_rank))
     finally:
         dist.destroy_process_group()
 
@@ -48,3 +66,4 @@ def test_two_rank_shard_and_gather():
         p.join(60)
     assert [r[1] for r in res] == [True, True]         # bit-identical to the unsharded scores
     assert sorted(r[2] for r in res) == [500, 501]
+    assert [r[3] for r in res] == [True, True]         # sharded ranking == single-rank ranking
