@@ -182,6 +182,48 @@ __device__ __forceinline__ void gather_row(float* dst, const float* __restrict__
   *reinterpret_cast<float4*>(dst + 4 * q) = v;
 }
 
+// Side features of a 32-row tile shared by the DIN-family CUDA-core kernels: the userGenre1,
+// userId and movieGenre1 embedding rows (DenseFeatures columns of the user-profile / context
+// layers, e.g. DIN.py:108-123) land at tile columns off_ug / off_u / off_mg, the 7 numerics
+// (+ one zero pad) at off_num.  Rows past the batch end and missing / OOV genres (-1) are zero;
+// an id outside its vocabulary latches the error flag.
+template <int EP, int R>
+__device__ __forceinline__ void tile_side_features(float* __restrict__ Xs, int ldx, int row0,
+                                                   const BatchView& b, const float* user,
+                                                   const float* ugenre, const float* mgenre,
+                                                   int n_users, int n_genres, int off_ug, int off_u,
+                                                   int off_mg, int off_num) {
+  constexpr int Q = EP / 4;
+  for (int i = threadIdx.x; i < R * 3 * Q; i += kThreads) {
+    const int q = i % Q;
+    const int t = i / Q;
+    const int slot = t % 3;
+    const int r = t / 3;
+    const int row = row0 + r;
+    int id = -1;
+    const float* table = user;
+    const int off = slot == 0 ? off_ug : slot == 1 ? off_u : off_mg;
+    if (row < b.B) {
+      if (slot == 1) {
+        id = checked_id(__ldg(b.user_id + row), n_users, b.err_flag);
+      } else {
+        id = slot == 0 ? __ldg(b.user_genre + row * 5) : __ldg(b.movie_genre + row * 3);
+        if (id >= n_genres) { atomicExch(b.err_flag, 1); id = -1; }
+        if (id < 0) id = -1;
+        table = slot == 0 ? ugenre : mgenre;
+      }
+    }
+    gather_row<EP>(Xs + r * ldx + off, table, id, q);
+  }
+  for (int i = threadIdx.x; i < R * kNumPad; i += kThreads) {
+    const int r = i / kNumPad, j = i % kNumPad;
+    const int row = row0 + r;
+    float v = 0.f;
+    if (j < kNumNumerics && row < b.B) v = __ldg(b.numerics + row * kNumNumerics + j);
+    Xs[r * ldx + off_num + j] = v;
+  }
+}
+
 // FingerprintCat64 / crossed_column bucket (WideNDeep.py:72-73; restated from
 // tensorflow/core/platform/fingerprint.h as recorded in SURVEY.md section 8a row a3).
 __host__ __device__ __forceinline__ uint64_t shift_mix(uint64_t v) { return v ^ (v >> 47); }

@@ -46,41 +46,8 @@ __global__ void __launch_bounds__(kThreads) din_kernel(DinParams p, BatchView b)
   float* hc = Hc + warp * TC * EP;
 
   // ---- side features: user genre, user, movie genre rows and numerics ------------
-  for (int i = tid; i < R * 3 * Q; i += kThreads) {
-    const int q = i % Q;
-    const int t = i / Q;
-    const int slot = t % 3;
-    const int r = t / 3;
-    const int row = row0 + r;
-    int id = -1;
-    const float* table = p.user;
-    int off = OFF_U;
-    if (row < b.B) {
-      if (slot == 0) {
-        id = __ldg(b.user_genre + row * 5);
-        if (id >= p.n_genres) { atomicExch(b.err_flag, 1); id = -1; }
-        if (id < 0) id = -1;
-        table = p.ugenre; off = OFF_UG;
-      } else if (slot == 1) {
-        id = checked_id(__ldg(b.user_id + row), p.n_users, b.err_flag);
-      } else {
-        id = __ldg(b.movie_genre + row * 3);
-        if (id >= p.n_genres) { atomicExch(b.err_flag, 1); id = -1; }
-        if (id < 0) id = -1;
-        table = p.mgenre; off = OFF_MG;
-      }
-    } else {
-      off = slot == 0 ? OFF_UG : slot == 1 ? OFF_U : OFF_MG;
-    }
-    gather_row<EP>(Xs + r * LDX + off, table, id, q);
-  }
-  for (int i = tid; i < R * kNumPad; i += kThreads) {
-    const int r = i / kNumPad, j = i % kNumPad;
-    const int row = row0 + r;
-    float v = 0.f;
-    if (j < kNumNumerics && row < b.B) v = __ldg(b.numerics + row * kNumNumerics + j);
-    Xs[r * LDX + OFF_NUM + j] = v;
-  }
+  tile_side_features<EP, R>(Xs, LDX, row0, b, p.user, p.ugenre, p.mgenre, p.n_users, p.n_genres,
+                            OFF_UG, OFF_U, OFF_MG, OFF_NUM);
 
   // ---- activation unit + pooling: one warp per row ---------------------------------
   const float wout = __ldg(p.au_wout + lane);

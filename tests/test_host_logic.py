@@ -192,3 +192,29 @@ def test_shard_bounds_cover_rows():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_abi_argument_validation_needs_no_device():
+    """Bad arguments are rejected before any CUDA call, with a message (never a fault)."""
+    import ctypes as C
+    from sparrowrecsys_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_float * 4)()
+    idx = (C.c_int32 * 4)()
+    assert lib.srs_topk_device(buf, -1, 1, idx, None, 0, None) == _lib.SRS_ERR_INVALID
+    assert b"negative" in lib.srs_last_error()
+    assert lib.srs_topk_device(buf, 4, -2, idx, None, 0, None) == _lib.SRS_ERR_INVALID
+    assert lib.srs_topk_device(None, 4, 2, idx, None, 0, None) == _lib.SRS_ERR_INVALID
+    assert lib.srs_topk_device(buf, 4, 2, None, None, 0, None) == _lib.SRS_ERR_INVALID
+    assert lib.srs_topk_device(None, 0, 5, None, None, 0, None) == _lib.SRS_OK     # nothing to rank
+    assert lib.srs_topk_device(buf, 4, 0, None, None, 0, None) == _lib.SRS_OK
+    assert lib.srs_rank_host(None, None, 3, idx, buf) == _lib.SRS_ERR_INVALID
+    assert lib.srs_predict_host(None, None, buf, None) == _lib.SRS_ERR_INVALID
+    assert lib.srs_cosine_scores_device(buf, buf, 4, 0, buf, 0, None) == _lib.SRS_ERR_INVALID
+    spec = _lib.SrsSpec()
+    spec.kind = 8                                            # one past SRS_DIEN
+    h = C.c_void_p()
+    assert lib.srs_model_create(C.byref(spec), None, 0, 0, C.byref(h)) == _lib.SRS_ERR_INVALID
+    assert b"unknown model kind" in lib.srs_last_error() and not h.value
+    with pytest.raises(ValueError):
+        default_spec("dien", emb_dim=33)                     # one lane per state element
