@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRS_ABI_VERSION 1
+#define SRS_ABI_VERSION 2
 
 enum srs_status {
   SRS_OK = 0,
@@ -107,6 +107,13 @@ typedef struct srs_batch {
   const float* numerics;       /* [B, 7] movieAvgRating, movieRatingCount,
                                   movieRatingStddev, releaseYear, userAvgRating,
                                   userRatingCount, userRatingStddev               */
+  const uint16_t* hist16;      /* host batches only, optional: the history ids as uint16
+                                  [B, T] (same stride and order as `hist`, which is then
+                                  ignored) for vocabularies of at most 65536 movies - the
+                                  history is most of a DIN batch, so this halves the bytes
+                                  that cross PCIe; widened to int32 on the device.  In the
+                                  packed layout it takes the place of `hist`, padded to a
+                                  multiple of 4 bytes.  NULL otherwise.                 */
 } srs_batch;
 
 typedef struct srs_model srs_model;

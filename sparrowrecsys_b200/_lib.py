@@ -14,7 +14,7 @@ SRS_OK = 0
 SRS_ERR_INVALID, SRS_ERR_MISSING, SRS_ERR_SHAPE = -1, -2, -3
 SRS_ERR_CUDA, SRS_ERR_RANGE, SRS_ERR_NOMEM = -4, -5, -6
 SRS_HOST, SRS_DEVICE_BORROWED = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SrsSpec(C.Structure):
@@ -32,7 +32,7 @@ class SrsTensor(C.Structure):
 class SrsBatch(C.Structure):
     _fields_ = [("B", C.c_int32), ("hist_stride", C.c_int32), ("movie_id", C.c_void_p),
                 ("user_id", C.c_void_p), ("hist", C.c_void_p), ("movie_genre", C.c_void_p),
-                ("user_genre", C.c_void_p), ("numerics", C.c_void_p)]
+                ("user_genre", C.c_void_p), ("numerics", C.c_void_p), ("hist16", C.c_void_p)]
 
 
 EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_destroy",

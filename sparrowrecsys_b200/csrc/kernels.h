@@ -260,6 +260,7 @@ cudaError_t launch_umma_bench(unsigned long long* out, int N, int n_mma, int a_i
                               int uniform, cudaStream_t s);
 cudaError_t launch_cosine(const float* q, const float* c, int n, int dim, float* out,
                           cudaStream_t s);
+cudaError_t launch_widen_u16(const uint16_t* src, int32_t* dst, int64_t n, cudaStream_t s);
 // topk.cu: ranking = descending score, ties by position; min(k, n) results
 size_t topk_scratch_bytes(int n);
 cudaError_t launch_topk(const float* scores, int n, int k, int32_t* top_idx, float* top_scores,

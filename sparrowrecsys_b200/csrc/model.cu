@@ -59,6 +59,7 @@ struct Slot {
   uint8_t* d_block = nullptr;       // one allocation: [movie|user|hist|movie_genre|user_genre|numerics]
   float* d_probs = nullptr;
   float* d_logits = nullptr;
+  int32_t* d_hist32 = nullptr;      // widened history ids when the batch came with hist16
   int rank_capacity = 0;            // srs_rank_host only: rows d_rank can rank
   uint8_t* d_rank = nullptr;        // [top_idx cap | top_scores cap | sort scratch]
   int* h_err = nullptr;             // pinned mirror of the device error flag
@@ -1025,7 +1026,9 @@ int check_batch(const srs_model* m, const srs_batch* b) {
   if (dense_feats && (!b->movie_genre || !b->user_genre || !b->numerics))
     return fail(SRS_ERR_INVALID, "movie_genre / user_genre / numerics are required for this model");
   if (m->hist_cols > 0) {
-    if (!b->hist) return fail(SRS_ERR_INVALID, "hist is required for this model");
+    if (!b->hist && !b->hist16) return fail(SRS_ERR_INVALID, "hist is required for this model");
+    if (b->hist16 && m->spec.n_movies > 65536)
+      return fail(SRS_ERR_INVALID, "hist16 needs a movie vocabulary of at most 65536 ids");
     if (b->hist_stride < m->hist_cols)
       return fail(SRS_ERR_INVALID, "hist_stride %d < history columns %d", b->hist_stride, m->hist_cols);
   }
@@ -1064,14 +1067,15 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
 struct PackedLayout {
   size_t movie, user, hist, mg, ug, num, total;
 };
-PackedLayout packed_layout(const srs_model* m, size_t B) {
+PackedLayout packed_layout(const srs_model* m, size_t B, bool narrow_hist = false) {
   const int k = m->spec.kind;
   const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
   PackedLayout L{};
   size_t off = 0;
   L.movie = off; off += B * 4;
   L.user = off; off += B * 4;
-  L.hist = off; off += B * (size_t)m->hist_cols * 4;
+  L.hist = off;
+  off += narrow_hist ? ((B * (size_t)m->hist_cols * 2 + 3) & ~(size_t)3) : B * (size_t)m->hist_cols * 4;
   L.mg = off; off += dense_feats ? B * 3 * 4 : 0;
   L.ug = off; off += dense_feats ? B * 5 * 4 : 0;
   L.num = off; off += dense_feats ? B * 7 * 4 : 0;
@@ -1087,12 +1091,14 @@ int ensure_slot(srs_model* m, Slot& s, int B) {
   }
   if (B <= s.capacity) return SRS_OK;
   int cap = std::max(B, 1024);
-  cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits);
-  s.d_block = nullptr; s.d_probs = nullptr; s.d_logits = nullptr;
+  cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_hist32);
+  s.d_block = nullptr; s.d_probs = nullptr; s.d_logits = nullptr; s.d_hist32 = nullptr;
   s.capacity = 0;
   CUDA_TRY(cudaMalloc(&s.d_block, packed_layout(m, (size_t)cap).total + 256));
   CUDA_TRY(cudaMalloc(&s.d_probs, (size_t)cap * 4));
   CUDA_TRY(cudaMalloc(&s.d_logits, (size_t)cap * 4));
+  if (m->hist_cols > 0 && m->spec.n_movies <= 65536)
+    CUDA_TRY(cudaMalloc(&s.d_hist32, (size_t)cap * m->hist_cols * 4));
   s.capacity = cap;
   return SRS_OK;
 }
@@ -1109,13 +1115,15 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
   const size_t B = (size_t)b->B;
   const int k = m->spec.kind;
   const bool dense_feats = !(k == SRS_NEURALCF || k == SRS_TWOTOWERS);
-  const PackedLayout L = packed_layout(m, B);
+  const bool narrow = m->hist_cols > 0 && b->hist16 != nullptr;
+  const PackedLayout L = packed_layout(m, B, narrow);
   uint8_t* d = s.d_block;
   const uint8_t* h0 = reinterpret_cast<const uint8_t*>(b->movie_id);
   bool packed = reinterpret_cast<const uint8_t*>(b->user_id) == h0 + L.user;
   if (m->hist_cols > 0)
     packed = packed && b->hist_stride == m->hist_cols &&
-             reinterpret_cast<const uint8_t*>(b->hist) == h0 + L.hist;
+             (narrow ? reinterpret_cast<const uint8_t*>(b->hist16)
+                     : reinterpret_cast<const uint8_t*>(b->hist)) == h0 + L.hist;
   if (dense_feats)
     packed = packed && reinterpret_cast<const uint8_t*>(b->movie_genre) == h0 + L.mg &&
              reinterpret_cast<const uint8_t*>(b->user_genre) == h0 + L.ug &&
@@ -1126,11 +1134,13 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
     CUDA_TRY(cudaMemcpyAsync(d + L.movie, b->movie_id, B * 4, cudaMemcpyHostToDevice, s.stream));
     CUDA_TRY(cudaMemcpyAsync(d + L.user, b->user_id, B * 4, cudaMemcpyHostToDevice, s.stream));
     if (m->hist_cols > 0) {
+      const size_t es = narrow ? 2 : 4;                       // bytes per history id on the host
+      const void* hsrc = narrow ? static_cast<const void*>(b->hist16) : static_cast<const void*>(b->hist);
       if (b->hist_stride == m->hist_cols) {
-        CUDA_TRY(cudaMemcpyAsync(d + L.hist, b->hist, B * m->hist_cols * 4, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(d + L.hist, hsrc, B * m->hist_cols * es, cudaMemcpyHostToDevice, s.stream));
       } else {
-        CUDA_TRY(cudaMemcpy2DAsync(d + L.hist, (size_t)m->hist_cols * 4, b->hist, (size_t)b->hist_stride * 4,
-                                   (size_t)m->hist_cols * 4, B, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpy2DAsync(d + L.hist, (size_t)m->hist_cols * es, hsrc, (size_t)b->hist_stride * es,
+                                   (size_t)m->hist_cols * es, B, cudaMemcpyHostToDevice, s.stream));
       }
     }
     if (dense_feats) {
@@ -1144,6 +1154,11 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
   v.movie_id = reinterpret_cast<const int32_t*>(d + L.movie);
   v.user_id = reinterpret_cast<const int32_t*>(d + L.user);
   v.hist = reinterpret_cast<const int32_t*>(d + L.hist);
+  if (narrow) {
+    CUDA_TRY(launch_widen_u16(reinterpret_cast<const uint16_t*>(d + L.hist), s.d_hist32,
+                              (int64_t)B * m->hist_cols, s.stream));
+    v.hist = s.d_hist32;
+  }
   v.movie_genre = reinterpret_cast<const int32_t*>(d + L.mg);
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
@@ -1330,6 +1345,7 @@ void srs_model_destroy(srs_model* m) {
   for (Slot& s : m->slots) {
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
     cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_rank);
+    cudaFree(s.d_hist32);
     if (s.h_err) cudaFreeHost(s.h_err);
   }
   for (void* p : m->owned) cudaFree(p);
@@ -1342,6 +1358,8 @@ int srs_predict_device(srs_model* m, const srs_batch* b, float* probs, float* lo
   if (rc != SRS_OK) return rc;
   if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
   if (b->B == 0) return SRS_OK;
+  if (m->hist_cols > 0 && !b->hist)
+    return fail(SRS_ERR_INVALID, "device batches carry int32 history ids (hist16 is for host batches)");
   CUDA_TRY(cudaSetDevice(m->device));
   BatchView v{};
   v.B = b->B; v.hist_stride = b->hist_stride;

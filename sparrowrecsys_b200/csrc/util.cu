@@ -33,6 +33,30 @@ cudaError_t launch_fill_uniform(float* x, int64_t n, uint64_t seed, float lo, fl
   return cudaGetLastError();
 }
 
+// uint16 -> int32 history ids (srs_batch::hist16): the narrow form crosses PCIe, the kernels
+// read int32.  `src` is 4-byte aligned (packed layout); two ids per thread.
+__global__ void widen_u16_kernel(const uint16_t* __restrict__ src, int32_t* __restrict__ dst,
+                                 int64_t n) {
+  const int64_t pairs = n >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+    *reinterpret_cast<int2*>(dst + 2 * i) = make_int2((int)(v & 0xFFFFu), (int)(v >> 16));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = src[n - 1];
+}
+
+cudaError_t launch_widen_u16(const uint16_t* src, int32_t* dst, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  int64_t blocks = ((n >> 1) + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  widen_u16_kernel<<<(int)blocks, threads, 0, s>>>(src, dst, n);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
 // Cosine similarity of one query against n candidates, one warp per candidate.
 // Reference: online/model/Embedding.java:33-47 - float products accumulated in double,
 // dot / (sqrt(n1) * sqrt(n2)).

@@ -109,7 +109,7 @@ class EncodedBatch:
         self.B = B
         self.movie_id = movie_id        # int32 [B]
         self.user_id = user_id          # int32 [B]
-        self.hist = hist                # int32 [B, T] or None
+        self.hist = hist                # int32 [B, T] (uint16 with narrow_ids) or None
         self.movie_genre = movie_genre  # int32 [B, 3] (-1 = missing/OOV) or None
         self.user_genre = user_genre    # int32 [B, 5] or None
         self.numerics = numerics        # float32 [B, 7] in NUMERIC_KEYS order or None
@@ -120,13 +120,16 @@ class EncodedBatch:
                             s(self.movie_genre), s(self.user_genre), s(self.numerics))
 
 
-def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=None) -> EncodedBatch:
+def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=None,
+                 narrow_ids: bool = False) -> EncodedBatch:
     """Feature dict (keys as in the Keras `inputs` dicts, e.g. DIN.py:34-59) ->
     `EncodedBatch`.  Unknown keys are ignored (the reference datasets carry
     `rating`, `timestamp`, ... which no model reads); a missing required key raises
     `KeyError`; an out-of-range id raises `ValueError`.  `arena_alloc(nbytes)` may supply
     the backing uint8 buffer (e.g. pinned memory); the arrays are views into it, back to
-    back in the packed order the library recognises."""
+    back in the packed order the library recognises.  `narrow_ids`: store the history ids as
+    uint16 (`srs_batch::hist16`; vocabularies of at most 65536 movies) - the history is most
+    of a DIN batch, so the host-to-device copy roughly halves."""
     m = spec.model
     movie_id_in = _as_ids(features, "movieId", spec.n_movies, "movie id")
     user_id_in = _as_ids(features, "userId", spec.n_users, "user id")
@@ -139,14 +142,18 @@ def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=No
     hist_keys = history_keys(spec.hist_len) if m in ("din", "dien") \
         else (["userRatedMovie1"] if m == "widendeep" else [])
     dense = m not in ("neuralcf", "twotowers")
-    words = B * (2 + len(hist_keys) + (15 if dense else 0))
-    arena = arena_alloc(words * 4) if arena_alloc is not None else np.empty(words * 4, np.uint8)
+    narrow = bool(narrow_ids) and bool(hist_keys)
+    if narrow and spec.n_movies > 65536:
+        raise ValueError("narrow_ids needs a movie vocabulary of at most 65536 ids")
+    hist_bytes = (B * len(hist_keys) * 2 + 3) & ~3 if narrow else B * len(hist_keys) * 4
+    nbytes = B * (2 + (15 if dense else 0)) * 4 + hist_bytes
+    arena = arena_alloc(nbytes) if arena_alloc is not None else np.empty(nbytes, np.uint8)
     cursor = [0]
 
     def carve(shape, dtype):
-        n = int(np.prod(shape)) * 4
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         view = arena[cursor[0]:cursor[0] + n].view(dtype).reshape(shape)
-        cursor[0] += n
+        cursor[0] += (n + 3) & ~3
         return view
 
     movie_id = carve((B,), np.int32)
@@ -154,7 +161,7 @@ def encode_batch(spec: ModelSpec, features: Mapping[str, object], arena_alloc=No
     user_id = carve((B,), np.int32)
     user_id[:] = user_id_in
     if hist_keys:
-        hist = carve((B, len(hist_keys)), np.int32)
+        hist = carve((B, len(hist_keys)), np.uint16 if narrow else np.int32)
         for p, k in enumerate(hist_keys):
             hist[:, p] = _as_ids(features, k, spec.n_movies, "history movie id")
     if dense:

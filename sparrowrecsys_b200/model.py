@@ -53,7 +53,7 @@ class DeviceBatch:
         self.B = enc.B
         self.movie_id = t(enc.movie_id)
         self.user_id = t(enc.user_id)
-        self.hist = t(enc.hist)
+        self.hist = t(None if enc.hist is None else enc.hist.astype(np.int32, copy=False))
         self.movie_genre = t(enc.movie_genre)
         self.user_genre = t(enc.user_genre)
         self.numerics = t(enc.numerics)
@@ -74,19 +74,24 @@ def _host_struct(enc: EncodedBatch, keep: list) -> _lib.SrsBatch:
         keep.append(a)
         return a.ctypes.data
     hs = 0 if enc.hist is None else enc.hist.shape[1]
+    narrow = enc.hist is not None and enc.hist.dtype == np.uint16      # srs_batch::hist16
     return _lib.SrsBatch(enc.B, hs, p(enc.movie_id, np.int32), p(enc.user_id, np.int32),
-                         p(enc.hist, np.int32), p(enc.movie_genre, np.int32),
-                         p(enc.user_genre, np.int32), p(enc.numerics, np.float32))
+                         None if narrow else p(enc.hist, np.int32), p(enc.movie_genre, np.int32),
+                         p(enc.user_genre, np.int32), p(enc.numerics, np.float32),
+                         p(enc.hist, np.uint16) if narrow else None)
 
 
 class CTRModel:
     """One CTR ranking model resident on one GPU."""
 
-    def __init__(self, spec: ModelSpec, weights: Mapping[str, object], device: int = 0):
+    def __init__(self, spec: ModelSpec, weights: Mapping[str, object], device: int = 0,
+                 narrow_ids: bool = False):
         """`weights`: canonical name -> float32 numpy array (reference shapes), or a
         torch CUDA tensor for an embedding table that is already in HBM (used in
-        place, see SRS_DEVICE_BORROWED in include/srs_ctr.h)."""
+        place, see SRS_DEVICE_BORROWED in include/srs_ctr.h).  `narrow_ids`: host batches
+        carry the history ids as uint16 (`srs_batch::hist16`, n_movies <= 65536)."""
         self.spec = spec
+        self.narrow_ids = bool(narrow_ids) and spec.n_movies <= 65536
         self.device = int(device)
         self._h = None
         lib = _lib.load()
@@ -174,7 +179,7 @@ class CTRModel:
         return self._predict(features, batch_size, want_logits=True)
 
     def _predict(self, features, batch_size, want_logits):
-        enc = encode_batch(self.spec, features)
+        enc = encode_batch(self.spec, features, narrow_ids=self.narrow_ids)
         n = enc.B
         probs = np.empty(n, np.float32)
         logits = np.empty(n, np.float32) if want_logits else None
@@ -219,7 +224,7 @@ class CTRModel:
         """`RecForYouProcess.getRecList`'s tail for one request: score the candidate rows
         and return the best `size` (positions int32 [k], scores float32 [k], best first;
         equal scores by position) - `srs_rank_host`, only k results leave the device."""
-        enc = encode_batch(self.spec, features)
+        enc = encode_batch(self.spec, features, narrow_ids=self.narrow_ids)
         k = max(0, min(int(size), enc.B))
         idx = np.empty(k, np.int32)
         top = np.empty(k, np.float32)

@@ -145,7 +145,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libsrs_ctr.so does not export %s" % name
     assert set(declared) == set(_lib.EXPORTS)
-    assert lib.srs_abi_version() == 1
+    assert lib.srs_abi_version() == 2
     assert lib.srs_num_slots() >= 2
     assert lib.srs_launch_count() == 0
 
@@ -155,7 +155,8 @@ def test_struct_layouts_match_header():
     from sparrowrecsys_b200 import _lib
     assert C.sizeof(_lib.SrsSpec) == 15 * 4
     assert C.sizeof(_lib.SrsTensor) == 40 and _lib.SrsTensor.rows.offset == 16
-    assert C.sizeof(_lib.SrsBatch) == 8 + 6 * 8 and _lib.SrsBatch.movie_id.offset == 8
+    assert C.sizeof(_lib.SrsBatch) == 8 + 7 * 8 and _lib.SrsBatch.movie_id.offset == 8
+    assert _lib.SrsBatch.hist16.offset == 8 + 6 * 8
 
 
 def test_product_path_fails_loudly_without_gpu(have_gpu):
