@@ -76,6 +76,9 @@ def parse_args():
     ap.add_argument("--gather", action="store_true", help="all-gather scores every step (N>1)")
     ap.add_argument("--no-graph", action="store_true", help="launch directly instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="S > 1: consecutive batches run side by side, each launch limited to "
+                         "SMs/S CTAs (srs_model_set_sm_limit), S branches in the CUDA graph")
     ap.add_argument("--narrow-ids", default="off", choices=["auto", "off"],
                     help="e2e leg: history ids cross PCIe as uint16 (srs_batch::hist16) when the "
                          "movie vocabulary has at most 65536 ids")
@@ -344,6 +347,11 @@ def run_ours(args):
         gather_buf = torch.empty(world * B, dtype=torch.float32, device=dev)
 
     stream = torch.cuda.Stream(device=dev)
+    S = max(1, args.streams) if gather_buf is None else 1
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    side = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+    if S > 1:
+        model.set_sm_limit(max(1, n_sms // S))
     graph = None
     launch_mode = "direct"
     with torch.cuda.stream(stream):
@@ -354,10 +362,19 @@ def run_ours(args):
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
+                    cur = torch.cuda.current_stream()
+                    for sd in side:                       # fork: S branches, batch i on branch i % S
+                        sd.wait_stream(cur)
+                    branches = [cur] + side
                     for i in range(ring):
-                        launch(i, torch.cuda.current_stream().cuda_stream)
+                        launch(i, branches[i % S].cuda_stream)
+                    for sd in side:                       # join
+                        cur.wait_stream(sd)
                 graph = g
                 launch_mode = "cuda-graph of %d launches (one pass over the ring)" % ring
+                if S > 1:
+                    launch_mode += (", %d parallel branches, each launch limited to %d of %d SMs"
+                                    % (S, max(1, n_sms // S), n_sms))
             except Exception as e:                    # pragma: no cover
                 sys.stderr.write("graph capture failed (%r); launching directly\n" % (e,))
                 torch.cuda.synchronize()
@@ -368,11 +385,16 @@ def run_ours(args):
                 while n - i >= ring:
                     graph.replay()
                     i += ring
+            if i < n and side:
+                for sd in side:
+                    sd.wait_stream(stream)
             while i < n:
-                launch(i, stream.cuda_stream)
+                launch(i, ([stream] + side)[i % S].cuda_stream)
                 if gather_buf is not None:
                     dist.all_gather_into_tensor(gather_buf, out[i % ring])
                 i += 1
+            for sd in side:
+                stream.wait_stream(sd)
 
         run_steps(args.warmup)
         stream.synchronize()
@@ -492,6 +514,11 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": bpi * B, "launch_us": launch_us,
                          "peak_source": peak_src},
         }
+        if S > 1:
+            line["roofline"]["concurrency"] = (
+                "%d launches in flight on disjoint sets of %d SMs; launch_us is the timed region / "
+                "launches (device time per batch), a single launch lasts about %d times that"
+                % (S, max(1, n_sms // S), S))
         if not args.no_cpu_baseline:
             n_cpu = min(B, 4096)
             cspec, cW, cnote = cpu_spec_and_weights(spec)

@@ -181,6 +181,15 @@ int64_t srs_model_bytes_per_inference(const srs_model* m);
  * (tc | cudacore) do the same for EmbeddingMLP / Wide&Deep and DeepFM. */
 const char* srs_model_kernel_name(const srs_model* m);
 
+/* Limit the persistent tensor-core kernels of this model (din_rt / din_rt64 / din_tc /
+ * embmlp_tc / deepfm_tc) to at most n_sms CTAs per launch (n_sms <= 0: every SM of the device,
+ * the default).  A launch then leaves the other SMs to launches of other streams: with
+ * 148 / S CTAs per launch, S consecutive batches of a pipeline run side by side on disjoint SM
+ * sets, each CTA walking several row groups, so the per-launch latency chain (prologue, first
+ * ids, launch gap) is paid once per S batches per SM instead of once per batch.  Takes effect
+ * at the next srs_predict_* call; results do not depend on it. */
+int srs_model_set_sm_limit(srs_model* m, int32_t n_sms);
+
 /* Number of kernels this library has launched in this process (all models). */
 int64_t srs_launch_count(void);
 

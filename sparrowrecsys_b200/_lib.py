@@ -38,7 +38,7 @@ class SrsBatch(C.Structure):
 EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_destroy",
            "srs_predict_device", "srs_predict_host", "srs_predict_host_batches", "srs_num_slots", "srs_predict_host_async",
            "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
-           "srs_model_kernel_name", "srs_launch_count", "srs_fill_uniform",
+           "srs_model_kernel_name", "srs_model_set_sm_limit", "srs_launch_count", "srs_fill_uniform",
            "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
     lib.srs_model_bytes_per_inference.argtypes = [C.c_void_p]
     lib.srs_model_kernel_name.restype = C.c_char_p
     lib.srs_model_kernel_name.argtypes = [C.c_void_p]
+    lib.srs_model_set_sm_limit.restype = C.c_int
+    lib.srs_model_set_sm_limit.argtypes = [C.c_void_p, C.c_int32]
     lib.srs_launch_count.restype = C.c_int64
     lib.srs_fill_uniform.restype = C.c_int
     lib.srs_fill_uniform.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_float, C.c_float,

@@ -90,6 +90,7 @@ struct srs_model {
   DeepFmTcParams fm_tc{};
   bool use_fm_tc = false;
   const char* kernel_name = "";
+  int device_sms = 148;
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
   std::mutex mu;
@@ -1232,6 +1233,11 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   srs_model* m = new srs_model();
   m->spec = *spec;
   m->device = device;
+  {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    m->device_sms = sms > 0 ? sms : 148;
+  }
   m->EP = round_ep(spec->emb_dim);
   m->hist_cols = (spec->kind == SRS_DIN || spec->kind == SRS_DIEN) ? spec->hist_len
                  : spec->kind == SRS_WIDENDEEP ? 1 : 0;
@@ -1437,6 +1443,17 @@ int srs_model_status(srs_model* m) {
 int64_t srs_model_bytes_per_inference(const srs_model* m) { return m ? m->bytes_per_inf : 0; }
 
 const char* srs_model_kernel_name(const srs_model* m) { return m ? m->kernel_name : ""; }
+
+int srs_model_set_sm_limit(srs_model* m, int32_t n_sms) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  const int n = (n_sms <= 0 || n_sms > m->device_sms) ? m->device_sms : n_sms;
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->din_rt.num_sms = n;
+  m->din_tc.num_sms = n;
+  m->emb_tc.num_sms = n;
+  m->fm_tc.num_sms = n;
+  return SRS_OK;
+}
 
 int64_t srs_launch_count(void) { return g_launch_count; }
 

@@ -166,6 +166,11 @@ class CTRModel:
     def kernel_name(self) -> str:
         return self._lib.srs_model_kernel_name(self._h).decode()
 
+    def set_sm_limit(self, n_sms: int):
+        """At most `n_sms` CTAs per launch of the persistent tensor-core kernels (<= 0: all
+        SMs), so that launches on other streams run beside it (`srs_model_set_sm_limit`)."""
+        _lib.check(self._lib.srs_model_set_sm_limit(self._h, int(n_sms)))
+
     @property
     def bytes_per_inference(self) -> int:
         return int(self._lib.srs_model_bytes_per_inference(self._h))

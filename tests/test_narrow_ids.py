@@ -90,3 +90,19 @@ def test_hist16_strided_host_arrays_and_rejections():
         b.hist, b.hist16 = None, h16.ctypes.data
         out = np.empty(16, np.float32)
         assert lib.srs_predict_host(m._h, C.byref(b), out.ctypes.data, None) == _lib.SRS_ERR_INVALID
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,B", [("cfg3_din", 4096), ("cfg3_din", 4736 + 33), ("cfg4_widendeep", 8192),
+                                   ("cfg2_deepfm", 4096)])
+def test_sm_limit_does_not_change_scores(cfg, B):
+    """`srs_model_set_sm_limit`: fewer CTAs per launch, each walking more row groups - the
+    scores must be the same bits (bench.py --streams relies on it)."""
+    from sparrowrecsys_b200.model import CTRModel
+    spec = baseline_spec(cfg)
+    f = synthetic_features(spec, B, seed=11)
+    with CTRModel(spec, init_weights(spec, 5)) as m:
+        ref = m.predict(f)
+        for n in (74, 37, 5, 1, 0, 1000):
+            m.set_sm_limit(n)
+            assert np.array_equal(m.predict(f), ref), n
