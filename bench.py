@@ -8,15 +8,21 @@ A *step* is one pass of the hot path over one batch: one fused-kernel launch sco
 synthetic Zipf inputs, seeded random-init weights of the reference architecture).
 
 * `value`  : rows scored per second with the batch already resident in HBM, device-timed
-             with CUDA events around exactly K launches, max over ranks.  Inputs cycle
+             with CUDA events around exactly K launches, max over ranks.  By default two
+             consecutive batches are in flight (`--streams 2`: each launch limited to half the
+             SMs, two branches in the CUDA graph), which hides the per-launch latency chain;
+             `--streams 1` is one full-width launch at a time.  Inputs cycle
              through a ring of distinct batches whose footprint exceeds the 126 MB L2, so
              every step's ids/numerics come from HBM; the 21 MB of embedding tables stay
              L2 resident by size (that is the workload's nature, see `config.l2`).
 * `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
              (`srs_predict_host_batches`: H2D of each batch from pinned memory, kernel, D2H of
-             the scores, pipelined over the library's slots), wall-clock, max over ranks.
-* `roofline`: algorithmic bytes per launch (7160 B/row) / average launch
-             duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+             the scores, pipelined over the library's slots), wall-clock, max over ranks.  The
+             history ids cross PCIe as uint16 when the vocabulary allows (`--narrow-ids auto`,
+             `srs_batch::hist16`); `h2d_bytes_per_step` is the size of the packed host batch.
+* `roofline`: algorithmic bytes per launch (7160 B/row) / device time per launch
+             (timed region / launches), against the measured HBM copy bandwidth in
+             MEASURED_PEAKS.json.
 * `cpu_baseline`: the oracle (numpy restatement of the Keras graph; TensorFlow is not
              installable here) timed on this box's host cores on a bounded sample.
 
@@ -76,16 +82,20 @@ def parse_args():
     ap.add_argument("--gather", action="store_true", help="all-gather scores every step (N>1)")
     ap.add_argument("--no-graph", action="store_true", help="launch directly instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--streams", type=int, default=None,
                     help="S > 1: consecutive batches run side by side, each launch limited to "
-                         "SMs/S CTAs (srs_model_set_sm_limit), S branches in the CUDA graph")
-    ap.add_argument("--narrow-ids", default="off", choices=["auto", "off"],
+                         "SMs/S CTAs (srs_model_set_sm_limit), S branches in the CUDA graph; "
+                         "default 2 for the headline workload (measured: profiles/bench_r01_streams), "
+                         "1 for the others")
+    ap.add_argument("--narrow-ids", default="auto", choices=["auto", "off"],
                     help="e2e leg: history ids cross PCIe as uint16 (srs_batch::hist16) when the "
                          "movie vocabulary has at most 65536 ids")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.batch is None:
         args.batch = WORKLOADS[args.workload][0]
+    if args.streams is None:
+        args.streams = 2 if args.workload == WORKLOAD else 1
     return args
 
 
