@@ -87,6 +87,9 @@ def parse_args():
                          "SMs/S CTAs (srs_model_set_sm_limit), S branches in the CUDA graph; "
                          "default 2 for the headline workload (measured: profiles/bench_r01_streams), "
                          "1 for the others")
+    ap.add_argument("--sm-limit", type=int, default=None,
+                    help="CTAs per launch with --streams S > 1 (default SMs/S; 0: no limit - for "
+                         "kernels that fit two CTAs per SM, e.g. SRS_DIN_IMPL=rth)")
     ap.add_argument("--narrow-ids", default="auto", choices=["auto", "off"],
                     help="e2e leg: history ids cross PCIe as uint16 (srs_batch::hist16) when the "
                          "movie vocabulary has at most 65536 ids")
@@ -360,8 +363,9 @@ def run_ours(args):
     S = max(1, args.streams) if gather_buf is None else 1
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     side = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+    sm_limit = max(1, n_sms // S) if args.sm_limit is None else args.sm_limit
     if S > 1:
-        model.set_sm_limit(max(1, n_sms // S))
+        model.set_sm_limit(sm_limit)
     graph = None
     launch_mode = "direct"
     with torch.cuda.stream(stream):
@@ -384,7 +388,7 @@ def run_ours(args):
                 launch_mode = "cuda-graph of %d launches (one pass over the ring)" % ring
                 if S > 1:
                     launch_mode += (", %d parallel branches, each launch limited to %d of %d SMs"
-                                    % (S, max(1, n_sms // S), n_sms))
+                                    % (S, sm_limit if sm_limit > 0 else n_sms, n_sms))
             except Exception as e:                    # pragma: no cover
                 sys.stderr.write("graph capture failed (%r); launching directly\n" % (e,))
                 torch.cuda.synchronize()
@@ -526,9 +530,9 @@ def run_ours(args):
         }
         if S > 1:
             line["roofline"]["concurrency"] = (
-                "%d launches in flight on disjoint sets of %d SMs; launch_us is the timed region / "
-                "launches (device time per batch), a single launch lasts about %d times that"
-                % (S, max(1, n_sms // S), S))
+                "%d launches in flight, %d SMs each; launch_us is the timed region / launches "
+                "(device time per batch), a single launch lasts about %d times that"
+                % (S, sm_limit if sm_limit > 0 else n_sms, S))
         if not args.no_cpu_baseline:
             n_cpu = min(B, 4096)
             cspec, cW, cnote = cpu_spec_and_weights(spec)

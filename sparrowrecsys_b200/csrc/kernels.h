@@ -230,6 +230,7 @@ struct DinRtParams {
   int nch;                   // din_rt64: 128-position chunks per row (1 or 2)
   int num_sms;
   int trace;
+  int ctas_per_sm;           // din_rth: 1 (co-residency comes from other streams' launches) or 2
 };
 
 // launchers (defined next to their kernels); return cudaGetLastError()
@@ -237,6 +238,8 @@ cudaError_t launch_din_rt(const DinRtParams& p, const BatchView& b, cudaStream_t
 cudaError_t launch_split_table(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t read_din_rt_trace(unsigned long long* out40);
 cudaError_t setup_din_rt_attributes();
+cudaError_t launch_din_rth(const DinRtParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t setup_din_rth_attributes();
 cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t setup_din_rt64_attributes();

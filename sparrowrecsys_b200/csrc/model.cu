@@ -21,6 +21,7 @@ cudaError_t setup_din_attributes();
 cudaError_t setup_dien_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_din_rt_attributes();
+cudaError_t setup_din_rth_attributes();
 cudaError_t setup_din_rt64_attributes();
 cudaError_t setup_embmlp_tc_attributes();
 cudaError_t setup_deepfm_tc_attributes();
@@ -85,6 +86,7 @@ struct srs_model {
   DinRtParams din_rt{};
   bool use_din_rt = false;
   bool use_din_rt64 = false;         // din_rt holds the parameters of din_rt64_kernel
+  bool use_din_rth = false;          // din_rt holds the parameters; the half-SM kernel runs them
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
   DeepFmTcParams fm_tc{};
@@ -1051,6 +1053,7 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
       e = m->use_din_rt64 ? launch_din_rt64(m->din_rt, v, stream)
+          : m->use_din_rth ? launch_din_rth(m->din_rt, v, stream)
           : m->use_din_rt ? launch_din_rt(m->din_rt, v, stream)
           : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
                           : launch_din(m->din, v, stream);
@@ -1306,6 +1309,12 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
         if (!fits_tc && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=tc needs 16 < emb_dim <= 32 and hist_len <= 128");
         want_tc = true; want_rt = false;
       }
+      const bool want_rth = impl && !strcmp(impl, "rth");       // experimental half-SM row-tile kernel
+      if (want_rth) {
+        if (!fits_rt32 && rc == SRS_OK)
+          rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rth needs 16 < emb_dim <= 32 and hist_len <= 64");
+        want_rt = true; want_tc = false;
+      }
       if (impl && !strcmp(impl, "rt")) {
         if (!fits_rt && rc == SRS_OK)
           rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rt needs 16 < emb_dim <= 32 and hist_len <= 64, or 32 < emb_dim <= 64 and hist_len <= 256");
@@ -1318,6 +1327,14 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
       if (rc == SRS_OK && want_rt && fits_rt32) {
         rc = build_din_rt(B);
         if (rc == SRS_OK) { m->use_din_rt = true; m->kernel_name = "din_rt_kernel"; }
+        if (rc == SRS_OK && want_rth) {
+          // experimental kernel: its attribute setup stays off the path of every other model
+          cudaError_t ea = setup_din_rth_attributes();
+          if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rth attribute setup failed: %s", cudaGetErrorString(ea));
+          const char* cps = getenv("SRS_DIN_RTH_CTAS");
+          m->din_rt.ctas_per_sm = (cps && atoi(cps) == 2) ? 2 : 1;
+          m->use_din_rt = false; m->use_din_rth = true; m->kernel_name = "din_rth_kernel";
+        }
       }
       if (rc == SRS_OK && want_rt && fits_rt64) {
         rc = build_din_rt64(B);
