@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
   __shared__ uint64_t empty[kHSlots];       // both MMAs of the tile in the slot have completed
   __shared__ uint64_t d1_full;              // tile K: activation-unit accumulators ready
   __shared__ uint64_t d1_free;              // tile K: the consumer has read them (128 arrivals)
-  __shared__ uint64_t w_ready;              // tile K: pooling weights written (128 arrivals)
+  __shared__ uint64_t w_ready[2];           // tile K -> [K & 1]: pooling weights written (128 arrivals).  Two,
+                                            // because MMA1 of tile K + 1 is issued before the issuer waits for
+                                            // tile K here: one barrier could run a phase ahead of its waiter
   __shared__ uint64_t d2_full[2];           // buffer u: pooled accumulators ready
   __shared__ uint64_t pfull[3];             // weight piece landed in buffer j
   __shared__ uint64_t pfree[3];             // MMAs reading buffer j have completed
@@ -119,11 +121,11 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
     else if (lane < 6) mbar_init(&empty[lane - 3], 1);
     else if (lane == 6) mbar_init(&d1_full, 1);
     else if (lane == 7) mbar_init(&d1_free, 128);
-    else if (lane == 8) mbar_init(&w_ready, 128);
-    else if (lane < 11) mbar_init(&d2_full[lane - 9], 1);
-    else if (lane < 14) mbar_init(&pfull[lane - 11], 1);
-    else if (lane < 17) mbar_init(&pfree[lane - 14], 1);
-    else if (lane == 17) mbar_init(&cbar, 1);
+    else if (lane < 10) mbar_init(&w_ready[lane - 8], 128);
+    else if (lane < 12) mbar_init(&d2_full[lane - 10], 1);
+    else if (lane < 15) mbar_init(&pfull[lane - 12], 1);
+    else if (lane < 18) mbar_init(&pfree[lane - 15], 1);
+    else if (lane == 18) mbar_init(&cbar, 1);
     fence_mbar_init();
   }
   // per-thread constants of the roles
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
       for (int k = 0; k < n_tiles; ++k) {
         const int K = kbase + k, slot = K % kHSlots, u = K & 1;
         if (k + 1 < n_tiles) mma1(k + 1);                   // overlaps the gate arithmetic of tile K
-        mbar_wait(&w_ready, K & 1);
+        mbar_wait(&w_ready[u], (K >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD2 = tbase + HT_D2 + 16u * u;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&w_ready);
+        mbar_arrive(&w_ready[u]);
         if (k >= 1) pool_out(k - 1);                        // the other D2 buffer: its MMAs finished long ago
       }
       if (n_tiles > 0) pool_out(n_tiles - 1);
