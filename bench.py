@@ -23,8 +23,11 @@ synthetic Zipf inputs, seeded random-init weights of the reference architecture)
 * `roofline`: algorithmic bytes per launch (7160 B/row) / device time per launch
              (timed region / launches), against the measured HBM copy bandwidth in
              MEASURED_PEAKS.json.
-* `cpu_baseline`: the oracle (numpy restatement of the Keras graph; TensorFlow is not
-             installable here) timed on this box's host cores on a bounded sample.
+* `cpu_baseline`: the CPU port of the Keras graph (TensorFlow is not installable here) timed on
+             this box's host cores on a bounded sample.  It uses the host threads the way TF's
+             intra-op pool would (oracle/ctr_oracle_torch.py: torch CPU ops for DIN, the numpy
+             oracle over row chunks on a thread pool otherwise) - the plain numpy oracle, which
+             earlier bench lines of this round timed, runs mostly on one core and is ~10x slower.
 
 `--impl reference` times that CPU restatement as the reference arm (rank 0 only).
 Multi-GPU (`torchrun`, one rank per GPU): rows shard by rank, weights replicate, no
@@ -236,40 +239,46 @@ def ncu_traffic():
 
 
 # ----------------------------------------------------------------------------------------
-def cpu_oracle_throughput(spec, W, feats, seconds, max_reps=50):
-    """Rows/s of the numpy oracle on `feats` (one bounded sample), all BLAS threads."""
-    from oracle import ctr_oracle as O
-    O.forward(spec, W, feats)                                     # warm-up
+def cpu_oracle_throughput(spec, W, feats, seconds, max_reps=200):
+    """Rows/s of the threaded CPU restatement (oracle/ctr_oracle_torch.py) on `feats` (one
+    bounded sample), every host thread; returns (rows/s, reps, seconds, description)."""
+    from oracle import ctr_oracle_torch as OT
+    fwd, how = OT.cpu_predictor(spec, W)
+    fwd(feats)                                                    # warm-up
     n = len(feats["movieId"])
     t0 = time.perf_counter()
     reps = 0
     while True:
-        O.forward(spec, W, feats)
+        fwd(feats)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= seconds or reps >= max_reps:
             break
-    return n * reps / dt, reps, dt
+    return n * reps / dt, reps, dt, how
 
 
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path.  TensorFlow is
-    not installed / installable on this image, so this is the oracle port (numpy + OpenBLAS
-    threads) of the Keras graph, same workload, each step a bounded sample of the batch."""
+    not installed / installable on this image, so this is the port of the Keras graph that uses
+    the host threads the way TF's intra-op pool would (oracle/ctr_oracle_torch.py: torch CPU ops
+    for DIN, row-chunked numpy oracle otherwise), same workload, each step a bounded sample of
+    the batch."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    from oracle import ctr_oracle as O
+    from oracle import ctr_oracle_torch as OT
     from sparrowrecsys_b200.features import synthetic_features
     from sparrowrecsys_b200.spec import baseline_spec
     from sparrowrecsys_b200.weights import init_weights
     spec, W, note = cpu_spec_and_weights(baseline_spec(args.workload))
     feats = synthetic_features(spec, args.batch, seed=2, uniform_history=args.workload == "cfg5_din")
     cores = os.cpu_count() or 1
+    fwd, how = OT.cpu_predictor(spec, W, cores)
     # size the per-step sample so that steps+warmup stay within ~2 minutes
+    fwd(feats)
     t0 = time.perf_counter()
-    O.forward(spec, W, feats)
-    O.forward(spec, W, feats)
+    fwd(feats)
+    fwd(feats)
     t_batch = (time.perf_counter() - t0) / 2
     budget = 120.0
     rows = args.batch
@@ -278,10 +287,10 @@ def run_reference(args):
         rows = int(max(16, min(args.batch, args.batch * budget / (t_batch * total))))
     sample = {k: np.asarray(v)[:rows] for k, v in feats.items()}
     for _ in range(args.warmup):
-        O.forward(spec, W, sample)
+        fwd(sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.forward(spec, W, sample)
+        fwd(sample)
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     line = {
@@ -291,8 +300,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(args.workload, spec, args.batch) + note, "rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "inferences/s", "cores": cores, "kind": "port",
-                         "sample": "%d of %d rows per step, numpy float32 oracle (OpenBLAS, %d threads); "
-                                   "TF2 itself is not installable here" % (rows, args.batch, cores)},
+                         "sample": "%d of %d rows per step, %s; TF2 itself is not installable here"
+                                   % (rows, args.batch, how)},
         "e2e": {"value": value, "unit": "inferences/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -539,11 +548,11 @@ def run_ours(args):
             cpu_feats = {k: np.asarray(v)[:n_cpu] for k, v in feats.items()}
             if cspec is not spec:
                 cpu_feats = synthetic_features(cspec, n_cpu, seed=7, uniform_history=True)
-            v, reps, dt = cpu_oracle_throughput(cspec, cW, cpu_feats, args.cpu_seconds)
+            v, reps, dt, how = cpu_oracle_throughput(cspec, cW, cpu_feats, args.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": v, "unit": "inferences/s", "cores": os.cpu_count() or 1, "kind": "port",
-                "sample": "%d x %d-row batch of the same workload in %.1f s, numpy float32 oracle "
-                          "(OpenBLAS threads = cores); TF2 is not installable here%s" % (reps, n_cpu, dt, cnote)}
+                "sample": "%d x %d-row batch of the same workload in %.1f s, %s; TF2 is not "
+                          "installable here%s" % (reps, n_cpu, dt, how, cnote)}
         print(json.dumps(line))
     model.close()
     if distributed:

@@ -202,3 +202,22 @@ def test_fill_uniform_and_cosine_helpers():
     q = np.array([1.0, 0.0], np.float32)
     c = np.array([[1.0, 0.0], [0.0, 2.0], [-3.0, 0.0]], np.float32)
     np.testing.assert_allclose(O.cosine_similarity(q, c), [1.0, 0.0, -1.0])
+
+
+def test_threaded_cpu_baselines_equal_the_oracle():
+    """bench.py times `oracle/ctr_oracle_torch.py` as the CPU side; it must compute what the
+    parity oracle computes."""
+    from oracle import ctr_oracle_torch as OT
+    from sparrowrecsys_b200.features import synthetic_features
+    from sparrowrecsys_b200.spec import default_spec
+    from sparrowrecsys_b200.weights import init_weights
+    for model, kw in (("din", dict(emb_dim=16, hist_len=12, n_movies=500, n_users=300)),
+                      ("deepfm", dict(n_movies=500, n_users=300)), ("neuralcf", {})):
+        spec = default_spec(model, **kw)
+        W = init_weights(spec, 4)
+        f = synthetic_features(spec, 700, seed=5)
+        fwd, how = OT.cpu_predictor(spec, W, threads=4)
+        p, z = fwd(f)
+        po, zo = O.forward(spec, W, f)
+        assert p.shape == po.shape and np.abs(z - zo).max() < 2e-5, (model, how)
+        assert ("torch" in how) == (model == "din")
