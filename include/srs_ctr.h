@@ -177,7 +177,8 @@ int64_t srs_model_bytes_per_inference(const srs_model* m);
  * (din_rt_kernel / din_rt64_kernel: tcgen05 row tiles; din_tc_kernel: tcgen05 per pair;
  * din_kernel: CUDA cores); the choice follows the shape and can be forced with the environment
  * variable SRS_DIN_IMPL = rt | tc | cudacore read by srs_model_create (a forced variant that does
- * not support the shape makes srs_model_create fail).  SRS_EMBMLP_IMPL and SRS_DEEPFM_IMPL
+ * not support the shape makes srs_model_create fail; rth selects the experimental half-SM row-tile
+ * kernel din_rth_kernel, see csrc/din_rth.cu).  SRS_EMBMLP_IMPL and SRS_DEEPFM_IMPL
  * (tc | cudacore) do the same for EmbeddingMLP / Wide&Deep and DeepFM. */
 const char* srs_model_kernel_name(const srs_model* m);
 
