@@ -12,3 +12,13 @@ timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:din_ -c 1 -s 3 -o gpurun_out/prof_din_final -f \
     python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/b_ncu_final.log 2>&1
 ls -la gpurun_out/prof_din_final.ncu-rep gpurun_out/launches_final.csv
+
+# Later in the round (second session), one gpurun call each:
+#   python -m pytest tests/test_ranking.py -m gpu -x -q; python profiles/rank_latency.py
+#   python -m pytest tests/test_seq_dien.py -m gpu -x -q; python bench.py --workload ref_dien --steps 2000 --warmup 20 --cpu-seconds 3;
+#       python -m pytest tests -m gpu -x -q --deselect tests/test_seq_dien.py
+#   python -m pytest tests/test_narrow_ids.py tests/test_ranking.py -m gpu -q;
+#       for S in 2 4; do python bench.py --steps 6000 --warmup 200 --no-cpu-baseline --narrow-ids auto --streams $S; done;
+#       python bench.py --steps 6000 --warmup 200 --no-cpu-baseline --streams 1 --narrow-ids off
+# (outputs: rank_*_r01.*, dien_tests_r01.log, gpu_suite_r01_session2.log, bench_r01/bench_ref_dien.json,
+#  narrow_ids_sm_limit_tests_r01.log, bench_r01_streams/)
