@@ -244,10 +244,20 @@ def serve(models: Mapping[str, tuple], host: str = "127.0.0.1", port: int = 8501
     merge concurrent requests per model (`srv.batchers[name]` exposes the counters)."""
     batchers = {name: MicroBatcher(fn, max_rows, max_wait_s) for name, (_, fn) in models.items()} \
         if micro_batch else {}
-    srv = ThreadingHTTPServer((host, port), make_handler(models, threading.Lock(), store, batchers))
+    srv = _Server((host, port), make_handler(models, threading.Lock(), store, batchers))
     srv.daemon_threads = True
     srv.batchers = batchers
     return srv
+
+
+class _Server(ThreadingHTTPServer):
+    """`server_close()` also stops the per-model dispatcher threads."""
+    batchers: Mapping[str, MicroBatcher] = {}
+
+    def server_close(self):
+        super().server_close()
+        for b in self.batchers.values():
+            b.close()
 
 
 def main():

@@ -209,3 +209,5 @@ def test_concurrent_http_requests_share_library_calls():
         assert mb.requests == 16 and mb.calls < 16
     finally:
         srv.shutdown()
+        srv.server_close()
+    assert not mb._thread.is_alive()                          # dispatcher stopped with the server
