@@ -660,8 +660,13 @@ cudaError_t launch_din_rth(const DinRtParams& p, const BatchView& b, cudaStream_
 }
 
 cudaError_t setup_din_rth_attributes() {
-  return cudaFuncSetAttribute(din_rth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)din_rth_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(din_rth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)din_rth_smem_bytes());
+  if (e != cudaSuccess) return e;
+  // two CTAs per SM need the whole shared-memory carve-out (2 x 103 KB), not the smallest one
+  // that fits a single CTA
+  return cudaFuncSetAttribute(din_rth_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
 }
 
 }  // namespace srs
