@@ -490,6 +490,23 @@ def run_ours(args):
     if e2e_n >= 1 and not np.array_equal(chk.cpu().numpy(), hout[0].numpy()):
         raise SystemExit("e2e scores differ from device-path scores")
 
+    # ---- single-call latency (not part of the metric): one synchronous srs_predict_host ----
+    latency = None
+    try:
+        lat = []
+        for i in range(60):
+            t1 = time.perf_counter()
+            rc = lib.srs_predict_host(handle, C.byref(hstructs[i % host_ring]), hout[i % host_ring].data_ptr(), None)
+            lat.append((time.perf_counter() - t1) * 1e6)
+            if rc != 0:
+                _lib.check(rc)
+        lat = np.sort(np.array(lat[10:]))
+        latency = {"median": round(float(np.median(lat)), 1), "p99": round(float(lat[-1]), 1),
+                   "what": "one synchronous srs_predict_host call on a %d-row pinned host batch "
+                           "(H2D, kernel, D2H, wait), nothing else in flight" % B}
+    except Exception as e:                              # pragma: no cover - never fail the line for this
+        sys.stderr.write("latency probe failed: %r\n" % (e,))
+
     # ---- reduce over ranks ------------------------------------------------------------
     if distributed:
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
@@ -530,6 +547,7 @@ def run_ours(args):
                            "host buffers%s, wall clock"
                            % (n_slots, ", history ids as uint16 (hist16) widened on the device" if narrow else "")},
             "gpu_launches": args.steps,
+            "single_call_latency_us": latency,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
