@@ -23,7 +23,7 @@
 //   * the 128 KB top-MLP weight image does not fit: its eight 16 KB K-block pieces stream through
 //     three buffers behind the X operand (`pfull` / `pfree` mbarriers, bulk copies by warp 3),
 //     each consumed by the MMAs of its K block;
-//   * no register prefetch of the next group's ids (the other CTA covers that latency), no trace.
+//   * no register prefetch of the next group's ids (the other CTA covers that latency).
 #include <climits>
 
 #include "rt_common.cuh"
@@ -66,6 +66,13 @@ constexpr uint32_t HT_D2 = 128;                         // buffer u, tile row r:
 constexpr uint32_t HT_TOP1 = 0, HT_TOP2 = 64;
 constexpr uint32_t HT_COLS = 256;
 
+__device__ unsigned long long g_din_rth_trace[40];
+// phase timestamps of CTA 0 (srs_debug_din_trace; slot meaning as in din_rt.cu / profiles/trace_din_rt.py)
+#define RTH_TRACE(slot, cond)                                                     \
+  do {                                                                            \
+    if (p.trace && blockIdx.x == 0 && (cond)) g_din_rth_trace[slot] = clock64();  \
+  } while (0)
+
 __device__ __forceinline__ void rth_store_x4(uint8_t* tile, int block, int row, int col, float4 v) {
   const uint32_t off = block * 8192u + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
   const Split2 s0 = split_pack(v.x, v.y), s1 = split_pack(v.z, v.w);
@@ -92,6 +99,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
+  RTH_TRACE(0, tid == 0);
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // warp-uniform by construction
   const int wg = warp >> 2;                                      // 0: warps 0-3, 1: warps 4-7
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  RTH_TRACE(1, tid == 0);
   const uint32_t tbase = tmem_slot;
   const uint32_t lane_base = (uint32_t)(warp_w * 32) << 16;
   const uint32_t s_ring = smem_u32(ring);
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
     }
     fence_async_smem();                                     // the zeroed pad rows are MMA operand bytes
     __syncthreads();                                        // history ids, candidate rows staged
+    RTH_TRACE(2, tid == 0);
 
     // ================= phase 1: tiles ====================================================
     if (is_gather) {
@@ -275,6 +285,9 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
         cp_async_wait<kHAhead - 1>();                       // this tile's rows have landed
         fence_async_smem();
         mbar_arrive(&full[slot]);
+        if (k == 0) RTH_TRACE(20, tid == 0);
+        if (k == 2) RTH_TRACE(21, tid == 0);
+        if (k == 4) RTH_TRACE(22, tid == 0);
         if (k + kHAhead < n_tiles) gather(k + kHAhead);     // its slot frees when tile K + kHAhead - kHSlots retires
         cp_async_commit();
       }
@@ -388,6 +401,8 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
         const uint32_t tD1 = tbase + HT_D1;
         mbar_wait(&d1_full, K & 1);
         tc_fence_after();
+        if (k == 0) RTH_TRACE(3, tid == 128);
+        if (k == 2) RTH_TRACE(10, tid == 128);
         // ---- gate: v = D_hi + D_lo + cst; s = sum_j v_j P_tj + |v_j| Q_tj
         float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
         {
@@ -433,13 +448,17 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(&w_ready[u]);
+        if (k == 2) RTH_TRACE(11, tid == 128);
         if (k >= 1) pool_out(k - 1);                        // the other D2 buffer: its MMAs finished long ago
+        if (k == 2) RTH_TRACE(16, tid == 128);
       }
       if (n_tiles > 0) pool_out(n_tiles - 1);
+      RTH_TRACE(4, tid == 128);
     }
     kbase += n_tiles;
     tc_fence_before();
     __syncthreads();                                        // every MMA of the group has completed: the ring is free
+    RTH_TRACE(5, tid == 0);
 
     // ================= phase 2: top MLP on the group's 32 row slots, whole CTA ===============
     // warp 3 lane 0 streams the 8 weight pieces (W1 hi/lo per K block, then W2) through 3 buffers.
@@ -534,6 +553,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
     cphase ^= 1;
     __syncwarp();
     tc_fence_after();
+    RTH_TRACE(6, tid == 0);
     {
       uint32_t d[16], d2[16];
       tmem_ld16(tT1 + 16 * wg + lane_base, d);             // W1 . X hi
@@ -629,10 +649,16 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();                                     // ring and scratch are reused by the next group
+    RTH_TRACE(7, tid == 0);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_slot, HT_COLS);
+  RTH_TRACE(8, tid == 0);
+}
+
+cudaError_t read_din_rth_trace(unsigned long long* out40) {
+  return cudaMemcpyFromSymbol(out40, g_din_rth_trace, sizeof(unsigned long long) * 40);
 }
 
 size_t din_rth_smem_bytes() { return 1024 + HRING + HX_BYTES; }

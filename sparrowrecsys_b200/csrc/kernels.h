@@ -240,6 +240,7 @@ cudaError_t read_din_rt_trace(unsigned long long* out40);
 cudaError_t setup_din_rt_attributes();
 cudaError_t launch_din_rth(const DinRtParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t setup_din_rth_attributes();
+cudaError_t read_din_rth_trace(unsigned long long* out40);
 cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t setup_din_rt64_attributes();

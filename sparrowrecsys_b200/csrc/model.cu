@@ -1547,7 +1547,8 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   m->din_rt.trace = enable;
   if (out40) {
     CUDA_TRY(cudaDeviceSynchronize());
-    if (m->use_din_rt) CUDA_TRY(read_din_rt_trace(reinterpret_cast<unsigned long long*>(out40)));
+    if (m->use_din_rth) CUDA_TRY(read_din_rth_trace(reinterpret_cast<unsigned long long*>(out40)));
+    else if (m->use_din_rt) CUDA_TRY(read_din_rt_trace(reinterpret_cast<unsigned long long*>(out40)));
     else CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
   }
   return SRS_OK;
