@@ -166,3 +166,66 @@ def test_rank_sharded_on_nccl_single_rank_group():
         assert np.array_equal(pos.cpu().numpy(), ridx) and np.array_equal(top.cpu().numpy(), rtop)
     finally:
         dist.destroy_process_group()
+
+
+# ---- the sort network of csrc/topk.cu, re-derived on the CPU ----------------------------------
+def _rank_keys(s):
+    """rank_key() of topk.cu: ascending key order = the ranking."""
+    u = s.view(np.uint32).astype(np.uint64)
+    mono = np.where(u & 0x80000000, ~u & 0xFFFFFFFF, u | 0x80000000)
+    mono = np.where(np.isnan(s), 0xFFFFFFFF, mono)
+    return ((~mono & 0xFFFFFFFF) << np.uint64(32)) | np.arange(len(s), dtype=np.uint64)
+
+
+def _bitonic(keys, chunk):
+    """The launch sequence of launch_topk for NP keys: per-chunk shared-memory stages, global
+    compare-exchange steps for strides >= chunk (pair_lo / direction rule copied from the kernels)."""
+    NP = len(keys)
+    pair_lo = lambda t, j: ((t & ~(j - 1)) << 1) | (t & (j - 1))
+
+    def step(a, lo, j, w, base=0):
+        hi = lo | j
+        x, y = a[lo].copy(), a[hi].copy()
+        swap = (x > y) == (((base + lo) & w) == 0)
+        a[lo], a[hi] = np.where(swap, y, x), np.where(swap, x, y)
+
+    def chunk_sort(first_w):
+        for c in range(NP // chunk):
+            a, base = keys[c * chunk:(c + 1) * chunk], c * chunk
+            t = np.arange(chunk // 2)
+            w_end = chunk if first_w == 2 else first_w
+            w = first_w
+            while True:
+                j = min(w, chunk) >> 1
+                while j > 0:
+                    step(a, pair_lo(t, j), j, w, base)
+                    j >>= 1
+                if w == w_end:
+                    break
+                w <<= 1
+    chunk_sort(2)
+    w = 2 * chunk
+    while w <= NP:
+        j = w >> 1
+        while j >= chunk:
+            step(keys, pair_lo(np.arange(NP // 2), j), j, w)
+            j >>= 1
+        chunk_sort(w)
+        w <<= 1
+    return keys
+
+
+@pytest.mark.parametrize("n,chunk", [(5, 32), (800, 1024), (100, 16), (1000, 64), (4097, 256)])
+def test_sort_network_and_key_order_match_the_java_comparator(n, chunk):
+    rng = np.random.default_rng(n)
+    s = rng.standard_normal(n).astype(np.float32)
+    s[rng.integers(0, n, n // 3)] = np.float32(0.5)
+    if n > 8:
+        s[1], s[2], s[3], s[4] = np.nan, -0.0, 0.0, -np.inf
+    NP = chunk
+    while NP < n:
+        NP <<= 1
+    keys = np.full(NP, np.iinfo(np.uint64).max, np.uint64)
+    keys[:n] = _rank_keys(s)
+    order = (_bitonic(keys, chunk)[:n] & np.uint64(0xFFFFFFFF)).astype(np.int32)
+    assert np.array_equal(order, O.rank_topk(s, n)[0])
