@@ -24,6 +24,7 @@ from .spec import (GENRE_VOCAB, MOVIE_GENRE_KEYS, NUMERIC_KEYS, USER_GENRE_KEYS,
                    ModelSpec, history_keys)
 
 _GENRE_INDEX = {g: i for i, g in enumerate(GENRE_VOCAB)}
+_GENRE_LOOKUP = {**_GENRE_INDEX, **{g.encode(): i for g, i in _GENRE_INDEX.items()}}   # str and bytes keys
 
 _FLOAT_COLS = {"rating", "movieAvgRating", "movieRatingStddev", "userAvgRating",
                "userRatingStddev", "userReleaseYearStddev"}
@@ -61,20 +62,13 @@ def load_samples_csv(path: str, max_rows: Optional[int] = None) -> Dict[str, np.
 
 def genre_to_index(values) -> np.ndarray:
     """Vocabulary lookup of `categorical_column_with_vocabulary_list` (default
-    `default_value=-1`, `num_oov_buckets=0`): known genre -> position, else -1."""
+    `default_value=-1`, `num_oov_buckets=0`): known genre (str or bytes) -> position, else -1."""
     arr = np.asarray(values)
     if arr.dtype.kind in "iu":          # already indexed by the caller
         return arr.astype(np.int32)
     flat = arr.ravel()
-    if flat.dtype.kind == "S":
-        flat = np.char.decode(flat, "utf-8", "replace")
-    elif flat.dtype == object and any(isinstance(v, bytes) for v in flat):
-        flat = np.array([v.decode("utf-8", "replace") if isinstance(v, bytes) else v for v in flat],
-                        dtype=object)
-    # look up each distinct value once (a batch holds at most 20 of them)
-    uniq, inv = np.unique(flat.astype(str), return_inverse=True)
-    lut = np.array([_GENRE_INDEX.get(str(u), -1) for u in uniq], dtype=np.int32)
-    return lut[inv.reshape(-1)].reshape(arr.shape)
+    get = _GENRE_LOOKUP.get             # one dict probe per element (~0.1 us)
+    return np.fromiter((get(v, -1) for v in flat.tolist()), np.int32, count=flat.shape[0]).reshape(arr.shape)
 
 
 def _as_1d(features: Mapping[str, object], key: str) -> np.ndarray:

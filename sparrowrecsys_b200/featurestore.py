@@ -28,6 +28,8 @@ from typing import Dict, Iterable, Mapping, Optional, Sequence
 
 import numpy as np
 
+from .features import genre_to_index
+
 USER_PREFIX = "uf:"          # FeatureEngForRecModel.scala:222
 MOVIE_PREFIX = "mf:"         # FeatureEngForRecModel.scala:144
 
@@ -142,6 +144,7 @@ class MovieFeatureTable:
         self.n_movies = int(n_movies)
         self.present = np.zeros(n_movies, bool)
         self.str_cols = {k: np.full(n_movies, "", dtype=object) for k in MOVIE_STR_FIELDS}
+        self.idx_cols = {k: np.full(n_movies, -1, np.int32) for k in MOVIE_STR_FIELDS}   # vocabulary indices
         self.int_cols = {k: np.zeros(n_movies, np.int32) for k in MOVIE_INT_FIELDS}
         self.float_cols = {k: np.zeros(n_movies, np.float32) for k in MOVIE_FLOAT_FIELDS}
 
@@ -158,18 +161,21 @@ class MovieFeatureTable:
             t.present[mid] = True
             for k in MOVIE_STR_FIELDS:
                 t.str_cols[k][mid] = h.get(k, "")
+                t.idx_cols[k][mid] = genre_to_index([h.get(k, "")])[0]
             for k in MOVIE_INT_FIELDS:
                 t.int_cols[k][mid] = parse_int(h.get(k, ""))
             for k in MOVIE_FLOAT_FIELDS:
                 t.float_cols[k][mid] = np.float32(parse_float(h.get(k, "")))
         return t
 
-    def gather(self, movie_ids: np.ndarray) -> Dict[str, np.ndarray]:
+    def gather(self, movie_ids: np.ndarray, encoded: bool = False) -> Dict[str, np.ndarray]:
+        """Columns of the given movies; `encoded`: genres as vocabulary indices (-1 = missing /
+        OOV), which `predict` accepts in place of the strings and skips the lookup for."""
         ids = np.asarray(movie_ids, np.int64)
         if ids.size and (ids.min() < 0 or ids.max() >= self.n_movies):
             raise ValueError("movie id out of range [0, %d)" % self.n_movies)
         out: Dict[str, np.ndarray] = {}
-        for cols in (self.str_cols, self.int_cols, self.float_cols):
+        for cols in (self.idx_cols if encoded else self.str_cols, self.int_cols, self.float_cols):
             for k, a in cols.items():
                 out[k] = a[ids]
         return out
@@ -191,17 +197,20 @@ def parse_user_features(fields: Mapping[str, str], hist_len: int = 5) -> Dict[st
 
 
 def assemble(user_id: int, user_fields: Mapping[str, str], candidate_ids: Sequence[int],
-             movies: MovieFeatureTable, hist_len: int = 5) -> Dict[str, np.ndarray]:
+             movies: MovieFeatureTable, hist_len: int = 5, encoded: bool = False) -> Dict[str, np.ndarray]:
     """Feature dict of one ranking request - the instances `callNeuralCFTFServing` would
     post (`RecForYouProcess.java:118-127`) widened by the stored features: user columns
     broadcast over the n candidates, movie columns gathered by candidate id.  Keys and dtypes
     are those of the Keras `inputs` dicts (e.g. `DIN.py:34-59`), so the result goes straight
-    into `predict` / `rank` of any of the models."""
+    into `predict` / `rank` of any of the models.  `encoded`: genre columns as vocabulary indices
+    instead of strings (same scores; saves the per-row string lookup on the request path)."""
     cand = np.asarray(candidate_ids, np.int32).reshape(-1)
     n = cand.shape[0]
     feats: Dict[str, np.ndarray] = {"movieId": cand, "userId": np.full(n, int(user_id), np.int32)}
     for k, v in parse_user_features(user_fields, hist_len).items():
-        if isinstance(v, str):
+        if isinstance(v, str) and encoded:
+            col = np.full(n, genre_to_index([v])[0], np.int32)
+        elif isinstance(v, str):
             col = np.empty(n, dtype=object)
             col[:] = v
         elif isinstance(v, np.floating):
@@ -209,7 +218,7 @@ def assemble(user_id: int, user_fields: Mapping[str, str], candidate_ids: Sequen
         else:
             col = np.full(n, v, np.int32)
         feats[k] = col
-    feats.update(movies.gather(cand))
+    feats.update(movies.gather(cand, encoded))
     return feats
 
 

@@ -126,3 +126,22 @@ def test_serving_fills_absent_inputs_from_the_store(store, raw):
     # without a store: plain defaults, as before
     f3 = serving.instances_to_features(spec, [{"userId": uid, "movieId": mids[0]}])
     assert f3["userGenre1"].tolist() == [""] and f3["releaseYear"].tolist() == [0.0]
+
+
+def test_encoded_assembly_is_the_same_batch(store, raw):
+    """`assemble(..., encoded=True)` hands `predict` vocabulary indices instead of genre strings:
+    same encoded batch, no per-row string lookup on the request path."""
+    spec = default_spec("embeddingmlp")                      # reads all 3 + 5 genre slots
+    table = FS.MovieFeatureTable.from_store(store, spec.n_movies)
+    uid = int(raw["userId"][3])
+    cands = store.movie_ids()[:60] + [998]
+    a = encode_batch(spec, FS.assemble(uid, store.user_features(uid), cands, table))
+    f = FS.assemble(uid, store.user_features(uid), cands, table, encoded=True)
+    assert f["movieGenre1"].dtype == np.int32 and f["userGenre3"].dtype == np.int32
+    b = encode_batch(spec, f)
+    for name in ("movie_id", "user_id", "movie_genre", "user_genre", "numerics"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    from sparrowrecsys_b200.features import genre_to_index
+    mixed = np.array(["Drama", b"Action", "", "nope", None], dtype=object)
+    assert genre_to_index(mixed).tolist() == [10, 1, -1, -1, -1]
+    assert genre_to_index(np.array([b"IMAX", b"x"])).tolist() == [15, -1]
