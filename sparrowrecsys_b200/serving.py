@@ -46,6 +46,20 @@ _PATH = re.compile(r"^/v1/models/([^/:]+)(?:/versions/\d+)?:predict$")
 _STRING_KEYS = set(MOVIE_GENRE_KEYS) | set(USER_GENRE_KEYS)
 
 
+def inputs_to_instances(inputs) -> List[Mapping[str, object]]:
+    """TF-Serving's columnar request format (`{"inputs": {"userId": [..], "movieId": [..]}}`,
+    which TF-Serving answers with `{"outputs": ...}`) -> the row format.  The Java server only
+    uses the row format; the columnar one is accepted so that other TF-Serving clients work."""
+    if not isinstance(inputs, Mapping) or not inputs:
+        raise ValueError("'inputs' must be an object of equally long lists")
+    cols = {k: (v if isinstance(v, list) else [v]) for k, v in inputs.items()}
+    n = {len(v) for v in cols.values()}
+    if len(n) != 1:
+        raise ValueError("'inputs' columns differ in length")
+    unwrap = lambda x: x[0] if isinstance(x, list) and len(x) == 1 else x      # [[1],[2]] and [1,2]
+    return [{k: unwrap(v[i]) for k, v in cols.items()} for i in range(n.pop())]
+
+
 def instances_to_features(spec: ModelSpec, instances: List[Mapping[str, object]],
                           store=None) -> Dict[str, np.ndarray]:
     """TF-Serving row format -> dict of columns for `predict`.  With a `FeatureStore`,
@@ -216,13 +230,16 @@ def make_handler(models: Mapping[str, tuple], lock: threading.Lock, store=None,
             try:
                 n = int(self.headers.get("Content-Length", "0"))
                 req = json.loads(self.rfile.read(n) or b"{}")
-                feats = instances_to_features(spec, req.get("instances"), store)
+                columnar = "instances" not in req and "inputs" in req
+                feats = instances_to_features(
+                    spec, inputs_to_instances(req["inputs"]) if columnar else req.get("instances"), store)
                 if batchers and m.group(1) in batchers:
                     p = batchers[m.group(1)].submit(feats)
                 else:
                     with lock:                   # one library call at a time per process
                         p = predict_fn(feats)
-                self._send(200, {"predictions": [[float(v)] for v in np.asarray(p).reshape(-1)]})
+                scores = [[float(v)] for v in np.asarray(p).reshape(-1)]
+                self._send(200, {"outputs": scores} if columnar else {"predictions": scores})
             except (ValueError, KeyError, TypeError, json.JSONDecodeError) as e:
                 self._send(400, {"error": str(e)})
 

@@ -62,6 +62,13 @@ def test_wire_contract_with_stand_in_scorer():
         assert code == 404
         code, body = _post(port, "/v1/models/recmodel:predict", {"nope": 1})
         assert code == 400
+        # TF-Serving's columnar format is answered with "outputs"
+        code, body = _post(port, "/v1/models/recmodel:predict",
+                           {"inputs": {"userId": [10351, 10351], "movieId": [[52], [53]]}})
+        assert code == 200 and abs(body["outputs"][0][0] - 0.68536943) < 1e-6 \
+            and abs(body["outputs"][1][0] - 0.17321654) < 1e-6
+        code, body = _post(port, "/v1/models/recmodel:predict", {"inputs": {"userId": [1, 2], "movieId": [3]}})
+        assert code == 400
     finally:
         srv.shutdown()
 
