@@ -54,3 +54,20 @@ def rank_by_embedding(query, cands, size: int, device: int = 0):
                                                         stream.cuda_stream))
         idx, top = topk_device(scores, size, stream)
     return idx.cpu().numpy(), top.cpu().numpy()
+
+
+def load_embeddings_csv(path: str):
+    """The reference's embedding files (`webroot/modeldata/item2vecEmb.csv`, `userEmb.csv`):
+    one `id:f f f ...` line per entity, read as `DataManager.loadMovieEmb` / `loadUserEmb` do
+    (`online/datamanager/DataManager.java:88-108,143-163`: split on ":", two parts or the line is
+    skipped; values split on whitespace, `Float.parseFloat` - `online/util/Utility.java:6-13`).
+    Returns (ids int32 [n], embeddings float32 [n, dim]) in file order."""
+    ids, rows = [], []
+    with open(path) as f:
+        for line in f:
+            parts = line.rstrip("\n").split(":")
+            if len(parts) != 2:
+                continue
+            ids.append(int(parts[0]))
+            rows.append([float(x) for x in parts[1].split()])
+    return np.asarray(ids, np.int32), np.asarray(rows, np.float32)

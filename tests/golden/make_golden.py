@@ -15,6 +15,9 @@ Writes, next to this file:
   `samples_head.csv` plus userId 10351 (the pair `HttpClient.main` posts,
   `online/util/HttpClient.java:110-147`); `user_ids` / `user_rows` rebuild a
   zero-filled table.
+* `item2vecEmb.csv`, `userEmb_head.csv` - the reference's shipped embeddings for the "emb"
+  ranker (`modeldata/item2vecEmb.csv` byte-for-byte; first 20 lines of `modeldata/userEmb.csv`),
+  in the `id:f f f ...` format `DataManager.loadMovieEmb` / `Utility.parseEmbStr` read.
 * `full_file_stats.json` - accuracy / ROC-AUC of neuralcf/002 over all 22 440 test
   rows (oracle output), for the whole-file sanity check quoted in SURVEY.md 8c.
 """
@@ -35,7 +38,19 @@ REF = "/root/reference/src/main/resources/webroot/"
 N_HEAD = 512
 
 
+def copy_embeddings():
+    with open(REF + "modeldata/item2vecEmb.csv", "rb") as f:
+        data = f.read()
+    with open(os.path.join(HERE, "item2vecEmb.csv"), "wb") as f:
+        f.write(data)
+    with open(REF + "modeldata/userEmb.csv", "rb") as f:
+        head = b"".join(f.readline() for _ in range(20))
+    with open(os.path.join(HERE, "userEmb_head.csv"), "wb") as f:
+        f.write(head)
+
+
 def main():
+    copy_embeddings()
     src = REF + "sampledata/testSamples.csv"
     with open(src, "rb") as f:
         lines = f.read().split(b"\n")

@@ -229,3 +229,58 @@ def test_sort_network_and_key_order_match_the_java_comparator(n, chunk):
     keys[:n] = _rank_keys(s)
     order = (_bitonic(keys, chunk)[:n] & np.uint64(0xFFFFFFFF)).astype(np.int32)
     assert np.array_equal(order, O.rank_topk(s, n)[0])
+
+
+# ---- the "emb" ranker on the reference's shipped embeddings -----------------------------------
+# Known answers: top 5 of all 881 shipped movie embeddings for the first three users of
+# userEmb.csv, by a literal restatement of Embedding.calculateSimilarity (float products,
+# double sums; tests/golden/make_golden.py copies the two files from the reference).
+EMB_KNOWN = {
+    10292: ([875, 15, 424, 433, 387], [0.9197663, 0.854994, 0.8533278, 0.8480263, 0.8424886]),
+    19125: ([293, 555, 868, 288, 16], [0.7498215, 0.7454202, 0.718767, 0.7139385, 0.7110246]),
+    26985: ([15, 415, 433, 170, 23], [0.8829988, 0.8794499, 0.8699859, 0.8569337, 0.8543974]),
+}
+
+
+def _shipped_embeddings():
+    import os
+    from conftest import GOLDEN
+    from sparrowrecsys_b200.ranking import load_embeddings_csv
+    mid, M = load_embeddings_csv(os.path.join(GOLDEN, "item2vecEmb.csv"))
+    uid, U = load_embeddings_csv(os.path.join(GOLDEN, "userEmb_head.csv"))
+    return mid, M, uid, U
+
+
+def _java_cosine(a, b):
+    """online/model/Embedding.java:33-47, statement for statement."""
+    import math
+    dot = n1 = n2 = 0.0
+    for x, y in zip(a, b):
+        dot += float(np.float32(x) * np.float32(y))
+        n1 += float(np.float32(x) * np.float32(x))
+        n2 += float(np.float32(y) * np.float32(y))
+    return dot / (math.sqrt(n1) * math.sqrt(n2))
+
+
+def test_emb_ranker_oracle_on_shipped_embeddings():
+    mid, M, uid, U = _shipped_embeddings()
+    assert M.shape == (881, 10) and U.shape == (20, 10) and mid[0] == 710 and uid[0] == 10292
+    for k in range(3):
+        ref = O.cosine_similarity(U[k], M)
+        lit = np.array([_java_cosine(U[k], m) for m in M[:60]])
+        assert np.abs(lit - ref[:60]).max() < 1e-15
+        idx, _ = O.rank_topk(ref.astype(np.float32), 5)
+        ids, sims = EMB_KNOWN[int(uid[k])]
+        assert mid[idx].tolist() == ids
+        np.testing.assert_allclose(ref[idx], sims, atol=5e-8)
+
+
+@pytest.mark.gpu
+def test_emb_ranker_device_on_shipped_embeddings():
+    from sparrowrecsys_b200.ranking import rank_by_embedding
+    mid, M, uid, U = _shipped_embeddings()
+    for k in range(3):
+        idx, top = rank_by_embedding(U[k], M, 5)
+        ids, sims = EMB_KNOWN[int(uid[k])]
+        assert mid[idx].tolist() == ids
+        np.testing.assert_allclose(top, sims, atol=1e-6)
