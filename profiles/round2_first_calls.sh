@@ -16,6 +16,9 @@
 # 4. the e2e leg: is it host-API bound now?  (184 M inf/s = 22 us per batch with 0.69 MB H2D =
 #    16.8 us and 18.7 us of device time: count the API calls per batch in srs_predict_host_batches -
 #    H2D, widen, forward, D2H, slot sync - and try 8 slots / one event per slot)
+#    and SRS_ZERO_COPY_SCORES=1 (kernels write the scores into the caller's pinned buffer, no D2H call):
+#      SRS_TEST_ZERO_COPY=1 python -m pytest tests/test_narrow_ids.py -k zero_copy -q
+#      SRS_ZERO_COPY_SCORES=1 python bench.py --steps 6000 --warmup 200 --no-cpu-baseline
 # 5. DIEN: dien_kernel runs one row per warp (70 us per 4096 rows at E = 10, T = 5); two or three
 #    rows per warp (EP = 12 uses 12 of 32 lanes) is the obvious next step there.
 echo "this file is a checklist, not a script to run as is"

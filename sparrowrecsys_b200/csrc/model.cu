@@ -92,6 +92,8 @@ struct srs_model {
   DeepFmTcParams fm_tc{};
   bool use_fm_tc = false;
   const char* kernel_name = "";
+  bool zero_copy_scores = false;     // SRS_ZERO_COPY_SCORES=1 (experimental): kernels write the scores
+                                     // of a host batch straight into the caller's pinned buffer
   int device_sms = 148;
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
@@ -1109,7 +1111,9 @@ int ensure_slot(srs_model* m, Slot& s, int B) {
 
 // H2D of the batch into the slot's staging and the forward kernel, on the slot's stream;
 // the scores are left in s.d_probs (and s.d_logits).
-int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits) {
+// `probs_out`: where the kernel writes the scores (default: the slot's device buffer).
+int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits,
+                     float* probs_out = nullptr) {
   int rc = check_batch(m, b);
   if (rc != SRS_OK) return rc;
   CUDA_TRY(cudaSetDevice(m->device));
@@ -1166,18 +1170,30 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
   v.movie_genre = reinterpret_cast<const int32_t*>(d + L.mg);
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
-  v.probs = s.d_probs; v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
+  v.probs = probs_out ? probs_out : s.d_probs;
+  v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
   return launch(m, v, s.stream);
 }
 
 int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float* logits,
                  bool copy_err = true) {
   if (!probs) return fail(SRS_ERR_INVALID, "probs is null");
-  int rc = stage_and_launch(m, s, b, logits != nullptr);
+  // Experimental (SRS_ZERO_COPY_SCORES=1): a pinned output buffer is device-addressable under
+  // unified addressing, so the kernel can write the 4 B per row over PCIe itself and the
+  // device-to-host copy - one driver call and one copy-engine operation per batch - goes away.
+  float* direct = nullptr;
+  if (m->zero_copy_scores && b && b->B > 0) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, probs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      direct = static_cast<float*>(at.devicePointer);
+    else
+      cudaGetLastError();                                 // pageable memory: not an error, use the copy
+  }
+  int rc = stage_and_launch(m, s, b, logits != nullptr, direct);
   if (rc != SRS_OK) return rc;
   if (b->B == 0) return SRS_OK;
   const size_t B = (size_t)b->B;
-  CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (!direct) CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (logits) CUDA_TRY(cudaMemcpyAsync(logits, s.d_logits, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (copy_err)
     CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -1236,6 +1252,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   srs_model* m = new srs_model();
   m->spec = *spec;
   m->device = device;
+  if (const char* zc = getenv("SRS_ZERO_COPY_SCORES")) m->zero_copy_scores = atoi(zc) == 1;
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

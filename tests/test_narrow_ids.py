@@ -106,3 +106,31 @@ def test_sm_limit_does_not_change_scores(cfg, B):
         for n in (74, 37, 5, 1, 0, 1000):
             m.set_sm_limit(n)
             assert np.array_equal(m.predict(f), ref), n
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not __import__("os").environ.get("SRS_TEST_ZERO_COPY"),
+                    reason="SRS_ZERO_COPY_SCORES is experimental: opt in with SRS_TEST_ZERO_COPY=1")
+def test_zero_copy_scores_equal_copied_scores(monkeypatch):
+    """Kernels writing the scores of a host batch straight into the caller's pinned buffer
+    (SRS_ZERO_COPY_SCORES=1, read at model creation) must give the bytes the copy gives."""
+    import torch
+    from sparrowrecsys_b200 import _lib
+    from sparrowrecsys_b200.model import CTRModel, _host_struct
+    spec = baseline_spec("cfg3_din")
+    W = init_weights(spec, 5)
+    f = synthetic_features(spec, 4096, seed=6)
+    enc = encode_batch(spec, f)
+    with CTRModel(spec, W) as m:
+        ref = m.predict(f)[:, 0]
+    monkeypatch.setenv("SRS_ZERO_COPY_SCORES", "1")
+    with CTRModel(spec, W) as m:
+        assert np.array_equal(m.predict(f)[:, 0], ref)            # pageable numpy buffer: falls back
+        out = torch.zeros(4096, dtype=torch.float32).pin_memory()
+        keep = []
+        b = _host_struct(enc, keep)
+        _lib.check(_lib.load().srs_predict_host(m._h, C.byref(b), out.data_ptr(), None))
+        assert np.array_equal(out.numpy(), ref)
+        outs = [torch.zeros(1024, dtype=torch.float32).pin_memory() for _ in range(4)]
+        m.predict_batches([enc.slice(i * 1024, (i + 1) * 1024) for i in range(4)], [o.numpy() for o in outs])
+        assert np.array_equal(np.concatenate([o.numpy() for o in outs]), ref)
