@@ -46,11 +46,12 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, tiles_per_group, seed):
+    def __init__(self, tiles_per_group, seed, builder_gathers=False):
         self.rng = random.Random(seed)
         self.groups = tiles_per_group
+        self.bg = builder_gathers              # SRS_DIN_RTH_BG=1: the builder warp is the third gatherer
         b = lambda n, c: Bar(n, c)
-        self.full = [b("full%d" % i, 64 + 32) for i in range(SLOTS)]
+        self.full = [b("full%d" % i, (96 if builder_gathers else 64) + 32) for i in range(SLOTS)]
         self.empty = [b("empty%d" % i, 1) for i in range(SLOTS)]
         self.d1_full, self.d1_free = b("d1_full", 1), b("d1_free", 128)
         self.w_ready = [b("w_ready%d" % i, 128) for i in range(2)]
@@ -136,14 +137,37 @@ class Sim:
         kbase = pbase = 0
         for n_tiles in self.groups:
             yield from self.syncthreads("b")
-            for k in range(n_tiles):
+
+            def build_b(k):
+                slot = (kbase + k) % SLOTS
+                self.touch("B%d" % slot, "builder write")
+                yield
+                self.full[slot].arrive(32)
+
+            def gather(k):
                 K = kbase + k
                 slot = K % SLOTS
                 if K >= SLOTS:
                     yield from self.wait(self.empty[slot], ((K // SLOTS) + 1) & 1, K // SLOTS - 1)
-                self.touch("B%d" % slot, "builder write")
-                yield
-                self.full[slot].arrive(32)
+                self.touch("A%d" % slot, "cp.async into tile (builder warp)")
+            if not self.bg:
+                for k in range(n_tiles):
+                    K = kbase + k
+                    slot = K % SLOTS
+                    if K >= SLOTS:
+                        yield from self.wait(self.empty[slot], ((K // SLOTS) + 1) & 1, K // SLOTS - 1)
+                    yield from build_b(k)
+            else:
+                for a in range(AHEAD):
+                    if a < n_tiles:
+                        yield from gather(a)
+                        yield from build_b(a)
+                for k in range(n_tiles):
+                    self.full[(kbase + k) % SLOTS].arrive(32)
+                    yield
+                    if k + AHEAD < n_tiles:
+                        yield from gather(k + AHEAD)
+                        yield from build_b(k + AHEAD)
             kbase += n_tiles
             yield from self.syncthreads("b")
 
@@ -301,7 +325,8 @@ def main():
     for shape in shapes:
         for seed in range(60):
             Sim(shape, seed).run()
-            runs += 1
+            Sim(shape, seed, builder_gathers=True).run()
+            runs += 2
     print("din_rth protocol model: %d runs over %d group shapes, no deadlock, no parity aliasing, "
           "no operand hazard" % (runs, len(shapes)))
 

@@ -23,7 +23,10 @@
 //   * the 128 KB top-MLP weight image does not fit: its eight 16 KB K-block pieces stream through
 //     three buffers behind the X operand (`pfull` / `pfree` mbarriers, bulk copies by warp 3),
 //     each consumed by the MMAs of its K block;
-//   * no register prefetch of the next group's ids (the other CTA covers that latency).
+//   * no register prefetch of the next group's ids (the other CTA covers that latency);
+//   * optional (SRS_DIN_RTH_BG=1 -> p.nch = 1): the builder warp also gathers a third of the tile's
+//     rows (96 gathering threads x 11 copies instead of 64 x 16) - cp.async issue is what bounds
+//     the tile phase, and the builder is idle most of the time.
 #include <climits>
 
 #include "rt_common.cuh"
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
   // and sit in griddepcontrol.wait, which is exactly the slot another stream's launch should get.
   if (warp == 0) tmem_alloc(&tmem_slot, HT_COLS);
   if (warp == 1) {                                       // one mbarrier per lane
-    if (lane < 3) mbar_init(&full[lane], kHGatherThreads + kHBuilderThreads);
+    if (lane < 3) mbar_init(&full[lane], (p.nch ? 96 : kHGatherThreads) + kHBuilderThreads);
     else if (lane < 6) mbar_init(&empty[lane - 3], 1);
     else if (lane == 6) mbar_init(&d1_full, 1);
     else if (lane == 7) mbar_init(&d1_free, 128);
@@ -170,26 +173,28 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
   int kbase = 0;                                        // tiles of earlier groups of this CTA
   int pbase = 0;                                        // weight pieces of earlier groups
 
-  // gatherer constants: copy n of this thread moves chunk (i & 7) of history cell (i >> 3), i = tid + 64 n,
-  // cells counted row 0 positions 0..T-1, then row 1
-  uint32_t g_dst[kHCopies];
-  int g_ids[kHCopies];
-#pragma unroll
-  for (int n = 0; n < kHCopies; ++n) {
-    const int i = (tid & 63) + kHGatherThreads * n, cell = i >> 3, c = i & 7;
-    const int r = cell >= T ? 1 : 0, pos = cell - r * T;
-    g_ids[n] = cell < 2 * T ? r * kHIdsLd + pos : -1;
-    g_dst[n] = (uint32_t)(r * 64 + pos) * 128u + (uint32_t)((c ^ (pos & 7)) << 4);
-  }
-  const uint32_t g_src = (uint32_t)(tid & 7) * 16u;
+  // gatherer constants: copy n of this thread moves chunk (i & 7) of history cell (i >> 3), i = gt + G n,
+  // cells counted row 0 positions 0..T-1, then row 1; G = 64 gathering threads (warps 0-1), or 96 when
+  // the builder warp gathers too (gt = 64 + lane there): 16 resp. 11 copies per thread
+  const bool builder_gathers = p.nch != 0;
+  const int gthreads = builder_gathers ? 96 : kHGatherThreads;
+  const int ncopies = builder_gathers ? 11 : kHCopies;
+  const int gt = is_builder ? 64 + lane : (tid & 63);
+  const uint32_t g_chunk = (uint32_t)(gt & 7);          // gthreads % 8 == 0: every copy of a thread moves the same chunk
   auto gather = [&](int k) {                            // local tile k -> slot of global tile kbase + k
     const int K = kbase + k, slot = K % kHSlots;
     if (K >= kHSlots) mbar_wait(&empty[slot], ((K / kHSlots) + 1) & 1);
     uint8_t* A = ring + slot * HS_SLOT;
     const int* idrow = ids_s + 2 * k * kHIdsLd;
 #pragma unroll
-    for (int n = 0; n < kHCopies; ++n)
-      if (g_ids[n] >= 0) cp_async16(A + g_dst[n], p.movie_split + (size_t)idrow[g_ids[n]] * 128 + g_src);
+    for (int n = 0; n < kHCopies; ++n) {
+      const int cell = (gt >> 3) + (gthreads >> 3) * n;   // addresses on the fly: 32 registers less than tables
+      if (n < ncopies && cell < 2 * T) {
+        const int r = cell >= T ? 1 : 0, pos = cell - r * T;
+        cp_async16(A + (uint32_t)(r * 64 + pos) * 128u + ((g_chunk ^ (uint32_t)(pos & 7)) << 4),
+                   p.movie_split + (size_t)idrow[r * kHIdsLd + pos] * 128 + g_chunk * 16u);
+      }
+    }
   };
 
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -294,9 +299,8 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
       cp_async_wait<0>();
     } else if (is_builder) {
       // ---- B operand of every tile: W_r = (Wsub+Wh) + diag(c_r) Wp, bf16 hi / lo; lane = unit
-      for (int k = 0; k < n_tiles; ++k) {
-        const int K = kbase + k, slot = K % kHSlots;
-        if (K >= kHSlots) mbar_wait(&empty[slot], ((K / kHSlots) + 1) & 1);
+      auto build_b = [&](int k) {                           // the slot of tile k is free (caller waited)
+        const int slot = (kbase + k) % kHSlots;
         uint8_t* Bt = ring + slot * HS_SLOT + HS_A;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -318,6 +322,33 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
           }
         fence_async_smem();
         mbar_arrive(&full[slot]);
+      };
+      if (!builder_gathers) {
+        for (int k = 0; k < n_tiles; ++k) {
+          const int K = kbase + k, slot = K % kHSlots;
+          if (K >= kHSlots) mbar_wait(&empty[slot], ((K / kHSlots) + 1) & 1);
+          build_b(k);
+        }
+      } else {
+        // this warp is also the third gatherer: per tile it requests its share of the rows (gather()
+        // waits for the slot), builds B while they fly (first arrival on `full`), and arrives a
+        // second time when its copies have landed - same schedule as warps 0-1
+#pragma unroll
+        for (int a = 0; a < kHAhead; ++a) {
+          if (a < n_tiles) gather(a);
+          cp_async_commit();
+          if (a < n_tiles) build_b(a);
+        }
+        for (int k = 0; k < n_tiles; ++k) {
+          const int slot = (kbase + k) % kHSlots;
+          cp_async_wait<kHAhead - 1>();
+          fence_async_smem();
+          mbar_arrive(&full[slot]);
+          if (k + kHAhead < n_tiles) gather(k + kHAhead);
+          cp_async_commit();
+          if (k + kHAhead < n_tiles) build_b(k + kHAhead);
+        }
+        cp_async_wait<0>();
       }
     } else if (is_issuer) {
       // ---- every MMA of the tile phase, in the order the operands become ready

@@ -1350,6 +1350,8 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
           if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rth attribute setup failed: %s", cudaGetErrorString(ea));
           const char* cps = getenv("SRS_DIN_RTH_CTAS");
           m->din_rt.ctas_per_sm = (cps && atoi(cps) == 2) ? 2 : 1;
+          const char* bg = getenv("SRS_DIN_RTH_BG");        // builder warp gathers too
+          m->din_rt.nch = (bg && atoi(bg) == 1) ? 1 : 0;
           m->use_din_rt = false; m->use_din_rth = true; m->kernel_name = "din_rth_kernel";
         }
       }

@@ -524,10 +524,10 @@ def test_deepfm_tensor_core_kernel(E, B, monkeypatch):
 # (under `timeout`: a wrong mbarrier phase shows up as a hang, which pytest cannot interrupt).
 @pytest.mark.skipif(not __import__("os").environ.get("SRS_TEST_RTH"),
                     reason="din_rth_kernel is opt-in (SRS_TEST_RTH=1) until it has run on a GPU")
-@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("ctas,bg", [(1, 0), (2, 0), (1, 1), (2, 1)])
 @pytest.mark.parametrize("E,T,B", [(32, 50, 28), (32, 50, 4096), (32, 9, 100), (32, 31, 17), (32, 64, 333),
                                    (20, 33, 15), (32, 50, 2 * 148 * 32 + 77)])
-def test_din_rth_kernel(E, T, B, ctas, din_impl, monkeypatch):
+def test_din_rth_kernel(E, T, B, ctas, bg, din_impl, monkeypatch):
     spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=27279, n_users=5000)
     W = init_weights(spec, E * 1000 + T)
     feats = synthetic_features(spec, B, seed=T)
@@ -535,6 +535,7 @@ def test_din_rth_kernel(E, T, B, ctas, din_impl, monkeypatch):
     with _model(spec, W) as m:
         p_rt, z_rt = m.predict_with_logits(feats)
     monkeypatch.setenv("SRS_DIN_RTH_CTAS", str(ctas))
+    monkeypatch.setenv("SRS_DIN_RTH_BG", str(bg))              # 1: the builder warp gathers too
     din_impl("rth")
     with _model(spec, W) as m:
         assert m.kernel_name == "din_rth_kernel"

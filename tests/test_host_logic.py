@@ -233,3 +233,4 @@ def test_din_rth_barrier_protocol_model():
     for shape in ([1], [2], [14], [3, 3, 3], [16, 1, 5, 16]):
         for seed in range(8):
             sim.Sim(shape, seed).run()
+            sim.Sim(shape, seed, builder_gathers=True).run()
