@@ -3,7 +3,7 @@
 # shown timeouts: the rth kernel has never run and a protocol error there is a hang).
 #
 # 1. the experimental half-SM DIN kernel against the oracle and against din_rt (14 cases)
-#    SRS_TEST_RTH=1 timeout 150 python -m pytest tests/test_gpu_parity.py -k "rth and 0-" -x -q   # plain mode first
+#    SRS_TEST_RTH=1 timeout 150 python -m pytest tests/test_gpu_parity.py -k "rth and plain" -x -q   # plain mode first
 #    SRS_TEST_RTH=1 timeout 150 python -m pytest tests/test_gpu_parity.py -k rth -x -q              # + SRS_DIN_RTH_BG=1
 # 2. if green: its two co-residency modes against the current default, same box
 #    for m in "" "SRS_DIN_IMPL=rth" "SRS_DIN_IMPL=rth SRS_DIN_RTH_CTAS=2" "SRS_DIN_IMPL=rth SRS_DIN_RTH_BG=1"; do

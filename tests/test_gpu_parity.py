@@ -524,7 +524,8 @@ def test_deepfm_tensor_core_kernel(E, B, monkeypatch):
 # (under `timeout`: a wrong mbarrier phase shows up as a hang, which pytest cannot interrupt).
 @pytest.mark.skipif(not __import__("os").environ.get("SRS_TEST_RTH"),
                     reason="din_rth_kernel is opt-in (SRS_TEST_RTH=1) until it has run on a GPU")
-@pytest.mark.parametrize("ctas,bg", [(1, 0), (2, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("ctas,bg", [(1, 0), (2, 0), (1, 1), (2, 1)],
+                         ids=["plain1", "plain2", "buildergathers1", "buildergathers2"])
 @pytest.mark.parametrize("E,T,B", [(32, 50, 28), (32, 50, 4096), (32, 9, 100), (32, 31, 17), (32, 64, 333),
                                    (20, 33, 15), (32, 50, 2 * 148 * 32 + 77)])
 def test_din_rth_kernel(E, T, B, ctas, bg, din_impl, monkeypatch):
