@@ -14,7 +14,9 @@ from sparrowrecsys_b200.weights import init_weights
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 spec = baseline_spec("cfg3_din")
 m = CTRModel(spec, init_weights(spec, 2), 0)
-assert m.kernel_name in ("din_rt_kernel", "din_rth_kernel"), m.kernel_name   # SRS_DIN_IMPL=rth: the half-SM kernel
+assert m.kernel_name in ("din_rt_kernel", "din_rth_kernel", "din_rtp_kernel"), m.kernel_name   # SRS_DIN_IMPL=rth / rtp
+if len(sys.argv) > 2:
+    m.set_sm_limit(int(sys.argv[2]))
 db = m.to_device(synthetic_features(spec, B, seed=1))
 out = torch.empty(B, dtype=torch.float32, device="cuda:0")
 lib = _lib.load()
@@ -25,13 +27,16 @@ lib.srs_debug_din_trace(m._h, 1, None)
 buf = (C.c_uint64 * 40)()
 names = {0: "entry", 1: "prologue", 2: "phase0", 3: "first_d1_ready", 4: "first_tile_pooled", 5: "tiles_done",
          6: "layer1", 7: "group", 8: "exit"}
+if m.kernel_name == "din_rtp_kernel":   # slots: 3/10 first d1 of consumer 0/1, 4/11 consumers done, 5 first pooled group at the top MLP,
+    names = {0: "entry", 1: "prologue", 20: "first_gather_issued", 3: "c0_first_d1", 10: "c1_first_d1", 5: "top_group0_pooled_ready",
+             6: "top_group0_layer1", 7: "top_group0_done", 4: "c0_done", 11: "c1_done", 8: "exit"}
 for rep in range(3):
     m.predict_device(db, out)
     _lib.check(lib.srs_debug_din_trace(m._h, 1, buf))
     t = np.array(buf[:], dtype=np.int64)
     prev = t[0]
     line = []
-    for i in sorted(names):
+    for i in sorted(names, key=lambda i: t[i]):
         if t[i] == 0:
             continue
         line.append("%s=%d(+%d)" % (names[i], t[i] - t[0], t[i] - prev))

@@ -70,7 +70,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("CUDA build failed")
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs])
+    tmp = LIB + ".tmp%d" % os.getpid()                   # link aside, then rename: a reader (or a gpurun
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", tmp, *objs])   # snapshot) never sees a half-written library
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -28,7 +28,6 @@ constexpr int k64Slots = 4;
 constexpr int k64Ahead = 2;                 // tiles in flight ahead of the one being delivered
 constexpr int k64GatherThreads = 160;       // warps 0-3 and 7
 constexpr int k64Copies = 13;               // ceil(128 positions * 16 chunks / 160)
-constexpr int kNoCopy = INT_MIN;            // id sentinel: this copy does not exist
 
 // ring slot: A hi [128 positions][64 bf16] SW128 (16 KB) | A lo (16 KB) | B [32 hi | 32 lo units][64 k] SW128 (8 KB)
 constexpr uint32_t S64_ALO = 16384, S64_B = 32768, S64_SLOT = 40960;
@@ -219,17 +218,18 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
 #pragma unroll
         for (int n = 0; n < k64Copies; ++n) {
           const int cell = cell0 + 10 * n;
-          ids[n] = cell < valid ? __ldg(h + cell) : kNoCopy;
+          ids[n] = cell < valid ? __ldg(h + cell) : 0;       // liveness is decided from the cell index, never from the id value
         }
       };
       auto gather = [&](int k, const int (&ids)[k64Copies]) {
         const int K = kbase + k, slot = K % k64Slots;
         if (K >= k64Slots) mbar_wait(&empty[slot], ((K / k64Slots) + 1) & 1);
         uint8_t* A = ring + slot * S64_SLOT + g_part;
+        const int valid = min(128, T - 128 * (NCH == 2 ? (k & 1) : 0));     // gather() is only called for live tiles
 #pragma unroll
         for (int n = 0; n < k64Copies; ++n) {
           const int cell = cell0 + 10 * n;
-          if (ids[n] != kNoCopy) {
+          if (cell < valid) {
             const int id = checked_id(rt_f32_roundtrip_id(ids[n]), p.n_movies, b.err_flag);
             cp_async16(A + cell * 128 + (((c16 & 7) ^ (cell & 7)) << 4), p.movie_split + (size_t)id * 256 + c16 * 16);
           }

@@ -22,6 +22,7 @@ cudaError_t setup_dien_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_din_rt_attributes();
 cudaError_t setup_din_rth_attributes();
+cudaError_t setup_din_rtp_attributes();
 cudaError_t setup_din_rt64_attributes();
 cudaError_t setup_embmlp_tc_attributes();
 cudaError_t setup_deepfm_tc_attributes();
@@ -53,6 +54,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 4;           // public pipelining slots; slot kSlots is private to
                                     // the synchronous srs_predict_host
+constexpr int kErrWords = kSlots + 2;
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -74,7 +76,9 @@ struct srs_model {
   int EP = 0;
   int hist_cols = 0;                // history columns the model reads (T for DIN, 1 for W&D)
   std::vector<void*> owned;
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;          // kErrWords device words: [0] srs_predict_device, [1 + i] host slot i.  One word
+                                    // per slot: a flag shared by every slot could be copied by slot A, set by
+                                    // slot B's kernel and cleared by A's wait before B ever read it
   NcfParams ncf{};
   EmbMlpParams emb{};
   DeepFmParams fm{};
@@ -87,6 +91,7 @@ struct srs_model {
   bool use_din_rt = false;
   bool use_din_rt64 = false;         // din_rt holds the parameters of din_rt64_kernel
   bool use_din_rth = false;          // din_rt holds the parameters; the half-SM kernel runs them
+  bool use_din_rtp = false;          // din_rt holds the parameters; the pipelined row-tile kernel runs them
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
   DeepFmTcParams fm_tc{};
@@ -99,6 +104,11 @@ struct srs_model {
   Slot slots[kSlots + 1];
   std::mutex mu;
 };
+
+namespace {
+inline int* slot_err(srs_model* m, const Slot& s) { return m->err_flag + 1 + (&s - m->slots); }
+}  // namespace
+
 
 namespace {
 
@@ -803,8 +813,53 @@ int build_din_rt(Builder& B) {
   std::vector<float> w1num(8 * 128, 0.f);
   for (int n = 0; n < 7; ++n)
     for (int j = 0; j < h0; ++j) w1num[(size_t)n * 128 + j] = k1[(size_t)nrows[n] * h0 + j];
+  // din_rtp: W1^T over K = [userId | pooled | candidate] as a tensor-memory A operand (lane = unit,
+  // one 32-bit column per pair of consecutive k: 48 hi words, then 48 lo words), and the two genre
+  // blocks of dense/kernel folded into fp32 tables G[genre][unit] = emb[genre] . rows (exact: 19 values)
+  std::vector<float> w1t_words((size_t)128 * 96, 0.f);
+  {
+    const int kstart[3] = {1 + E, 3 + 2 * E, 3 + 3 * E};
+    auto w1k = [&](int j, int k) -> float {
+      const int f = k >> 5, ee = k & 31;
+      if (j >= h0 || ee >= E) return 0.f;
+      return k1[(size_t)(kstart[f] + ee) * h0 + j];
+    };
+    uint32_t* words = reinterpret_cast<uint32_t*>(w1t_words.data());
+    for (int j = 0; j < 128; ++j)
+      for (int w = 0; w < 48; ++w) {
+        uint32_t hi = 0, lo = 0;
+        for (int half = 0; half < 2; ++half) {
+          const float x = w1k(j, 2 * w + half);
+          const uint16_t hb = bf16_rn_bits(x);
+          const uint16_t lb = bf16_rn_bits(x - u2f((uint32_t)hb << 16));
+          hi |= (uint32_t)hb << (16 * half);
+          lo |= (uint32_t)lb << (16 * half);
+        }
+        words[(size_t)j * 96 + w] = hi;
+        words[(size_t)j * 96 + 48 + w] = lo;
+      }
+  }
+  std::vector<float> gtab_u((size_t)s.n_genres * 128, 0.f), gtab_m((size_t)s.n_genres * 128, 0.f);
+  {
+    const float* ug = B.host("userGenre1_embedding", s.n_genres, E);
+    const float* mg = B.host("movieGenre1_embedding", s.n_genres, E);
+    if (B.status != SRS_OK) return B.status;
+    for (int g = 0; g < s.n_genres; ++g)
+      for (int j = 0; j < h0; ++j) {
+        double su = 0.0, sm = 0.0;
+        for (int ee = 0; ee < E; ++ee) {
+          su += (double)ug[(size_t)g * E + ee] * (double)k1[(size_t)(1 + ee) * h0 + j];
+          sm += (double)mg[(size_t)g * E + ee] * (double)k1[(size_t)(base + 1 + ee) * h0 + j];
+        }
+        gtab_u[(size_t)g * 128 + j] = (float)su;
+        gtab_m[(size_t)g * 128 + j] = (float)sm;
+      }
+  }
   DinRtParams& p = m->din_rt;
   const DinParams& v1 = m->din;                 // tables / vectors uploaded by build_din
+  p.w1_tmem = reinterpret_cast<const uint32_t*>(B.upload(w1t_words));
+  p.gtab_u = B.upload(gtab_u);
+  p.gtab_m = B.upload(gtab_m);
   // history rows: [n_movies][32 bf16 hi | 32 bf16 lo]
   void* d_split = nullptr;
   const size_t split_bytes = (size_t)s.n_movies * 128;
@@ -1056,6 +1111,7 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_DIN:
       e = m->use_din_rt64 ? launch_din_rt64(m->din_rt, v, stream)
           : m->use_din_rth ? launch_din_rth(m->din_rt, v, stream)
+          : m->use_din_rtp ? launch_din_rtp(m->din_rt, v, stream)
           : m->use_din_rt ? launch_din_rt(m->din_rt, v, stream)
           : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
                           : launch_din(m->din, v, stream);
@@ -1171,7 +1227,7 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
   v.probs = probs_out ? probs_out : s.d_probs;
-  v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = m->err_flag;
+  v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = slot_err(m, s);
   return launch(m, v, s.stream);
 }
 
@@ -1196,7 +1252,7 @@ int enqueue_host(srs_model* m, Slot& s, const srs_batch* b, float* probs, float*
   if (!direct) CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (logits) CUDA_TRY(cudaMemcpyAsync(logits, s.d_logits, B * 4, cudaMemcpyDeviceToHost, s.stream));
   if (copy_err)
-    CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   return SRS_OK;
 }
 
@@ -1206,7 +1262,7 @@ int wait_slot(srs_model* m, Slot& s) {
   CUDA_TRY(cudaStreamSynchronize(s.stream));
   if (s.h_err && *s.h_err) {
     *s.h_err = 0;
-    CUDA_TRY(cudaMemsetAsync(m->err_flag, 0, sizeof(int), s.stream));
+    CUDA_TRY(cudaMemsetAsync(slot_err(m, s), 0, sizeof(int), s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return fail(SRS_ERR_RANGE, "an id in the batch is outside its vocabulary");
   }
@@ -1332,6 +1388,12 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
           rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rth needs 16 < emb_dim <= 32 and hist_len <= 64");
         want_rt = true; want_tc = false;
       }
+      const bool want_rtp = impl && !strcmp(impl, "rtp");       // pipelined row-tile kernel (din_rtp.cu)
+      if (want_rtp) {
+        if (!fits_rt32 && rc == SRS_OK)
+          rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rtp needs 16 < emb_dim <= 32 and hist_len <= 64");
+        want_rt = true; want_tc = false;
+      }
       if (impl && !strcmp(impl, "rt")) {
         if (!fits_rt && rc == SRS_OK)
           rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rt needs 16 < emb_dim <= 32 and hist_len <= 64, or 32 < emb_dim <= 64 and hist_len <= 256");
@@ -1354,6 +1416,11 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
           m->din_rt.nch = (bg && atoi(bg) == 1) ? 1 : 0;
           m->use_din_rt = false; m->use_din_rth = true; m->kernel_name = "din_rth_kernel";
         }
+        if (rc == SRS_OK && want_rtp) {
+          cudaError_t ea = setup_din_rtp_attributes();
+          if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rtp attribute setup failed: %s", cudaGetErrorString(ea));
+          m->use_din_rt = false; m->use_din_rtp = true; m->kernel_name = "din_rtp_kernel";
+        }
       }
       if (rc == SRS_OK && want_rt && fits_rt64) {
         rc = build_din_rt64(B);
@@ -1363,8 +1430,8 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     }
   }
   if (rc == SRS_OK) {
-    e = cudaMalloc(&m->err_flag, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(m->err_flag, 0, sizeof(int));
+    e = cudaMalloc(&m->err_flag, kErrWords * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->err_flag, 0, kErrWords * sizeof(int));
     if (e != cudaSuccess) rc = fail(SRS_ERR_CUDA, "error-flag allocation failed: %s", cudaGetErrorString(e));
   }
   if (rc == SRS_OK) {
@@ -1439,10 +1506,12 @@ int srs_predict_host_batches(srs_model* m, int32_t n, const srs_batch* batches,
         rc = fail(SRS_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }
   if (rc != SRS_OK) return rc;
-  int flag = 0;
-  CUDA_TRY(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+  int flags[kSlots] = {0};
+  CUDA_TRY(cudaMemcpy(flags, m->err_flag + 1, kSlots * sizeof(int), cudaMemcpyDeviceToHost));
+  bool any = false;
+  for (int k = 0; k < kSlots; ++k) any = any || flags[k] != 0;
+  if (any) {
+    CUDA_TRY(cudaMemset(m->err_flag + 1, 0, kSlots * sizeof(int)));
     return fail(SRS_ERR_RANGE, "an id in a batch was outside its vocabulary");
   }
   return SRS_OK;
@@ -1467,10 +1536,12 @@ int srs_model_status(srs_model* m) {
   if (!m) return fail(SRS_ERR_INVALID, "null model");
   CUDA_TRY(cudaSetDevice(m->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  int flag = 0;
-  CUDA_TRY(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+  int flags[kErrWords] = {0};
+  CUDA_TRY(cudaMemcpy(flags, m->err_flag, kErrWords * sizeof(int), cudaMemcpyDeviceToHost));
+  bool any = false;
+  for (int k = 0; k < kErrWords; ++k) any = any || flags[k] != 0;
+  if (any) {
+    CUDA_TRY(cudaMemset(m->err_flag, 0, kErrWords * sizeof(int)));
     return fail(SRS_ERR_RANGE, "an id in a batch was outside its vocabulary");
   }
   return SRS_OK;
@@ -1555,7 +1626,7 @@ int srs_rank_host(srs_model* m, const srs_batch* b, int32_t k, int32_t* top_idx,
   CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
   if (top_scores)
     CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.h_err, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   return wait_slot(m, s);
 }
 
@@ -1567,6 +1638,7 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   if (out40) {
     CUDA_TRY(cudaDeviceSynchronize());
     if (m->use_din_rth) CUDA_TRY(read_din_rth_trace(reinterpret_cast<unsigned long long*>(out40)));
+    else if (m->use_din_rtp) CUDA_TRY(read_din_rtp_trace(reinterpret_cast<unsigned long long*>(out40)));
     else if (m->use_din_rt) CUDA_TRY(read_din_rt_trace(reinterpret_cast<unsigned long long*>(out40)));
     else CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
   }

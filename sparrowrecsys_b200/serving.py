@@ -111,23 +111,28 @@ class MicroBatcher:
         self._q: "queue.Queue" = queue.Queue()
         self._held = None                 # a request taken off the queue that did not fit
         self._stop = False
+        self._gate = threading.Lock()     # orders submit's enqueue against close's sentinel
         self._thread = threading.Thread(target=self._run, name="srs-microbatcher", daemon=True)
         self._thread.start()
 
     def submit(self, feats: Dict[str, np.ndarray]) -> np.ndarray:
-        if self._stop:
-            raise RuntimeError("batcher is closed")
         item = {"feats": feats, "n": len(next(iter(feats.values()))), "done": threading.Event(),
                 "out": None, "err": None}
-        self._q.put(item)
-        item["done"].wait()
+        with self._gate:                  # either the request is queued before the close sentinel
+            if self._stop:                # (the dispatcher drains it), or it sees the closed flag
+                raise RuntimeError("batcher is closed")
+            self._q.put(item)
+        while not item["done"].wait(timeout=1.0):
+            if not self._thread.is_alive():      # dispatcher gone without completing this request
+                raise RuntimeError("batcher is closed")
         if item["err"] is not None:
             raise item["err"]
         return item["out"]
 
     def close(self):
-        self._stop = True
-        self._q.put(None)
+        with self._gate:
+            self._stop = True
+            self._q.put(None)
         self._thread.join(timeout=5)
 
     # ---- dispatcher thread ----------------------------------------------------------------
@@ -230,6 +235,9 @@ def make_handler(models: Mapping[str, tuple], lock: threading.Lock, store=None,
             try:
                 n = int(self.headers.get("Content-Length", "0"))
                 req = json.loads(self.rfile.read(n) or b"{}")
+                if not isinstance(req, dict):
+                    return self._send(400, {"error": "the request body must be a JSON object with "
+                                                     "\"instances\" or \"inputs\""})
                 columnar = "instances" not in req and "inputs" in req
                 feats = instances_to_features(
                     spec, inputs_to_instances(req["inputs"]) if columnar else req.get("instances"), store)
@@ -242,6 +250,8 @@ def make_handler(models: Mapping[str, tuple], lock: threading.Lock, store=None,
                 self._send(200, {"outputs": scores} if columnar else {"predictions": scores})
             except (ValueError, KeyError, TypeError, json.JSONDecodeError) as e:
                 self._send(400, {"error": str(e)})
+            except Exception as e:               # library / CUDA failure, closed batcher: TF-Serving answers
+                self._send(500, {"error": "%s: %s" % (type(e).__name__, e)})   # every failure with a JSON error
 
         def do_GET(self):
             m = re.match(r"^/v1/models/([^/:]+)$", self.path)

@@ -548,3 +548,45 @@ def test_din_rth_kernel(E, T, B, ctas, bg, din_impl, monkeypatch):
     assert np.abs(z - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z - zo).max()
     assert np.abs(p - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p - po).max()
     assert np.abs(p - p_rt).max() <= 2 * PROB_ATOL
+
+
+# ---- pipelined row-tile kernel (csrc/din_rtp.cu) ----------------------------------------------
+# Every role is a persistent loop over the CTA's row groups; the SM limit decides how many groups a
+# CTA walks (1 SM: every group of the batch on one CTA - staging by the loader warp, both staging
+# buffers, pooled-buffer reuse, odd last tiles, one-tile groups all get exercised).
+@pytest.mark.parametrize("E,T,B,sms", [(32, 50, 28, 0), (32, 50, 4096, 0), (32, 50, 4096, 74), (32, 50, 4096, 37),
+                                       (32, 50, 1500, 3), (32, 9, 100, 1), (32, 31, 17, 0), (32, 64, 333, 2),
+                                       (20, 33, 15, 0), (32, 50, 2 * 148 * 32 + 77, 0), (32, 50, 1, 0),
+                                       (32, 50, 223, 1), (24, 17, 2, 0), (32, 50, 9000, 148)])
+def test_din_rtp_kernel(E, T, B, sms, din_impl):
+    spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=27279, n_users=5000)
+    W = init_weights(spec, E * 1000 + T)
+    feats = synthetic_features(spec, B, seed=T + B)
+    din_impl("rtp")
+    with _model(spec, W) as m:
+        assert m.kernel_name == "din_rtp_kernel"
+        if sms:
+            m.set_sm_limit(sms)
+        p, z = m.predict_with_logits(feats)
+        assert np.array_equal(m.predict(feats), p)                 # deterministic
+        m.set_sm_limit(5)                                          # results do not depend on the grid
+        assert np.array_equal(m.predict(feats), p)
+    po, zo = O.forward(spec, W, feats)
+    assert np.abs(z - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z - zo).max()
+    assert np.abs(p - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p - po).max()
+
+
+def test_din_rtp_out_of_range_ids_latch_the_error_flag(din_impl):
+    from sparrowrecsys_b200._lib import SrsError
+    spec = default_spec("din", emb_dim=32, hist_len=50, n_movies=27279, n_users=5000)
+    W = init_weights(spec, 1)
+    feats = synthetic_features(spec, 300, seed=3)
+    din_impl("rtp")
+    with _model(spec, W) as m:
+        d = m.to_device(feats)
+        import torch
+        d.hist[17, 3] = spec.n_movies + 5                          # device path: no host pre-validation
+        out = torch.empty(300, dtype=torch.float32, device="cuda:0")
+        m.predict_device(d, out)
+        with pytest.raises((SrsError, ValueError)):
+            m.status()

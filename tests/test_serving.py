@@ -218,3 +218,48 @@ def test_concurrent_http_requests_share_library_calls():
         srv.shutdown()
         srv.server_close()
     assert not mb._thread.is_alive()                          # dispatcher stopped with the server
+
+
+def test_http_front_answers_every_failure_with_a_json_error():
+    """TF-Serving answers every failure with {"error": ...} (HttpClient.java:32-40 reads the body):
+    a library failure is a 500, a non-object body a 400 - never a dropped connection."""
+    import json
+    import threading
+    import urllib.error
+    import urllib.request
+    from sparrowrecsys_b200 import serving
+    from sparrowrecsys_b200.spec import default_spec
+
+    def broken(feats):
+        raise RuntimeError("CUDA went away")
+
+    srv = serving.serve({"recmodel": (default_spec("neuralcf"), broken)}, port=0, micro_batch=True)
+    port = srv.server_address[1]
+    th = threading.Thread(target=srv.serve_forever, daemon=True)
+    th.start()
+    try:
+        def post(body):
+            req = urllib.request.Request("http://127.0.0.1:%d/v1/models/recmodel:predict" % port, data=body,
+                                         headers={"Content-Type": "application/json"})
+            try:
+                with urllib.request.urlopen(req, timeout=10) as r:
+                    return r.status, json.loads(r.read())
+            except urllib.error.HTTPError as e:
+                return e.code, json.loads(e.read())
+        code, body = post(json.dumps({"instances": [{"userId": 1, "movieId": 2}]}).encode())
+        assert code == 500 and "CUDA went away" in body["error"]
+        code, body = post(b"[1, 2, 3]")
+        assert code == 400 and "error" in body
+    finally:
+        srv.shutdown()
+        srv.server_close()
+
+
+def test_micro_batcher_submit_after_close_raises_instead_of_hanging():
+    import pytest as _pt
+    from sparrowrecsys_b200.serving import MicroBatcher
+    mb = MicroBatcher(lambda f: np.zeros((len(f["movieId"]), 1), np.float32))
+    assert mb.submit({"movieId": np.arange(3)}).shape == (3, 1)
+    mb.close()
+    with _pt.raises(RuntimeError):
+        mb.submit({"movieId": np.arange(3)})
