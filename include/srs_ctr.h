@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRS_ABI_VERSION 2
+#define SRS_ABI_VERSION 3
 
 enum srs_status {
   SRS_OK = 0,
@@ -141,6 +141,30 @@ void srs_model_destroy(srs_model* m);
  * srs_model_status() reports. */
 int srs_predict_device(srs_model* m, const srs_batch* batch, float* probs, float* logits,
                        void* stream);
+
+/* ---- One ranking call that spans the GPUs of a box (RecForYouProcess.java:56-59,92-94 with the
+ * candidate list sharded by rows): every rank needs every rank's scores.
+ * Instead of kernel + all-gather, each rank's forward kernel stores its scores into its slice of
+ * EVERY rank's gather buffer over NVLink (CUDA IPC peer mappings), followed by one flag word per
+ * rank.  One process per GPU; `slice_rows` = rows per rank (the last rank may score fewer).
+ *   1. every rank: srs_gather_create, srs_gather_export -> 64-byte handle
+ *   2. exchange the handles (torch.distributed / MPI / a pipe), every rank: srs_gather_connect with
+ *      the world x 64 bytes in rank order
+ *   3. per call: srs_predict_device_gather (asynchronous on `stream`), then srs_gather_wait on the
+ *      stream that consumes the scores, then srs_gather_scores for the device pointer of the full
+ *      [world * slice_rows] vector (valid until the call after the next one: two buffers alternate).
+ * Every rank must make the same sequence of calls.  Not capturable in a CUDA graph (the step
+ * counter is a kernel argument). */
+typedef struct srs_gather srs_gather;
+int srs_gather_create(int32_t device, int32_t world, int32_t rank, int64_t slice_rows, srs_gather** out);
+int srs_gather_export(srs_gather* g, void* handle64);
+int srs_gather_connect(srs_gather* g, const void* handles /* world * 64 bytes, rank order */);
+void srs_gather_destroy(srs_gather* g);
+int srs_predict_device_gather(srs_model* m, const srs_batch* batch, srs_gather* g, void* stream);
+int srs_gather_wait(srs_gather* g, void* stream);
+int srs_gather_scores(srs_gather* g, float** scores, int64_t* rows);
+/* copy the gathered vector of the latest call to `dst` (device or host memory), asynchronous on `stream` */
+int srs_gather_copy_scores(srs_gather* g, float* dst, int32_t dst_on_host, void* stream);
 
 /* Forward pass from host buffers: H2D of the batch, kernel, D2H of the scores,
  * synchronous.  This is the drop-in for `model.predict(dict) -> float32[B,1]`

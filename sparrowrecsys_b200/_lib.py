@@ -14,7 +14,7 @@ SRS_OK = 0
 SRS_ERR_INVALID, SRS_ERR_MISSING, SRS_ERR_SHAPE = -1, -2, -3
 SRS_ERR_CUDA, SRS_ERR_RANGE, SRS_ERR_NOMEM = -4, -5, -6
 SRS_HOST, SRS_DEVICE_BORROWED = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SrsSpec(C.Structure):
@@ -39,7 +39,9 @@ EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_d
            "srs_predict_device", "srs_predict_host", "srs_predict_host_batches", "srs_num_slots", "srs_predict_host_async",
            "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
            "srs_model_kernel_name", "srs_model_set_sm_limit", "srs_launch_count", "srs_fill_uniform",
-           "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
+           "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_gather_create", "srs_gather_export",
+           "srs_gather_connect", "srs_gather_destroy", "srs_predict_device_gather", "srs_gather_wait",
+           "srs_gather_scores", "srs_gather_copy_scores", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
 
 _lib = None
 
@@ -107,6 +109,22 @@ def load():
     lib.srs_rank_host.restype = C.c_int
     lib.srs_rank_host.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_int32, C.c_void_p,
                                   C.c_void_p]
+    lib.srs_gather_create.restype = C.c_int
+    lib.srs_gather_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.srs_gather_export.restype = C.c_int
+    lib.srs_gather_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.srs_gather_connect.restype = C.c_int
+    lib.srs_gather_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.srs_gather_destroy.restype = None
+    lib.srs_gather_destroy.argtypes = [C.c_void_p]
+    lib.srs_predict_device_gather.restype = C.c_int
+    lib.srs_predict_device_gather.argtypes = [C.c_void_p, C.POINTER(SrsBatch), C.c_void_p, C.c_void_p]
+    lib.srs_gather_wait.restype = C.c_int
+    lib.srs_gather_wait.argtypes = [C.c_void_p, C.c_void_p]
+    lib.srs_gather_scores.restype = C.c_int
+    lib.srs_gather_scores.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.srs_gather_copy_scores.restype = C.c_int
+    lib.srs_gather_copy_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.srs_debug_din_trace.restype = C.c_int
     lib.srs_debug_din_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.srs_debug_umma_bench.restype = C.c_int

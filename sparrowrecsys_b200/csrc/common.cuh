@@ -33,7 +33,40 @@ struct BatchView {
   float* probs;                 // [B]
   float* logits;                // [B] or nullptr
   int* err_flag;                // latched when an id is out of range
+  // ---- score exchange of a ranking call that spans GPUs (gather.cu; all zero otherwise) ----------
+  // `probs` is then this rank's slice of its own gather buffer and peer_probs[k] the same slice of
+  // the other ranks' buffers (peer memory over NVLink): the epilogue stores each score N times and
+  // no collective follows.  Kernels that end with gather_signal_tail() also publish the step number
+  // to every rank's flag word once their last CTA has finished.
+  float* peer_probs[7];
+  int n_peers;
+  int n_sig;                    // ranks to signal (0: no in-kernel signal)
+  uint32_t sig_step;
+  uint32_t* sig_flags[8];       // flag word of THIS rank in every rank's flag array (own included)
+  unsigned int* sig_counter;    // local: CTAs of this launch that have finished
 };
+
+__device__ __forceinline__ void store_score(const BatchView& b, int row, float v) {
+  b.probs[row] = v;
+  for (int k = 0; k < b.n_peers; ++k) b.peer_probs[k][row] = v;
+}
+
+// Last statement of a kernel that supports the in-kernel signal (every thread calls it): when the
+// last CTA of the launch gets here, every score of this rank's slice has been stored - locally and
+// on the peers - and the step number goes out to the flag words the waiters poll.
+__device__ __forceinline__ void gather_signal_tail(const BatchView& b) {
+  if (b.n_sig == 0) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(b.sig_counter, 1u) + 1u;
+    if (done == gridDim.x) {
+      *b.sig_counter = 0u;
+      __threadfence_system();
+      for (int k = 0; k < b.n_sig; ++k) *reinterpret_cast<volatile uint32_t*>(b.sig_flags[k]) = b.sig_step;
+    }
+  }
+}
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) deepfm_kernel(DeepFmParams p, BatchV
 #pragma unroll
     for (int d = 0; d < 4; ++d) z = fmaf(Ds[r * 4 + d], p.wdot[d], z);
     z += s + p.bout;
-    b.probs[row] = sigmoidf_acc(z);
+    store_score(b, row, sigmoidf_acc(z));
     if (b.logits) b.logits[row] = z;
   });
 }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) deepfm2_kernel(DeepFm2Params p, Batc
     }
     const float z = warp_sum(part) + p.bout;
     if (lane == 0) {
-      b.probs[row] = sigmoidf_acc(z);
+      store_score(b, row, sigmoidf_acc(z));
       if (b.logits) b.logits[row] = z;
     }
   }

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) deepfm_tc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int d = 0; d < 4; ++d) z = fmaf(dots[tid * 4 + d], p.wdot[d], z);
         z += ((zp[tid] + zp[kFtRows + tid]) + (zp[2 * kFtRows + tid] + zp[3 * kFtRows + tid])) + p.bout;
-        b.probs[row] = sigmoidf_acc(z);
+        store_score(b, row, sigmoidf_acc(z));
         if (b.logits) b.logits[row] = z;
       }
     }

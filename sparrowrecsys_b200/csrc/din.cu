@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) din_kernel(DinParams p, BatchView b)
     const int row = row0 + r;
     if (row >= b.B) return;
     const float z = s + p.b3;
-    b.probs[row] = sigmoidf_acc(z);
+    store_score(b, row, sigmoidf_acc(z));
     if (b.logits) b.logits[row] = z;
   });
 }

@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
 #pragma unroll
         for (int pt = 0; pt < 16; ++pt) z += zp[pt * 32 + tid];
         if (tid < nrows) {
-          b.probs[row0 + tid] = sigmoidf_acc(z);
+          store_score(b, row0 + tid, sigmoidf_acc(z));
           if (b.logits) b.logits[row0 + tid] = z;
         }
       }
@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_slot, 512);
   RT_TRACE(8, tid == 0);
+  gather_signal_tail(b);                                  // spanning ranking call: publish "slice complete"
 }
 
 // fp32 table [rows][32] -> [rows][32 x bf16 hi | 32 x bf16 lo]

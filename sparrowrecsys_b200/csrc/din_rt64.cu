@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
 #pragma unroll
         for (int pt = 0; pt < 16; ++pt) z += zp[pt * 32 + tid];
         if (tid < nrows) {
-          b.probs[row0 + tid] = sigmoidf_acc(z);
+          store_score(b, row0 + tid, sigmoidf_acc(z));
           if (b.logits) b.logits[row0 + tid] = z;
         }
       }

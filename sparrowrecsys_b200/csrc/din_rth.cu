@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kHThreads, 2) din_rth_kernel(const __grid_cons
 #pragma unroll
         for (int pt = 0; pt < 8; ++pt) z += zp[pt * 32 + tid];
         if (tid < nrows) {
-          b.probs[row0 + tid] = sigmoidf_acc(z);
+          store_score(b, row0 + tid, sigmoidf_acc(z));
           if (b.logits) b.logits[row0 + tid] = z;
         }
       }

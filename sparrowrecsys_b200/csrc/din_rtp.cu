@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         if (tw < kPRows) {
           const float z = p.b3 + ((zp[tw] + zp[32 + tw]) + (zp[64 + tw] + zp[96 + tw]));
           if (tw < g.nrows) {
-            b.probs[g.row0 + tw] = sigmoidf_acc(z);
+            store_score(b, g.row0 + tw, sigmoidf_acc(z));
             if (b.logits) b.logits[g.row0 + tw] = z;
           }
         }
@@ -748,6 +748,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_slot, 512);
   RTP_TRACE(8, tid == 0);
+  gather_signal_tail(b);                                  // spanning ranking call: publish "slice complete"
 }
 
 cudaError_t read_din_rtp_trace(unsigned long long* out40) {

@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kTcWG * 128, 1) din_tc_kernel(const __grid_con
         for (int pt = 0; pt < 16; ++pt) z += zp[pt * 32 + tid];
         const int row = sg * kTcSG + tid;
         if (row < b.B) {
-          b.probs[row] = sigmoidf_acc(z);
+          store_score(b, row, sigmoidf_acc(z));
           if (b.logits) b.logits[row] = z;
         }
       }

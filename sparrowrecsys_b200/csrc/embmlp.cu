@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) embmlp_kernel(EmbMlpParams p, BatchV
                                    b.err_flag);
       z += __ldg(p.wide + crossed_bucket(mid, rated, (uint32_t)p.cross_buckets));
     }
-    b.probs[row] = sigmoidf_acc(z);
+    store_score(b, row, sigmoidf_acc(z));
     if (b.logits) b.logits[row] = z;
   });
 }

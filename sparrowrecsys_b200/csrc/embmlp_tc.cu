@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256, 1) embmlp_tc_kernel(const __grid_constant
           const int rated = checked_id(__ldg(b.hist + (size_t)row * b.hist_stride), p.n_movies, b.err_flag);
           z += __ldg(p.wide + crossed_bucket(mid, rated, (uint32_t)p.cross_buckets));
         }
-        b.probs[row] = sigmoidf_acc(z);
+        store_score(b, row, sigmoidf_acc(z));
         if (b.logits) b.logits[row] = z;
       }
     }

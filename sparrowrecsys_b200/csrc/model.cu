@@ -26,6 +26,21 @@ cudaError_t setup_din_rtp_attributes();
 cudaError_t setup_din_rt64_attributes();
 cudaError_t setup_embmlp_tc_attributes();
 cudaError_t setup_deepfm_tc_attributes();
+// gather.cu
+struct PeerGather;
+cudaError_t gather_create(int device, int world, int rank, int64_t slice_rows, PeerGather** out);
+cudaError_t gather_export(PeerGather* g, void* handle64);
+cudaError_t gather_connect(PeerGather* g, const void* handles);
+void gather_destroy(PeerGather* g);
+bool gather_connected(const PeerGather* g);
+int gather_begin_step(PeerGather* g, BatchView& v, bool in_kernel_signal);
+cudaError_t gather_signal(PeerGather* g, cudaStream_t s);
+cudaError_t gather_wait(PeerGather* g, cudaStream_t s);
+float* gather_buffer(PeerGather* g, int parity);
+int gather_parity(const PeerGather* g);
+int64_t gather_rows(const PeerGather* g);
+int gather_device(const PeerGather* g);
+int64_t gather_slice_rows(const PeerGather* g);
 }  // namespace srs
 
 using namespace srs;
@@ -1476,6 +1491,80 @@ int srs_predict_device(srs_model* m, const srs_batch* b, float* probs, float* lo
   v.movie_genre = b->movie_genre; v.user_genre = b->user_genre; v.numerics = b->numerics;
   v.probs = probs; v.logits = logits; v.err_flag = m->err_flag;
   return launch(m, v, static_cast<cudaStream_t>(stream));
+}
+
+// ---- score exchange over peer memory (gather.cu) -------------------------------------------------
+int srs_gather_create(int32_t device, int32_t world, int32_t rank, int64_t slice_rows, srs_gather** out) {
+  if (!out) return fail(SRS_ERR_INVALID, "null argument");
+  PeerGather* g = nullptr;
+  cudaError_t e = gather_create(device, world, rank, slice_rows, &g);
+  if (e == cudaErrorInvalidValue) return fail(SRS_ERR_INVALID, "need 1 <= world <= 8, 0 <= rank < world, slice_rows >= 1");
+  if (e != cudaSuccess) return fail(SRS_ERR_CUDA, "gather buffer allocation failed: %s", cudaGetErrorString(e));
+  *out = reinterpret_cast<srs_gather*>(g);
+  return SRS_OK;
+}
+
+int srs_gather_export(srs_gather* g, void* handle64) {
+  if (!g || !handle64) return fail(SRS_ERR_INVALID, "null argument");
+  CUDA_TRY(gather_export(reinterpret_cast<PeerGather*>(g), handle64));
+  return SRS_OK;
+}
+
+int srs_gather_connect(srs_gather* g, const void* handles) {
+  if (!g || !handles) return fail(SRS_ERR_INVALID, "null argument");
+  CUDA_TRY(gather_connect(reinterpret_cast<PeerGather*>(g), handles));
+  return SRS_OK;
+}
+
+void srs_gather_destroy(srs_gather* g) { gather_destroy(reinterpret_cast<PeerGather*>(g)); }
+
+int srs_predict_device_gather(srs_model* m, const srs_batch* b, srs_gather* gg, void* stream) {
+  int rc = check_batch(m, b);
+  if (rc != SRS_OK) return rc;
+  PeerGather* g = reinterpret_cast<PeerGather*>(gg);
+  if (!g) return fail(SRS_ERR_INVALID, "null gather object");
+  if (!gather_connected(g)) return fail(SRS_ERR_INVALID, "srs_gather_connect has not been called");
+  if (gather_device(g) != m->device) return fail(SRS_ERR_INVALID, "gather object lives on another device");
+  if (b->B < 1 || b->B > gather_slice_rows(g)) return fail(SRS_ERR_INVALID, "batch rows must be in 1..slice_rows");
+  if (m->hist_cols > 0 && !b->hist)
+    return fail(SRS_ERR_INVALID, "device batches carry int32 history ids (hist16 is for host batches)");
+  CUDA_TRY(cudaSetDevice(m->device));
+  BatchView v{};
+  v.B = b->B; v.hist_stride = b->hist_stride;
+  v.movie_id = b->movie_id; v.user_id = b->user_id; v.hist = b->hist;
+  v.movie_genre = b->movie_genre; v.user_genre = b->user_genre; v.numerics = b->numerics;
+  v.logits = nullptr; v.err_flag = m->err_flag;
+  const bool in_kernel = m->spec.kind == SRS_DIN && (m->use_din_rtp || m->use_din_rt) ;   // kernels ending in gather_signal_tail()
+  gather_begin_step(g, v, in_kernel);
+  rc = launch(m, v, static_cast<cudaStream_t>(stream));
+  if (rc != SRS_OK) return rc;
+  if (!in_kernel) CUDA_TRY(gather_signal(g, static_cast<cudaStream_t>(stream)));
+  return SRS_OK;
+}
+
+int srs_gather_wait(srs_gather* g, void* stream) {
+  if (!g) return fail(SRS_ERR_INVALID, "null gather object");
+  CUDA_TRY(cudaSetDevice(gather_device(reinterpret_cast<PeerGather*>(g))));
+  CUDA_TRY(gather_wait(reinterpret_cast<PeerGather*>(g), static_cast<cudaStream_t>(stream)));
+  return SRS_OK;
+}
+
+int srs_gather_scores(srs_gather* gg, float** scores, int64_t* rows) {
+  PeerGather* g = reinterpret_cast<PeerGather*>(gg);
+  if (!g || !scores) return fail(SRS_ERR_INVALID, "null argument");
+  *scores = gather_buffer(g, gather_parity(g));
+  if (rows) *rows = gather_rows(g);
+  return SRS_OK;
+}
+
+int srs_gather_copy_scores(srs_gather* gg, float* dst, int32_t dst_on_host, void* stream) {
+  PeerGather* g = reinterpret_cast<PeerGather*>(gg);
+  if (!g || !dst) return fail(SRS_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(gather_device(g)));
+  CUDA_TRY(cudaMemcpyAsync(dst, gather_buffer(g, gather_parity(g)), (size_t)gather_rows(g) * 4,
+                           dst_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  return SRS_OK;
 }
 
 int srs_predict_host(srs_model* m, const srs_batch* b, float* probs, float* logits) {

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) ncf_kernel(NcfParams p, BatchView b) {
     z = sw[p.out_b];
 #pragma unroll
     for (int j = 0; j < HP; ++j) z = fmaf(h[j], sw[p.out_w + j], z);
-    b.probs[row] = sigmoidf_acc(z);
+    store_score(b, row, sigmoidf_acc(z));
     if (b.logits) b.logits[row] = z;
   } else {
     float hi[HP], hu[HP];
@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(128) ncf_kernel(NcfParams p, BatchView b) {
     for (int j = 0; j < HP; ++j) d = fmaf(hi[j], hu[j], d);
     if (p.final_dense) {
       z = fmaf(d, sw[p.out_w], sw[p.out_b]);
-      b.probs[row] = sigmoidf_acc(z);
+      store_score(b, row, sigmoidf_acc(z));
     } else {
       z = d;                                   // shipped MLPRec/005: raw Dot output
-      b.probs[row] = d;
+      store_score(b, row, d);
     }
     if (b.logits) b.logits[row] = z;
   }

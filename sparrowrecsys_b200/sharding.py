@@ -104,3 +104,80 @@ def rank_sharded(rank_fn: Callable[[Dict[str, np.ndarray], int], tuple], feature
         merge_fn = topk_device
     idx, top = merge_fn(scores, size)
     return positions[idx.long()], top
+
+
+class FusedScoreGather:
+    """The score exchange of a ranking call that spans GPUs, fused into the forward kernel
+    (`include/srs_ctr.h`: srs_gather_*): every rank's kernel stores its scores into its slice of
+    every rank's gather buffer over NVLink (CUDA IPC peer mappings), one flag word per rank follows,
+    and `wait()` makes the consuming stream wait for all N slices.  Replaces
+    `srs_predict_device` + `all_gather_into_tensor` (the call site it serves:
+    RecForYouProcess.java:56-59,92-94 with the candidate list sharded by rows).
+
+    One process per GPU; `torch.distributed` only carries the 64-byte IPC handles at set-up."""
+
+    def __init__(self, model, slice_rows: int, device, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.model = model
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.slice_rows = int(slice_rows)
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        _lib.check(self._lib.srs_gather_create(self.device.index or 0, self.world, self.rank, self.slice_rows,
+                                               C.byref(h)))
+        self._h = h
+        mine = (C.c_uint8 * 64)()
+        _lib.check(self._lib.srs_gather_export(self._h, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        _lib.check(self._lib.srs_gather_connect(self._h, blob))
+        dist.barrier(group=group)
+
+    def describe(self) -> str:
+        return ("scores stored by the forward kernel's epilogue into every rank's gather buffer over NVLink "
+                "(CUDA IPC peer mappings, %d B per rank per launch to each of %d peers), one flag word per rank, "
+                "a one-warp wait kernel per launch; no collective" % (4 * self.slice_rows, self.world - 1))
+
+    def predict(self, batch_struct, stream_ptr=None, wait: bool = True):
+        """Forward pass of this rank's slice with the fused exchange; asynchronous on the stream."""
+        import ctypes as C
+        rc = self._lib.srs_predict_device_gather(self.model._h, C.byref(batch_struct), self._h, stream_ptr)
+        if rc != 0:
+            self._check(rc)
+        if wait:
+            self.wait(stream_ptr)
+
+    def wait(self, stream_ptr=None):
+        rc = self._lib.srs_gather_wait(self._h, stream_ptr)
+        if rc != 0:
+            self._check(rc)
+
+    def scores(self):
+        """The gathered [world * slice_rows] float32 scores of the latest call as a torch tensor
+        (copied out of the gather buffer on the current stream; call after `wait`)."""
+        import ctypes as C
+        import torch
+        ptr, rows = C.c_void_p(), C.c_int64()
+        self._check(self._lib.srs_gather_scores(self._h, C.byref(ptr), C.byref(rows)))
+        out = torch.empty(rows.value, dtype=torch.float32, device=self.device)
+        self._check(self._lib.srs_gather_copy_scores(self._h, out.data_ptr(), 0,
+                                                     torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.srs_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

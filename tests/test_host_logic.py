@@ -145,7 +145,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libsrs_ctr.so does not export %s" % name
     assert set(declared) == set(_lib.EXPORTS)
-    assert lib.srs_abi_version() == 2
+    assert lib.srs_abi_version() == _lib.ABI_VERSION == 3
     assert lib.srs_num_slots() >= 2
     assert lib.srs_launch_count() == 0
 
