@@ -247,6 +247,29 @@ int srs_topk_device(const float* scores, int32_t n, int32_t k, int32_t* top_idx,
 int srs_rank_host(srs_model* m, const srs_batch* batch, int32_t k, int32_t* top_idx,
                   float* top_scores);
 
+/* ---- One ranking request "one user x n candidates" with the movie-side features resident in HBM.
+ * The reference defines the serving feature store as Redis hashes `uf:<userId>` / `mf:<movieId>`
+ * (FeatureEngForRecModel.scala:130-174,208-259; read at RecForYouProcess.java:46-52 and
+ * DataManager.java:127-140).  srs_model_set_movie_features uploads the `mf:` side once: genres
+ * [n_movies][3] as vocabulary indices (-1 = missing), numerics [n_movies][4] = movieAvgRating,
+ * movieRatingCount, movieRatingStddev, releaseYear (already cast to float32).  A request then ships
+ * one srs_user_row and n candidate ids - (9 + T + n) words instead of n full feature rows - and a
+ * device kernel expands them into the batch the forward kernel reads (user columns broadcast, movie
+ * columns gathered by candidate id).  srs_rank_user_host = that + forward + sort-and-cut
+ * (RecForYouProcess.java:56-59), D2H of the best k positions / scores (and all n scores if
+ * `probs` != NULL).  Candidate ids outside the table or the model's vocabulary give SRS_ERR_RANGE. */
+typedef struct srs_user_row {
+  int32_t user_id;
+  int32_t user_genre[5];       /* userGenre1..5 vocabulary indices, -1 = missing                        */
+  float user_numerics[3];      /* userAvgRating, userRatingCount, userRatingStddev                      */
+  int32_t n_hist;              /* entries of `hist` (<= the model's history columns; the rest is id 0)  */
+  const int32_t* hist;         /* userRatedMovie1.. in graph position order (most recent first)         */
+} srs_user_row;
+int srs_model_set_movie_features(srs_model* m, int32_t n_movies, const int32_t* genres,
+                                 const float* numerics);
+int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* candidate_movie_ids,
+                       int32_t n, int32_t k, int32_t* top_idx, float* top_scores, float* probs);
+
 /* Debug aid for kernel tuning: enable/disable recording of per-phase SM-clock timestamps
  * in the tensor-core DIN kernels (CTA 0; slot meaning: profiles/trace_din_rt.py,
  * profiles/trace_din_tc.py) and, if out40 != NULL, synchronise and copy the 40 recorded values

@@ -41,9 +41,16 @@ EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_d
            "srs_model_kernel_name", "srs_model_set_sm_limit", "srs_launch_count", "srs_fill_uniform",
            "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_gather_create", "srs_gather_export",
            "srs_gather_connect", "srs_gather_destroy", "srs_predict_device_gather", "srs_gather_wait",
-           "srs_gather_scores", "srs_gather_copy_scores", "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
+           "srs_gather_scores", "srs_gather_copy_scores", "srs_model_set_movie_features", "srs_rank_user_host",
+           "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
 
 _lib = None
+
+
+class SrsUserRow(C.Structure):
+    """`srs_user_row` (include/srs_ctr.h): the typed `uf:<userId>` hash of one user."""
+    _fields_ = [("user_id", C.c_int32), ("user_genre", C.c_int32 * 5), ("user_numerics", C.c_float * 3),
+                ("n_hist", C.c_int32), ("hist", C.c_void_p)]
 
 
 class SrsError(RuntimeError):
@@ -125,6 +132,11 @@ def load():
     lib.srs_gather_scores.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.srs_gather_copy_scores.restype = C.c_int
     lib.srs_gather_copy_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.srs_model_set_movie_features.restype = C.c_int
+    lib.srs_model_set_movie_features.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.srs_rank_user_host.restype = C.c_int
+    lib.srs_rank_user_host.argtypes = [C.c_void_p, C.POINTER(SrsUserRow), C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
     lib.srs_debug_din_trace.restype = C.c_int
     lib.srs_debug_din_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.srs_debug_umma_bench.restype = C.c_int

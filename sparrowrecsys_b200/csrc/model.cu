@@ -81,6 +81,9 @@ struct Slot {
   int rank_capacity = 0;            // srs_rank_host only: rows d_rank can rank
   uint8_t* d_rank = nullptr;        // [top_idx cap | top_scores cap | sort scratch]
   int* h_err = nullptr;             // pinned mirror of the device error flag
+  int req_capacity = 0;             // srs_rank_user_host only: candidates the request staging holds
+  int32_t* d_req = nullptr;         // [user row | history | candidate ids] on the device
+  int32_t* h_req = nullptr;         // pinned copy of it
 };
 
 }  // namespace
@@ -114,6 +117,8 @@ struct srs_model {
   const char* kernel_name = "";
   bool zero_copy_scores = false;     // SRS_ZERO_COPY_SCORES=1 (experimental): kernels write the scores
                                      // of a host batch straight into the caller's pinned buffer
+  void* movie_feats = nullptr;       // srs_model_set_movie_features: [n][8 words] movie-side features in HBM
+  int movie_feats_rows = 0;
   int device_sms = 148;
   int64_t bytes_per_inf = 0;
   Slot slots[kSlots + 1];
@@ -1471,9 +1476,12 @@ void srs_model_destroy(srs_model* m) {
     cudaFree(s.d_block); cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_rank);
     cudaFree(s.d_hist32);
     if (s.h_err) cudaFreeHost(s.h_err);
+    if (s.h_req) cudaFreeHost(s.h_req);
+    cudaFree(s.d_req);
   }
   for (void* p : m->owned) cudaFree(p);
   if (m->err_flag) cudaFree(m->err_flag);
+  cudaFree(m->movie_feats);
   delete m;
 }
 
@@ -1715,6 +1723,106 @@ int srs_rank_host(srs_model* m, const srs_batch* b, int32_t k, int32_t* top_idx,
   CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
   if (top_scores)
     CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  return wait_slot(m, s);
+}
+
+int srs_model_set_movie_features(srs_model* m, int32_t n_movies, const int32_t* genres, const float* numerics) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (n_movies < 1 || !genres || !numerics) return fail(SRS_ERR_INVALID, "null or empty movie feature table");
+  std::lock_guard<std::mutex> lock(m->mu);
+  CUDA_TRY(cudaSetDevice(m->device));
+  std::vector<int32_t> packed((size_t)n_movies * 8, 0);
+  for (int i = 0; i < n_movies; ++i) {
+    for (int g = 0; g < 3; ++g) {
+      const int32_t v = genres[(size_t)i * 3 + g];
+      if (v >= m->spec.n_genres) return fail(SRS_ERR_RANGE, "movie %d: genre index %d outside the vocabulary", i, v);
+      packed[(size_t)i * 8 + g] = v < 0 ? -1 : v;
+    }
+    memcpy(&packed[(size_t)i * 8 + 3], numerics + (size_t)i * 4, 16);
+  }
+  cudaFree(m->movie_feats);
+  m->movie_feats = nullptr; m->movie_feats_rows = 0;
+  CUDA_TRY(cudaMalloc(&m->movie_feats, packed.size() * 4));
+  CUDA_TRY(cudaMemcpy(m->movie_feats, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  m->movie_feats_rows = n_movies;
+  return SRS_OK;
+}
+
+int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* cand, int32_t n, int32_t k,
+                       int32_t* top_idx, float* top_scores, float* probs) {
+  if (!m) return fail(SRS_ERR_INVALID, "null model");
+  if (!user || (n > 0 && !cand) || n < 0 || k < 0) return fail(SRS_ERR_INVALID, "bad argument");
+  const int kind = m->spec.kind;
+  const bool dense_feats = !(kind == SRS_NEURALCF || kind == SRS_TWOTOWERS);
+  if (dense_feats && !m->movie_feats)
+    return fail(SRS_ERR_INVALID, "this model reads movie features: call srs_model_set_movie_features first");
+  const int hc = m->hist_cols;
+  if (user->n_hist < 0 || user->n_hist > hc || (user->n_hist > 0 && !user->hist))
+    return fail(SRS_ERR_INVALID, "n_hist must be in 0..%d", hc);
+  std::lock_guard<std::mutex> lock(m->mu);
+  Slot& s = m->slots[kSlots];
+  CUDA_TRY(cudaSetDevice(m->device));
+  int rc = ensure_slot(m, s, n);
+  if (rc != SRS_OK) return rc;
+  if (n == 0) return SRS_OK;
+  if (k > n) k = n;
+  if (k > 0 && !top_idx) return fail(SRS_ERR_INVALID, "top_idx is null");
+  if (n > s.req_capacity || !s.d_req) {
+    cudaFree(s.d_req);
+    if (s.h_req) cudaFreeHost(s.h_req);
+    s.d_req = nullptr; s.h_req = nullptr; s.req_capacity = 0;
+    const size_t words = 16 + (size_t)hc + (size_t)s.capacity;
+    CUDA_TRY(cudaMalloc(&s.d_req, words * 4));
+    CUDA_TRY(cudaMallocHost(&s.h_req, words * 4));
+    s.req_capacity = s.capacity;
+  }
+  // request block: [userId | userGenre1..5 | 3 user numerics | hist[hc] | candidate ids[n]]
+  int32_t* h = s.h_req;
+  h[0] = user->user_id;
+  for (int g = 0; g < 5; ++g) h[1 + g] = user->user_genre[g] < 0 ? -1 : user->user_genre[g];
+  memcpy(h + 6, user->user_numerics, 12);
+  for (int t = 0; t < hc; ++t) h[9 + t] = t < user->n_hist ? user->hist[t] : 0;     // 0 = the padding id
+  memcpy(h + 9 + hc, cand, (size_t)n * 4);
+  const size_t req_words = 9 + (size_t)hc + (size_t)n;
+  CUDA_TRY(cudaMemcpyAsync(s.d_req, h, req_words * 4, cudaMemcpyHostToDevice, s.stream));
+  const PackedLayout L = packed_layout(m, (size_t)n);
+  uint8_t* d = s.d_block;
+  BatchView v{};
+  v.B = n; v.hist_stride = hc;
+  v.movie_id = reinterpret_cast<const int32_t*>(d + L.movie);
+  v.user_id = reinterpret_cast<const int32_t*>(d + L.user);
+  v.hist = reinterpret_cast<const int32_t*>(d + L.hist);
+  v.movie_genre = reinterpret_cast<const int32_t*>(d + L.mg);
+  v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
+  v.numerics = reinterpret_cast<const float*>(d + L.num);
+  v.probs = s.d_probs; v.logits = nullptr; v.err_flag = slot_err(m, s);
+  CUDA_TRY(launch_assemble_request(s.d_req, m->movie_feats, m->movie_feats_rows, n, hc, dense_feats ? 1 : 0,
+                                   reinterpret_cast<int32_t*>(d + L.movie), reinterpret_cast<int32_t*>(d + L.user),
+                                   reinterpret_cast<int32_t*>(d + L.hist), reinterpret_cast<int32_t*>(d + L.mg),
+                                   reinterpret_cast<int32_t*>(d + L.ug), reinterpret_cast<float*>(d + L.num),
+                                   slot_err(m, s), s.stream));
+  rc = launch(m, v, s.stream);
+  if (rc != SRS_OK) return rc;
+  if (probs) CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (k > 0) {
+    if (n > s.rank_capacity) {
+      cudaFree(s.d_rank);
+      s.d_rank = nullptr;
+      s.rank_capacity = 0;
+      const int cap = s.capacity;
+      CUDA_TRY(cudaMalloc(&s.d_rank, (size_t)cap * 8 + topk_scratch_bytes(cap) + 256));
+      s.rank_capacity = cap;
+    }
+    const size_t cap = (size_t)s.rank_capacity;
+    int32_t* d_idx = reinterpret_cast<int32_t*>(s.d_rank);
+    float* d_top = reinterpret_cast<float*>(s.d_rank + cap * 4);
+    void* scratch = s.d_rank + cap * 8;
+    CUDA_TRY(launch_topk(s.d_probs, n, k, d_idx, d_top, scratch, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (top_scores)
+      CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+  }
   CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   return wait_slot(m, s);
 }

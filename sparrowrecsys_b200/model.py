@@ -241,6 +241,54 @@ class CTRModel:
                                            top.ctypes.data))
         return idx, top
 
+    # ---- one user x n candidates, movie features resident in HBM ----------------------------
+    def set_movie_table(self, table):
+        """Upload the movie side of the serving feature store (`featurestore.MovieFeatureTable`,
+        i.e. the `mf:<movieId>` hashes of FeatureEngForRecModel.scala:130-174) to HBM once;
+        `rank_user` requests then carry only the user's row and the candidate ids."""
+        n = table.n_movies
+        genres = np.ascontiguousarray(np.stack([table.idx_cols[k] for k in
+                                                ("movieGenre1", "movieGenre2", "movieGenre3")], axis=1), np.int32)
+        nums = np.ascontiguousarray(np.stack([
+            table.float_cols["movieAvgRating"], table.int_cols["movieRatingCount"].astype(np.float32),
+            table.float_cols["movieRatingStddev"], table.int_cols["releaseYear"].astype(np.float32)], axis=1),
+            np.float32)
+        _lib.check(self._lib.srs_model_set_movie_features(self._h, n, genres.ctypes.data, nums.ctypes.data))
+
+    def rank_user(self, user_id: int, user_fields: Mapping[str, object], candidate_ids, size: int,
+                  return_scores: bool = False):
+        """`RecForYouProcess.getRecList` for one request (`:40-59`): `user_fields` is the user's
+        `uf:` hash (strings, as `FeatureStore.user_features` returns it, or already typed values
+        under the model input names), `candidate_ids` the n candidate movies.  Ships the user's
+        row and the ids only (`srs_rank_user_host`); the movie features are gathered on the
+        device from the table uploaded by `set_movie_table`.  Returns (positions int32 [k],
+        scores float32 [k]) best first (+ all n scores with `return_scores`)."""
+        from .featurestore import parse_user_features
+        from .features import genre_to_index
+        typed = parse_user_features(user_fields, max(self.hist_cols, 1))
+        cand = np.ascontiguousarray(np.asarray(candidate_ids, np.int32).reshape(-1))
+        n = cand.shape[0]
+        k = max(0, min(int(size), n))
+        hist = np.ascontiguousarray(np.array([typed["userRatedMovie%d" % (t + 1)] for t in range(self.hist_cols)],
+                                             np.int32))
+        row = _lib.SrsUserRow()
+        row.user_id = int(user_id)
+        for g in range(5):
+            v = typed["userGenre%d" % (g + 1)]
+            row.user_genre[g] = int(genre_to_index([v])[0]) if isinstance(v, (str, bytes)) else int(v)
+        row.user_numerics[0] = float(typed["userAvgRating"])
+        row.user_numerics[1] = float(np.float32(typed["userRatingCount"]))
+        row.user_numerics[2] = float(typed["userRatingStddev"])
+        row.n_hist = self.hist_cols
+        row.hist = hist.ctypes.data if self.hist_cols else None
+        idx = np.empty(k, np.int32)
+        top = np.empty(k, np.float32)
+        probs = np.empty(n, np.float32) if return_scores else None
+        _lib.check(self._lib.srs_rank_user_host(self._h, C.byref(row), cand.ctypes.data, n, k,
+                                                idx.ctypes.data if k else None, top.ctypes.data if k else None,
+                                                probs.ctypes.data if return_scores else None))
+        return (idx, top, probs) if return_scores else (idx, top)
+
     # ---- pipelined host path -----------------------------------------------------------
     def num_slots(self) -> int:
         return int(self._lib.srs_num_slots())

@@ -145,3 +145,40 @@ def test_encoded_assembly_is_the_same_batch(store, raw):
     mixed = np.array(["Drama", b"Action", "", "nope", None], dtype=object)
     assert genre_to_index(mixed).tolist() == [10, 1, -1, -1, -1]
     assert genre_to_index(np.array([b"IMAX", b"x"])).tolist() == [15, -1]
+
+
+# ---- the assembled path on the GPU: store -> (user row, candidate ids) -> device gather -> forward -> rank ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,kw", [("din", {}), ("din", {"emb_dim": 32, "hist_len": 50}), ("deepfm", {}),
+                                      ("widendeep", {}), ("embeddingmlp", {}), ("deepfm_v2", {}),
+                                      ("neuralcf", {}), ("dien", {})])
+def test_rank_user_with_device_resident_movie_features(store, raw, model, kw):
+    """f2 on the device: the request ships one `uf:` row and n candidate ids; the `mf:` side is a
+    table in HBM (srs_model_set_movie_features) gathered by a device kernel.  Scores must equal the
+    oracle on the host-assembled feature dict (FS.assemble: the same hashes, per candidate) and the
+    ranking must be the Java sort of those scores (RecForYouProcess.java:56-59)."""
+    from oracle import ctr_oracle as O
+    from sparrowrecsys_b200.model import CTRModel
+    from sparrowrecsys_b200.weights import init_weights
+    spec = default_spec(model, **kw)
+    W = init_weights(spec, 11)
+    table = FS.MovieFeatureTable.from_store(store, spec.n_movies)
+    movie_ids = np.array(store.movie_ids(), np.int32)
+    rng = np.random.default_rng(5)
+    T = spec.hist_len if model in ("din", "dien") else 5
+    with CTRModel(spec, W, device=0) as m:
+        m.set_movie_table(table)
+        for uid in [int(u) for u in list(dict.fromkeys(raw["userId"]))[:6]]:
+            n = int(rng.integers(1, 400))
+            cand = rng.choice(movie_ids, size=n, replace=True).astype(np.int32)
+            fields = store.user_features(uid)
+            feats = FS.assemble(uid, fields, cand, table, hist_len=T)
+            po, _ = O.forward(spec, W, feats)
+            idx, top, probs = m.rank_user(uid, fields, cand, 10, return_scores=True)
+            assert np.abs(probs - po[:, 0]).max() <= 2e-5, (model, uid)
+            assert np.array_equal(probs, m.predict(feats)[:, 0])            # same bits as the host-assembled call
+            ridx, rtop = O.rank_topk(probs, 10)
+            assert np.array_equal(idx, ridx) and np.array_equal(top, rtop)
+        # a candidate id the table does not hold -> the identity-column assert, as a range error
+        with pytest.raises(ValueError):
+            m.rank_user(1, store.user_features(1), np.array([spec.n_movies + 3], np.int32), 1)
