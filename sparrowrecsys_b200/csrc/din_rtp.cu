@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     cp_async_wait<0>();
     while (Dg < Kg) deliver_one();
   } else if (wg == 1) {
-    reg_inc<96>();
+    reg_inc<88>();                                         // 40 + 40 + 88 + 120 + 120 + 96 = 504 of the 512 per thread slot
     if (warp == 4) {
       // =================================== issuer ==========================================
       int NT = 0;

@@ -282,6 +282,10 @@ cudaError_t launch_assemble_request(const int32_t* req, const void* movie_feats,
 size_t topk_scratch_bytes(int n);
 cudaError_t launch_topk(const float* scores, int n, int k, int32_t* top_idx, float* top_scores,
                         void* scratch, cudaStream_t s);
+// latency path: the last kernel of the call publishes {seq, error word (cleared)} to a host-mapped record
+cudaError_t launch_topk_done(const float* scores, int n, int k, int32_t* top_idx, float* top_scores,
+                             void* scratch, int* err_flag, uint32_t* done, uint32_t seq, cudaStream_t s);
+cudaError_t launch_finish(int* err_flag, uint32_t* done, uint32_t seq, cudaStream_t s);
 
 // one-time per-device kernel attribute setup (dynamic shared memory opt-in)
 cudaError_t setup_kernel_attributes();

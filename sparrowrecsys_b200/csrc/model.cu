@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -81,6 +82,12 @@ struct Slot {
   int rank_capacity = 0;            // srs_rank_host only: rows d_rank can rank
   uint8_t* d_rank = nullptr;        // [top_idx cap | top_scores cap | sort scratch]
   int* h_err = nullptr;             // pinned mirror of the device error flag
+  // latency path (synchronous single calls): the last kernel of the call writes {sequence number, error
+  // word} into a pinned record the caller spins on - no device-to-host copy, no stream synchronise
+  uint32_t* h_done = nullptr;       // pinned [4]
+  uint32_t seq = 0;
+  int res_capacity = 0;
+  int32_t* h_res = nullptr;         // pinned: top positions [cap] | top scores [cap]
   int req_capacity = 0;             // srs_rank_user_host only: candidates the request staging holds
   int32_t* d_req = nullptr;         // [user row | history | candidate ids] on the device
   int32_t* h_req = nullptr;         // pinned copy of it
@@ -115,6 +122,7 @@ struct srs_model {
   DeepFmTcParams fm_tc{};
   bool use_fm_tc = false;
   const char* kernel_name = "";
+  bool no_zero_copy = false;         // SRS_ZERO_COPY_SCORES=0 switches the latency path of srs_predict_host off
   bool zero_copy_scores = false;     // SRS_ZERO_COPY_SCORES=1 (experimental): kernels write the scores
                                      // of a host batch straight into the caller's pinned buffer
   void* movie_feats = nullptr;       // srs_model_set_movie_features: [n][8 words] movie-side features in HBM
@@ -1189,7 +1197,7 @@ int ensure_slot(srs_model* m, Slot& s, int B) {
 // the scores are left in s.d_probs (and s.d_logits).
 // `probs_out`: where the kernel writes the scores (default: the slot's device buffer).
 int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits,
-                     float* probs_out = nullptr) {
+                     float* probs_out = nullptr, float* logits_out = nullptr) {
   int rc = check_batch(m, b);
   if (rc != SRS_OK) return rc;
   CUDA_TRY(cudaSetDevice(m->device));
@@ -1247,7 +1255,7 @@ int stage_and_launch(srs_model* m, Slot& s, const srs_batch* b, bool want_logits
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
   v.probs = probs_out ? probs_out : s.d_probs;
-  v.logits = want_logits ? s.d_logits : nullptr; v.err_flag = slot_err(m, s);
+  v.logits = want_logits ? (logits_out ? logits_out : s.d_logits) : nullptr; v.err_flag = slot_err(m, s);
   return launch(m, v, s.stream);
 }
 
@@ -1286,6 +1294,45 @@ int wait_slot(srs_model* m, Slot& s) {
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return fail(SRS_ERR_RANGE, "an id in the batch is outside its vocabulary");
   }
+  return SRS_OK;
+}
+
+int ensure_done(Slot& s, int k) {
+  if (!s.h_done) {
+    CUDA_TRY(cudaMallocHost(&s.h_done, 4 * sizeof(uint32_t)));
+    memset(s.h_done, 0, 4 * sizeof(uint32_t));
+  }
+  if (k > s.res_capacity) {
+    if (s.h_res) cudaFreeHost(s.h_res);
+    s.h_res = nullptr; s.res_capacity = 0;
+    const int cap = std::max(k, 1024);
+    CUDA_TRY(cudaMallocHost(&s.h_res, (size_t)cap * 8));
+    s.res_capacity = cap;
+  }
+  return SRS_OK;
+}
+
+// Spin until the call's last kernel has published sequence number `s.seq` (the stream is polled now
+// and then so that a failed launch or a faulting kernel ends the wait with an error, not a hang).
+int wait_done(srs_model* m, Slot& s) {
+  volatile uint32_t* d = s.h_done;
+  uint64_t spins = 0;
+  while (d[0] != s.seq) {
+    if ((++spins & 0x1FFF) == 0) {
+      const cudaError_t q = cudaStreamQuery(s.stream);
+      if (q == cudaSuccess) {
+        if (d[0] == s.seq) break;
+        return fail(SRS_ERR_CUDA, "the stream drained without the completion record being written");
+      }
+      if (q != cudaErrorNotReady) return fail(SRS_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (d[1]) return fail(SRS_ERR_RANGE, "an id in the batch is outside its vocabulary");
+  (void)m;
   return SRS_OK;
 }
 
@@ -1328,7 +1375,10 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   srs_model* m = new srs_model();
   m->spec = *spec;
   m->device = device;
-  if (const char* zc = getenv("SRS_ZERO_COPY_SCORES")) m->zero_copy_scores = atoi(zc) == 1;
+  if (const char* zc = getenv("SRS_ZERO_COPY_SCORES")) {
+    m->zero_copy_scores = atoi(zc) == 1;              // pipelined paths too (experimental)
+    m->no_zero_copy = atoi(zc) == 0;
+  }
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1477,6 +1527,8 @@ void srs_model_destroy(srs_model* m) {
     cudaFree(s.d_hist32);
     if (s.h_err) cudaFreeHost(s.h_err);
     if (s.h_req) cudaFreeHost(s.h_req);
+    if (s.h_done) cudaFreeHost(s.h_done);
+    if (s.h_res) cudaFreeHost(s.h_res);
     cudaFree(s.d_req);
   }
   for (void* p : m->owned) cudaFree(p);
@@ -1575,10 +1627,37 @@ int srs_gather_copy_scores(srs_gather* gg, float* dst, int32_t dst_on_host, void
   return SRS_OK;
 }
 
+// device-visible alias of a host pointer if it is pinned (page-locked) memory, else nullptr
+static float* pinned_alias(float* p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+    return static_cast<float*>(at.devicePointer);
+  cudaGetLastError();                                   // pageable memory: not an error
+  return nullptr;
+}
+
 int srs_predict_host(srs_model* m, const srs_batch* b, float* probs, float* logits) {
   if (!m) return fail(SRS_ERR_INVALID, "null model");
   std::lock_guard<std::mutex> lock(m->mu);
   Slot& s = m->slots[kSlots];
+  // Latency path: when the caller's output buffers are pinned, the kernel writes the scores (4 B per row)
+  // straight into them over PCIe and a one-warp kernel publishes the completion record: two copy-engine
+  // operations, two driver calls and the stream synchronise of the general path go away.
+  if (probs && b && b->B > 0 && !m->no_zero_copy) {
+    float* dp = pinned_alias(probs);
+    float* dl = logits ? pinned_alias(logits) : nullptr;
+    if (dp && (!logits || dl)) {
+      int rc = ensure_slot(m, s, b->B);
+      if (rc == SRS_OK) rc = ensure_done(s, 0);
+      if (rc != SRS_OK) return rc;
+      rc = stage_and_launch(m, s, b, logits != nullptr, dp, dl);
+      if (rc != SRS_OK) return rc;
+      s.seq += 1;
+      CUDA_TRY(launch_finish(slot_err(m, s), s.h_done, s.seq, s.stream));
+      return wait_done(m, s);
+    }
+  }
   int rc = enqueue_host(m, s, b, probs, logits);
   if (rc != SRS_OK) return rc;
   return wait_slot(m, s);
@@ -1703,11 +1782,13 @@ int srs_rank_host(srs_model* m, const srs_batch* b, int32_t k, int32_t* top_idx,
   Slot& s = m->slots[kSlots];
   int rc = stage_and_launch(m, s, b, false);
   if (rc != SRS_OK) return rc;
-  if (b->B == 0 || k == 0) return wait_slot(m, s);
-  if (!top_idx) return fail(SRS_ERR_INVALID, "top_idx is null");
   const int n = b->B;
+  if (n == 0) return SRS_OK;
   if (k > n) k = n;
-  if (n > s.rank_capacity) {
+  if (k > 0 && !top_idx) return fail(SRS_ERR_INVALID, "top_idx is null");
+  rc = ensure_done(s, k);
+  if (rc != SRS_OK) return rc;
+  if (k > 0 && n > s.rank_capacity) {
     cudaFree(s.d_rank);
     s.d_rank = nullptr;
     s.rank_capacity = 0;
@@ -1715,16 +1796,19 @@ int srs_rank_host(srs_model* m, const srs_batch* b, int32_t k, int32_t* top_idx,
     CUDA_TRY(cudaMalloc(&s.d_rank, (size_t)cap * 8 + topk_scratch_bytes(cap) + 256));
     s.rank_capacity = cap;
   }
-  const size_t cap = (size_t)s.rank_capacity;
-  int32_t* d_idx = reinterpret_cast<int32_t*>(s.d_rank);
-  float* d_top = reinterpret_cast<float*>(s.d_rank + cap * 4);
-  void* scratch = s.d_rank + cap * 8;
-  CUDA_TRY(launch_topk(s.d_probs, n, k, d_idx, d_top, scratch, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
-  if (top_scores)
-    CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-  return wait_slot(m, s);
+  // the ranking kernel writes the k positions / scores into pinned host memory and then the completion
+  // record the caller spins on: no device-to-host copy, no stream synchronise
+  int32_t* r_idx = s.h_res;
+  float* r_top = reinterpret_cast<float*>(s.h_res + s.res_capacity);
+  void* scratch = s.d_rank ? s.d_rank + (size_t)s.rank_capacity * 8 : nullptr;
+  s.seq += 1;
+  CUDA_TRY(launch_topk_done(s.d_probs, n, k, r_idx, r_top, scratch, slot_err(m, s), s.h_done, s.seq, s.stream));
+  rc = wait_done(m, s);
+  if (k > 0) {
+    memcpy(top_idx, r_idx, (size_t)k * 4);
+    if (top_scores) memcpy(top_scores, r_top, (size_t)k * 4);
+  }
+  return rc;
 }
 
 int srs_model_set_movie_features(srs_model* m, int32_t n_movies, const int32_t* genres, const float* numerics) {
@@ -1771,6 +1855,8 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   if (n > s.req_capacity || !s.d_req) {
     cudaFree(s.d_req);
     if (s.h_req) cudaFreeHost(s.h_req);
+    if (s.h_done) cudaFreeHost(s.h_done);
+    if (s.h_res) cudaFreeHost(s.h_res);
     s.d_req = nullptr; s.h_req = nullptr; s.req_capacity = 0;
     const size_t words = 16 + (size_t)hc + (size_t)s.capacity;
     CUDA_TRY(cudaMalloc(&s.d_req, words * 4));
@@ -1784,8 +1870,10 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   memcpy(h + 6, user->user_numerics, 12);
   for (int t = 0; t < hc; ++t) h[9 + t] = t < user->n_hist ? user->hist[t] : 0;     // 0 = the padding id
   memcpy(h + 9 + hc, cand, (size_t)n * 4);
-  const size_t req_words = 9 + (size_t)hc + (size_t)n;
-  CUDA_TRY(cudaMemcpyAsync(s.d_req, h, req_words * 4, cudaMemcpyHostToDevice, s.stream));
+  // the request block stays in pinned host memory: the assemble kernel reads its (9 + T + n) words over
+  // PCIe itself, which is cheaper than a copy-engine operation in front of it
+  rc = ensure_done(s, k);
+  if (rc != SRS_OK) return rc;
   const PackedLayout L = packed_layout(m, (size_t)n);
   uint8_t* d = s.d_block;
   BatchView v{};
@@ -1797,7 +1885,7 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
   v.probs = s.d_probs; v.logits = nullptr; v.err_flag = slot_err(m, s);
-  CUDA_TRY(launch_assemble_request(s.d_req, m->movie_feats, m->movie_feats_rows, n, hc, dense_feats ? 1 : 0,
+  CUDA_TRY(launch_assemble_request(s.h_req, m->movie_feats, m->movie_feats_rows, n, hc, dense_feats ? 1 : 0,
                                    reinterpret_cast<int32_t*>(d + L.movie), reinterpret_cast<int32_t*>(d + L.user),
                                    reinterpret_cast<int32_t*>(d + L.hist), reinterpret_cast<int32_t*>(d + L.mg),
                                    reinterpret_cast<int32_t*>(d + L.ug), reinterpret_cast<float*>(d + L.num),
@@ -1805,26 +1893,27 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   rc = launch(m, v, s.stream);
   if (rc != SRS_OK) return rc;
   if (probs) CUDA_TRY(cudaMemcpyAsync(probs, s.d_probs, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
-  if (k > 0) {
-    if (n > s.rank_capacity) {
-      cudaFree(s.d_rank);
-      s.d_rank = nullptr;
-      s.rank_capacity = 0;
-      const int cap = s.capacity;
-      CUDA_TRY(cudaMalloc(&s.d_rank, (size_t)cap * 8 + topk_scratch_bytes(cap) + 256));
-      s.rank_capacity = cap;
-    }
-    const size_t cap = (size_t)s.rank_capacity;
-    int32_t* d_idx = reinterpret_cast<int32_t*>(s.d_rank);
-    float* d_top = reinterpret_cast<float*>(s.d_rank + cap * 4);
-    void* scratch = s.d_rank + cap * 8;
-    CUDA_TRY(launch_topk(s.d_probs, n, k, d_idx, d_top, scratch, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(top_idx, d_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
-    if (top_scores)
-      CUDA_TRY(cudaMemcpyAsync(top_scores, d_top, (size_t)k * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (k > 0 && n > s.rank_capacity) {
+    cudaFree(s.d_rank);
+    s.d_rank = nullptr;
+    s.rank_capacity = 0;
+    const int cap = s.capacity;
+    CUDA_TRY(cudaMalloc(&s.d_rank, (size_t)cap * 8 + topk_scratch_bytes(cap) + 256));
+    s.rank_capacity = cap;
   }
-  CUDA_TRY(cudaMemcpyAsync(s.h_err, slot_err(m, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-  return wait_slot(m, s);
+  // positions and scores are written into pinned host memory by the ranking kernel itself, followed by the
+  // completion record
+  int32_t* r_idx = s.h_res;
+  float* r_top = reinterpret_cast<float*>(s.h_res + s.res_capacity);
+  void* scratch = s.d_rank ? s.d_rank + (size_t)s.rank_capacity * 8 : nullptr;
+  s.seq += 1;
+  CUDA_TRY(launch_topk_done(s.d_probs, n, k, r_idx, r_top, scratch, slot_err(m, s), s.h_done, s.seq, s.stream));
+  rc = wait_done(m, s);
+  if (k > 0) {
+    memcpy(top_idx, r_idx, (size_t)k * 4);
+    if (top_scores) memcpy(top_scores, r_top, (size_t)k * 4);
+  }
+  return rc;
 }
 
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {

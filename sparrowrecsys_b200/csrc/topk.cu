@@ -67,6 +67,60 @@ topk_cta_kernel(const float* __restrict__ scores, int n, int NP, int k,
   }
 }
 
+// n <= 1024: one key per thread, the compare-exchange steps of distance < 32 by warp shuffles, the
+// others through shared memory (the reference ranks 800 candidates: RecForYouProcess.java:34).
+// Optional tail for the latency path (model.cu): `done` is a host-mapped record the caller spins on
+// instead of synchronising the stream; the error word is moved into it and cleared.
+__global__ void __launch_bounds__(1024)
+topk_small_kernel(const float* __restrict__ scores, int n, int k, int32_t* __restrict__ top_idx,
+                  float* __restrict__ top_scores, int* err_flag, volatile uint32_t* done, uint32_t seq) {
+  __shared__ uint64_t keys[2][1024];
+  const uint32_t tid = threadIdx.x, NP = blockDim.x;
+  uint64_t key = tid < (uint32_t)n ? rank_key(scores[tid], tid) : kPadKey;
+  int buf = 0;
+  for (uint32_t w = 2; w <= NP; w <<= 1) {
+    const bool up = (tid & w) == 0;
+    for (uint32_t j = w >> 1; j > 0; j >>= 1) {
+      uint64_t other;
+      if (j >= 32) {
+        keys[buf][tid] = key;
+        __syncthreads();
+        other = keys[buf][tid ^ j];
+        buf ^= 1;                                    // the next exchange writes the other buffer: one barrier per step
+      } else {
+        other = __shfl_xor_sync(0xffffffffu, key, j);
+      }
+      const bool lower = (tid & j) == 0;
+      key = (lower == up) ? (key < other ? key : other) : (key > other ? key : other);
+    }
+  }
+  if (tid < (uint32_t)k) {
+    const uint32_t idx = (uint32_t)key;
+    top_idx[tid] = (int32_t)idx;
+    if (top_scores) top_scores[tid] = scores[idx];
+  }
+  if (done) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      done[1] = err_flag ? (uint32_t)atomicExch(err_flag, 0) : 0u;
+      __threadfence_system();
+      done[0] = seq;
+    }
+  }
+}
+
+// Tail of a latency-path call that does not end in topk_small_kernel: publish the error word and the
+// sequence number to the host-mapped record.
+__global__ void finish_kernel(int* err_flag, volatile uint32_t* done, uint32_t seq) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    done[1] = err_flag ? (uint32_t)atomicExch(err_flag, 0) : 0u;
+    __threadfence_system();
+    done[0] = seq;
+  }
+}
+
 // ---- n > kSortChunk -----------------------------------------------------------------------
 __global__ void make_keys_kernel(const float* __restrict__ scores, int n, int NP,
                                  uint64_t* __restrict__ keys) {
@@ -135,10 +189,34 @@ size_t topk_scratch_bytes(int n) {
 
 // top_idx / top_scores receive min(k, n) entries.  `scratch` (device, topk_scratch_bytes(n))
 // may be null when n <= kSortChunk.
+cudaError_t launch_finish(int* err_flag, uint32_t* done, uint32_t seq, cudaStream_t s) {
+  finish_kernel<<<1, 32, 0, s>>>(err_flag, done, seq);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+// `done` != nullptr: the last kernel also publishes {seq, error word} to that host-mapped record.
+cudaError_t launch_topk_done(const float* scores, int n, int k, int32_t* top_idx, float* top_scores,
+                             void* scratch, int* err_flag, uint32_t* done, uint32_t seq, cudaStream_t s) {
+  if (n <= 0 || k <= 0) return done ? launch_finish(err_flag, done, seq, s) : cudaSuccess;
+  if (k > n) k = n;
+  if (n <= 1024) {
+    int NP = 32;
+    while (NP < n) NP <<= 1;
+    topk_small_kernel<<<1, NP, 0, s>>>(scores, n, k, top_idx, top_scores, err_flag, done, seq);
+    ++g_launch_count;
+    return cudaGetLastError();
+  }
+  cudaError_t e = launch_topk(scores, n, k, top_idx, top_scores, scratch, s);
+  if (e == cudaSuccess && done) e = launch_finish(err_flag, done, seq, s);
+  return e;
+}
+
 cudaError_t launch_topk(const float* scores, int n, int k, int32_t* top_idx, float* top_scores,
                         void* scratch, cudaStream_t s) {
   if (n <= 0 || k <= 0) return cudaSuccess;
   if (k > n) k = n;
+  if (n <= 1024) return launch_topk_done(scores, n, k, top_idx, top_scores, scratch, nullptr, nullptr, 0, s);
   if (n <= kSortChunk) {
     int NP = 32;
     while (NP < n) NP <<= 1;
