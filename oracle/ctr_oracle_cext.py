@@ -66,6 +66,12 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
+        # idle OpenMP workers sleep instead of spinning: a thread-count sweep otherwise leaves the workers of
+        # the larger teams spinning on the cores the next measurement needs (seen as 25x swings on a 128-CPU host)
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+        os.environ.setdefault("GOMP_SPINCOUNT", "0")
+        os.environ.setdefault("OMP_PROC_BIND", "false")
+        os.environ.setdefault("OMP_DYNAMIC", "false")
         path = LIB_AVX2 if _host_has_avx2() else LIB_GENERIC
         if not os.path.exists(path):
             build()

@@ -81,6 +81,36 @@ __device__ unsigned long long g_din_rtp_trace[40];
     if (p.trace && blockIdx.x == 0 && (cond)) g_din_rtp_trace[slot] = clock64();  \
   } while (0)
 
+// Every mbarrier wait of this kernel goes through rtp_wait: a wait that lasts longer than any
+// legitimate one (2^28 cycles = 0.14 s) records who waited for what and raises g_din_rtp_abort, after
+// which every wait in the grid returns at once - a protocol error ends the launch with wrong scores
+// and a diagnosis (srs_model_status / srs_debug_din_trace slots 32..36) instead of hanging the GPU.
+__device__ unsigned int g_din_rtp_abort;
+__device__ __forceinline__ void rtp_wait_slow(uint64_t* bar, uint32_t parity, int code) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      if (*reinterpret_cast<volatile unsigned int*>(&g_din_rtp_abort)) return;
+      if (clock64() - t0 > (1ll << 28)) {
+        if (atomicCAS(&g_din_rtp_abort, 0u, 1u) == 0u) {
+          g_din_rtp_trace[32] = 1ull;
+          g_din_rtp_trace[33] = (unsigned long long)code;
+          g_din_rtp_trace[34] = (unsigned long long)blockIdx.x;
+          g_din_rtp_trace[35] = (unsigned long long)threadIdx.x;
+          g_din_rtp_trace[36] = (unsigned long long)parity;
+          __threadfence();
+        }
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void rtp_wait(uint64_t* bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  rtp_wait_slow(bar, parity, code);
+}
+
 __device__ __forceinline__ void rtp_store_x4(uint8_t* tile, int block, int row, int col, float4 v) {
   const uint32_t off = block * 8192u + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
   const Split2 s0 = split_pack(v.x, v.y), s1 = split_pack(v.z, v.w);
@@ -265,7 +295,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   const uint32_t s_ringA = smem_u32(ringA), s_ringB = smem_u32(ringB);
   const int first_loader_group = 2;
   // parity helpers: the n-th completion (n = 0, 1, ...) of an mbarrier is observed with parity n & 1
-  auto staged_wait = [&](int j) { if (j >= first_loader_group) mbar_wait(&staged[j & 1], ((j >> 1) - 1) & 1); };
+  auto staged_wait = [&](int j) { if (j >= first_loader_group) rtp_wait(&staged[j & 1], ((j >> 1) - 1) & 1, 1); };
 
   if (wg == 0 || wg == 5) {
     // =================================== gatherers =========================================
@@ -289,7 +319,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       const int* ids = ids_all + (j & 1) * (kPRows * kPIdsLd);
       for (int k = 0; k < g.n_tiles; ++k) {
         const int slot = Kg % kPSlotsA;
-        if (Kg >= kPSlotsA) mbar_wait(&a_empty[slot], ((Kg / kPSlotsA) + 1) & 1);
+        if (Kg >= kPSlotsA) rtp_wait(&a_empty[slot], ((Kg / kPSlotsA) + 1) & 1, 2);
         uint8_t* A = ringA + slot * PA_SLOT;
         const int* idrow = ids + 2 * k * kPIdsLd;
 #pragma unroll
@@ -321,9 +351,9 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       for (int j = 0; j < n_my; ++j) NT += geom(j).n_tiles;
       auto mma1 = [&](int K) {
         const int sa = K % kPSlotsA, sb = K % kPSlotsB, q = K & 1;
-        mbar_wait(&a_full[sa], (K / kPSlotsA) & 1);
-        mbar_wait(&b_full[sb], (K / kPSlotsB) & 1);
-        if (K >= 2) mbar_wait(&d1_free[q], ((K >> 1) - 1) & 1);   // the accumulators of tile K - 2 are in registers
+        rtp_wait(&a_full[sa], (K / kPSlotsA) & 1, 3);
+        rtp_wait(&b_full[sb], (K / kPSlotsB) & 1, 4);
+        if (K >= 2) rtp_wait(&d1_free[q], ((K >> 1) - 1) & 1, 5);   // the accumulators of tile K - 2 are in registers
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD1 = tbase + PT_D1 + 128u * q;
@@ -345,7 +375,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         // the accumulator buffer of tile K is in its consumer's registers half way through the gate
         // (d1_free): the next tile of that consumer is multiplied while the gate arithmetic runs
         if (K + 2 < NT) mma1(K + 2);
-        mbar_wait(&w_ready[q][u], (K >> 2) & 1);
+        rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD2 = tbase + PT_D2 + 32u * q + 16u * u;
@@ -364,7 +394,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     } else if (warp == 5) {
       // =================================== loader ==========================================
       for (int j = first_loader_group; j < n_my; ++j) {
-        mbar_wait(&stage_free[j & 1], ((j >> 1) - 1) & 1);  // every reader of group j - 2 is done
+        rtp_wait(&stage_free[j & 1], ((j >> 1) - 1) & 1, 7);  // every reader of group j - 2 is done
         stage_rows(j);
         stage_hist(j, lane, 32);
         mbar_arrive(&staged[j & 1]);
@@ -388,7 +418,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         const float* cand = cand_all + (j & 1) * (kPRows * 32);
         for (int k = 0; k < g.n_tiles; ++k, ++Kb) {
           const int slot = Kb % kPSlotsB;
-          if (Kb >= kPSlotsB) mbar_wait(&b_empty[slot], ((Kb / kPSlotsB) + 1) & 1);
+          if (Kb >= kPSlotsB) rtp_wait(&b_empty[slot], ((Kb / kPSlotsB) + 1) & 1, 8);
           uint8_t* Bt = ringB + slot * PB_SLOT;
 #pragma unroll
           for (int r = 0; r < 2; ++r)
@@ -436,13 +466,13 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     int pool_group = -1;                                  // group this thread last wrote pooled rows of
     auto pooled_buffer_wait = [&](int j) {                // before the first pooled write of group j
       if (pool_group != j) {
-        if (j >= 2) mbar_wait(&pooled_free[j & 1], ((j >> 1) - 1) & 1);
+        if (j >= 2) rtp_wait(&pooled_free[j & 1], ((j >> 1) - 1) & 1, 9);
         pool_group = j;
       }
     };
     auto pool_out = [&]() {
       const int u = (pend_K >> 1) & 1;
-      mbar_wait(&d2_full[q][u], (pend_K >> 2) & 1);
+      rtp_wait(&d2_full[q][u], (pend_K >> 2) & 1, 10);
       tc_fence_after();
       pooled_buffer_wait(pend_j);
       // D2 row m = 16 warp_w + lane (lane < 16): m < 32 -> hi e = m, else lo e = m - 32;
@@ -481,7 +511,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           cs_buf[cr * 32 + jj] = acc;
         }
         named_sync(1 + q, 128);
-        mbar_wait(&d1_full[q], (K >> 1) & 1);
+        rtp_wait(&d1_full[q], (K >> 1) & 1, 11);
         tc_fence_after();
         if (K == q) RTP_TRACE(3 + 7 * q, tw == 0);
         // ---- gate: v = D_hi + D_lo + cst; s = sum_j v_j P_tj + |v_j| Q_tj
@@ -586,7 +616,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       const GroupGeom g = geom(j);
       const int s = j & 1;
       staged_wait(j);
-      mbar_wait(&pooled_ready[s], (j >> 1) & 1);
+      rtp_wait(&pooled_ready[s], (j >> 1) & 1, 12);
       if (j == 0) RTP_TRACE(5, tw == 0);
       const float* cand = cand_all + s * (kPRows * 32);
       const float* pooled = pooled_all + s * (kPRows * 64);
@@ -633,7 +663,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         }
         __syncwarp();
       }
-      mbar_wait(&cbar, cphase);
+      rtp_wait(&cbar, cphase, 13);
       cphase ^= 1;
       __syncwarp();
       tc_fence_after();
@@ -673,7 +703,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       tc_fence_before();
       named_sync(3, 128);
       if (warp == 16) {
-        if (!w2_ready) { mbar_wait(&wbar, 0); w2_ready = true; }
+        if (!w2_ready) { rtp_wait(&wbar, 0, 14); w2_ready = true; }
         tc_fence_after();
         if (elect_one()) {
           uint32_t acc = 0;
@@ -691,7 +721,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         }
         __syncwarp();
       }
-      mbar_wait(&cbar, cphase);
+      rtp_wait(&cbar, cphase, 13);
       cphase ^= 1;
       __syncwarp();
       tc_fence_after();
@@ -753,6 +783,24 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
 
 cudaError_t read_din_rtp_trace(unsigned long long* out40) {
   return cudaMemcpyFromSymbol(out40, g_din_rtp_trace, sizeof(unsigned long long) * 40);
+}
+
+// Did a wait of an earlier launch time out (see rtp_wait)?  Copies the record {code, block, thread,
+// parity} and clears the flag.
+cudaError_t take_din_rtp_abort(int* aborted, unsigned long long* rec4) {
+  unsigned int flag = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&flag, g_din_rtp_abort, sizeof(flag));
+  if (e != cudaSuccess) return e;
+  *aborted = flag != 0;
+  if (flag) {
+    unsigned long long t[40];
+    e = cudaMemcpyFromSymbol(t, g_din_rtp_trace, sizeof(t));
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 4; ++i) rec4[i] = t[33 + i];
+    flag = 0;
+    e = cudaMemcpyToSymbol(g_din_rtp_abort, &flag, sizeof(flag));
+  }
+  return e;
 }
 
 static size_t din_rtp_smem_bytes() { return 1024 + P_SMEM; }

@@ -1712,6 +1712,14 @@ int srs_model_status(srs_model* m) {
   if (!m) return fail(SRS_ERR_INVALID, "null model");
   CUDA_TRY(cudaSetDevice(m->device));
   CUDA_TRY(cudaDeviceSynchronize());
+  if (m->use_din_rtp) {                              // a protocol error in din_rtp_kernel ends the launch, see rtp_wait
+    int aborted = 0;
+    unsigned long long rec[4] = {0, 0, 0, 0};
+    CUDA_TRY(take_din_rtp_abort(&aborted, rec));
+    if (aborted)
+      return fail(SRS_ERR_CUDA, "din_rtp_kernel: an mbarrier wait timed out (wait code %llu, block %llu, thread %llu, "
+                  "parity %llu); the scores of that launch are invalid", rec[0], rec[1], rec[2], rec[3]);
+  }
   int flags[kErrWords] = {0};
   CUDA_TRY(cudaMemcpy(flags, m->err_flag, kErrWords * sizeof(int), cudaMemcpyDeviceToHost));
   bool any = false;

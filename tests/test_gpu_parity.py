@@ -569,8 +569,10 @@ def test_din_rtp_kernel(E, T, B, sms, din_impl):
             m.set_sm_limit(sms)
         p, z = m.predict_with_logits(feats)
         assert np.array_equal(m.predict(feats), p)                 # deterministic
+        m.status()                                                 # raises with a diagnosis if a wait timed out
         m.set_sm_limit(5)                                          # results do not depend on the grid
         assert np.array_equal(m.predict(feats), p)
+        m.status()
     po, zo = O.forward(spec, W, feats)
     assert np.abs(z - zo).max() <= LOGIT_ATOL, "logit err %g" % np.abs(z - zo).max()
     assert np.abs(p - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p - po).max()
