@@ -370,11 +370,25 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       };
       if (0 < NT) mma1(0);
       if (1 < NT) mma1(1);
+      // every operand of mma1(K) is there already?  (lane 0 decides for the warp)
+      auto mma1_ready = [&](int K) -> bool {
+        const int sa = K % kPSlotsA, sb = K % kPSlotsB, q = K & 1;
+        int ok = mbar_try_wait(&a_full[sa], (K / kPSlotsA) & 1) && mbar_try_wait(&b_full[sb], (K / kPSlotsB) & 1) &&
+                 (K < 2 || mbar_try_wait(&d1_free[q], ((K >> 1) - 1) & 1));
+        return __shfl_sync(0xffffffffu, ok, 0) != 0;
+      };
       for (int K = 0; K < NT; ++K) {
         const int sa = K % kPSlotsA, q = K & 1, u = (K >> 1) & 1;
-        // the accumulator buffer of tile K is in its consumer's registers half way through the gate
-        // (d1_free): the next tile of that consumer is multiplied while the gate arithmetic runs
-        if (K + 2 < NT) mma1(K + 2);
+        // The accumulator buffer of tile K is in its consumer's registers half way through the gate
+        // (d1_free): if the operands of that consumer's next tile are in place, multiply it while the gate
+        // arithmetic of tile K runs.  Never WAIT for them here: tile K + 2 may belong to a group whose
+        // staging needs this tile's pooling MMAs to retire first (one-tile groups), see rtp_protocol_sim.py.
+        bool next_issued = !(K + 2 < NT);
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {   // poll both; then the watchdog wait below
+          if (!next_issued && mma1_ready(K + 2)) { mma1(K + 2); next_issued = true; }
+          const int w = mbar_try_wait(&w_ready[q][u], (K >> 2) & 1);
+          if (__shfl_sync(0xffffffffu, w, 0)) break;
+        }
         rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
         tc_fence_after();
         if (elect_one()) {
@@ -390,6 +404,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           mma_commit(&a_empty[sa]);
         }
         __syncwarp();
+        if (!next_issued) mma1(K + 2);
       }
     } else if (warp == 5) {
       // =================================== loader ==========================================
