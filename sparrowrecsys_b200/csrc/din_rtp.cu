@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     cp_async_wait<0>();
     while (Dg < Kg) deliver_one();
   } else if (wg == 1) {
-    reg_inc<88>();                                         // 40 + 40 + 88 + 120 + 120 + 96 = 504 of the 512 per thread slot
+    // registers: the CTA's pool is what it was LAUNCHED with (768 x 80): 480 per thread slot = 40 + 40 + 80 + 120 + 120 + 80;
+    // this warpgroup and the top-MLP one keep the 80 they were launched with
     if (warp == 4) {
       // =================================== issuer ==========================================
       int NT = 0;
@@ -589,7 +590,6 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     RTP_TRACE(4 + 7 * q, tw == 0);
   } else {
     // =================================== top MLP (wg == 4) ===================================
-    reg_inc<96>();
     // W1^T -> tensor memory (A operand): this thread's lane = unit tw, 96 packed bf16 pairs
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.w1_tmem + (size_t)tw * 96);

@@ -1878,8 +1878,9 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   memcpy(h + 6, user->user_numerics, 12);
   for (int t = 0; t < hc; ++t) h[9 + t] = t < user->n_hist ? user->hist[t] : 0;     // 0 = the padding id
   memcpy(h + 9 + hc, cand, (size_t)n * 4);
-  // the request block stays in pinned host memory: the assemble kernel reads its (9 + T + n) words over
-  // PCIe itself, which is cheaper than a copy-engine operation in front of it
+  // one small copy: (9 + T + n) words instead of n full feature rows.  (Letting the assemble kernel read the
+  // pinned block over PCIe itself was measured slower: every row re-reads the user part from host memory.)
+  CUDA_TRY(cudaMemcpyAsync(s.d_req, s.h_req, (9 + (size_t)hc + (size_t)n) * 4, cudaMemcpyHostToDevice, s.stream));
   rc = ensure_done(s, k);
   if (rc != SRS_OK) return rc;
   const PackedLayout L = packed_layout(m, (size_t)n);
@@ -1893,7 +1894,7 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
   v.user_genre = reinterpret_cast<const int32_t*>(d + L.ug);
   v.numerics = reinterpret_cast<const float*>(d + L.num);
   v.probs = s.d_probs; v.logits = nullptr; v.err_flag = slot_err(m, s);
-  CUDA_TRY(launch_assemble_request(s.h_req, m->movie_feats, m->movie_feats_rows, n, hc, dense_feats ? 1 : 0,
+  CUDA_TRY(launch_assemble_request(s.d_req, m->movie_feats, m->movie_feats_rows, n, hc, dense_feats ? 1 : 0,
                                    reinterpret_cast<int32_t*>(d + L.movie), reinterpret_cast<int32_t*>(d + L.user),
                                    reinterpret_cast<int32_t*>(d + L.hist), reinterpret_cast<int32_t*>(d + L.mg),
                                    reinterpret_cast<int32_t*>(d + L.ug), reinterpret_cast<float*>(d + L.num),

@@ -234,3 +234,18 @@ def test_din_rth_barrier_protocol_model():
         for seed in range(8):
             sim.Sim(shape, seed).run()
             sim.Sim(shape, seed, builder_gathers=True).run()
+
+
+def test_din_rtp_barrier_protocol_model():
+    """din_rtp_kernel (csrc/din_rtp.cu) orders seven roles with nothing but mbarriers across group
+    boundaries; its protocol is checked on a CPU model under random interleavings
+    (profiles/exp/rtp_protocol_sim.py: no deadlock, no parity aliasing, no operand / staging hazard).
+    One-tile groups are the case that deadlocked the first draft."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "rtp_protocol_sim", os.path.join(ROOT, "profiles", "exp", "rtp_protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for shape in ([1], [14], [14, 14, 14], [1, 1, 1, 1, 1, 1], [2, 1, 3, 1, 1, 2], [16, 1, 5, 16, 1, 1, 7]):
+        for seed in range(10):
+            sim.Sim(shape, seed).run()
