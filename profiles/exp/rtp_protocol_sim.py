@@ -16,7 +16,7 @@ interleavings.  Checked:
 import random
 import sys
 
-NSA, NSB, AHEAD = 6, 2, 3
+NSA, NSB, AHEAD = 6, 3, 3
 
 
 class Bar:

@@ -42,7 +42,8 @@ namespace {
 constexpr int kPThreads = 768;
 constexpr int kPRows = 32;                  // row slots per group = N/2 of the top-MLP MMAs
 constexpr int kPSlotsA = 6;                 // history tiles in flight or being consumed
-constexpr int kPSlotsB = 2;                 // per-row weight operands
+constexpr int kPSlotsB = 3;                 // per-row weight operands
+constexpr int kPCstSlots = 8;               // per-tile constants of the gate (see the builders)
 constexpr int kPAhead = 3;                  // tiles a gatherer keeps in flight before it delivers one
 constexpr int kPGatherThreads = 256;
 constexpr int kPIdsLd = 64;                 // ints per row of the staged history ids
@@ -60,12 +61,13 @@ constexpr uint32_t PX_IDS = 0;                               // [2] int [32][64]
 constexpr uint32_t PX_CAND = PX_IDS + 2 * 8192;              // [2] f32 [32][32]
 constexpr uint32_t PX_POOL = PX_CAND + 2 * 4096;             // [2] f32 [32][hi 32 | lo 32]
 constexpr uint32_t PX_NUMS = PX_POOL + 2 * 8192;             // [2] f32 [32][8]
-constexpr uint32_t PX_SID = PX_NUMS + 2 * 1024;              // [2] int [32][4]: user id, userGenre1, movieGenre1, -
+constexpr uint32_t PX_SID = PX_NUMS + 2 * 1024;              // [2] int [32][4]: userGenre1, movieGenre1, user id, -
 constexpr uint32_t PX_B2 = PX_SID + 2 * 512;                 // [consumer][buffer] x 2 K blocks x [8 n][64 positions] bf16, SW128
-constexpr uint32_t PX_CST = PX_B2 + 8192;                    // [consumer][buffer] f32 [2 rows][32]
-constexpr uint32_t PX_RED = PX_CST + 1024;                   // f32 [64][32]
-constexpr uint32_t PX_ZP = PX_RED + 8192;                    // f32 [4][32]
-constexpr uint32_t PX_BYTES = PX_ZP + 512;
+constexpr uint32_t PX_CST = PX_B2 + 8192;                    // [tile K % 8] f32 [2 rows][32]
+constexpr uint32_t PX_BYTES = PX_CST + kPCstSlots * 256;
+// layer-2 scratch lies over the X / H1 operand tile (dead once the layer-2 MMAs have completed)
+constexpr uint32_t PO_RED = PO_XB;                           // f32 [64][32]
+constexpr uint32_t PO_ZP = PO_XB + 8192;                     // f32 [4][32]
 static_assert(PX_B2 % 1024 == 0 && (PO_X + PX_B2) % 1024 == 0, "pooling-weight operand tiles are 1024-byte aligned");
 constexpr uint32_t P_SMEM = PO_X + PX_BYTES;
 static_assert(P_SMEM + 1024 <= 232448, "does not fit the 227 KB of one CTA");
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   float* nums_all = reinterpret_cast<float*>(xs + PX_NUMS);
   int* sid_all = reinterpret_cast<int*>(xs + PX_SID);
   uint8_t* b2s = xs + PX_B2;
-  float* cstq_all = reinterpret_cast<float*>(xs + PX_CST);
+  float* cst_all = reinterpret_cast<float*>(xs + PX_CST);
   const int T = p.T;
   const int RPG = p.rows_per_group;
   const int n_groups = (b.B + RPG - 1) / RPG;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     }
     *reinterpret_cast<float4*>(nums + lane * 8) = make_float4(nv[0], nv[1], nv[2], nv[3]);
     *reinterpret_cast<float4*>(nums + lane * 8 + 4) = make_float4(nv[4], nv[5], nv[6], 0.f);
-    *reinterpret_cast<int4*>(sid + lane * 4) = make_int4(uid, ug, mg, 0);
+    *reinterpret_cast<int4*>(sid + lane * 4) = make_int4(ug, mg, uid, 0);
   };
 
   // ---- prologue ---------------------------------------------------------------------------
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane < 12) mbar_init(&a_empty[lane - 6], 1);
     else if (lane < 14) mbar_init(&b_full[lane - 12], 64);
     else if (lane < 16) mbar_init(&b_empty[lane - 14], 1);
+    if (lane == 0) { mbar_init(&b_full[2], 64); mbar_init(&b_empty[2], 1); }
     else if (lane < 18) mbar_init(&d1_full[lane - 16], 1);
     else if (lane < 20) mbar_init(&d1_free[lane - 18], 128);
     else if (lane < 24) mbar_init(&w_ready[(lane - 20) >> 1][(lane - 20) & 1], 128);
@@ -300,18 +303,21 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   if (wg == 0 || wg == 5) {
     // =================================== gatherers =========================================
     reg_dec<40>();
+    RTP_TRACE(21, tid == 0);
     const int gt = wg == 0 ? tid : tid - 512;              // 0..255
     const uint32_t c = (uint32_t)(gt & 7);
     const int cell0 = gt >> 3;
     int Kg = 0, Dg = 0;
     auto deliver_one = [&]() {
       fence_async_smem();
+      if (Dg == 0) RTP_TRACE(24, tid == 0);
+      if (Dg == 6) RTP_TRACE(25, tid == 0);
       mbar_arrive(&a_full[Dg % kPSlotsA]);
       ++Dg;
     };
     for (int j = 0; j < n_my; ++j) {
       const GroupGeom g = geom(j);
-      if (j >= first_loader_group && !mbar_try_wait(&staged[j & 1], ((j >> 1) - 1) & 1)) {
+      if (j >= first_loader_group && !mbar_test_wait(&staged[j & 1], ((j >> 1) - 1) & 1)) {
         cp_async_wait<0>();                                // the loader is late: do not sit on landed tiles
         while (Dg < Kg) deliver_one();
         staged_wait(j);
@@ -368,14 +374,16 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           mma_commit(&b_empty[sb]);
         }
         __syncwarp();
+        if (K == 4) RTP_TRACE(15, lane == 0);
+        if (K == 6) RTP_TRACE(18, lane == 0);
       };
       if (0 < NT) mma1(0);
       if (1 < NT) mma1(1);
       // every operand of mma1(K) is there already?  (lane 0 decides for the warp)
       auto mma1_ready = [&](int K) -> bool {
         const int sa = K % kPSlotsA, sb = K % kPSlotsB, q = K & 1;
-        int ok = mbar_try_wait(&a_full[sa], (K / kPSlotsA) & 1) && mbar_try_wait(&b_full[sb], (K / kPSlotsB) & 1) &&
-                 (K < 2 || mbar_try_wait(&d1_free[q], ((K >> 1) - 1) & 1));
+        int ok = mbar_test_wait(&a_full[sa], (K / kPSlotsA) & 1) && mbar_test_wait(&b_full[sb], (K / kPSlotsB) & 1) &&
+                 (K < 2 || mbar_test_wait(&d1_free[q], ((K >> 1) - 1) & 1));
         return __shfl_sync(0xffffffffu, ok, 0) != 0;
       };
       for (int K = 0; K < NT; ++K) {
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         bool next_issued = !(K + 2 < NT);
         for (uint32_t spins = 0; spins < (1u << 22); ++spins) {   // poll both; then the watchdog wait below
           if (!next_issued && mma1_ready(K + 2)) { mma1(K + 2); next_issued = true; }
-          const int w = mbar_try_wait(&w_ready[q][u], (K >> 2) & 1);
+          const int w = mbar_test_wait(&w_ready[q][u], (K >> 2) & 1);
           if (__shfl_sync(0xffffffffu, w, 0)) break;
         }
         rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
@@ -405,6 +413,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           mma_commit(&a_empty[sa]);
         }
         __syncwarp();
+        if (K == 4) RTP_TRACE(16, lane == 0);
         if (!next_issued) mma1(K + 2);
       }
     } else if (warp == 5) {
@@ -455,8 +464,22 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
               *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
               *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
             }
+          // gate constants of the tile: cst[r][jj] = au_b[jj] + sum_e cand[r][e] (Wc - Wsub)[e][jj], thread -> (r, jj).
+          // Slot Kb % 8: the gate of tile Kb - 8 finished before MMA1(Kb - 3) completed (b_empty above).
+          {
+            const int cr = bt >> 5, jj = bt & 31;
+            const float* cv = cand + (2 * k + cr) * 32;
+            float acc0 = __ldg(p.au_b + jj), acc1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              acc0 = fmaf(cv[e], __ldg(p.au_wc + e * 32 + jj), acc0);
+              acc1 = fmaf(cv[e + 1], __ldg(p.au_wc + (e + 1) * 32 + jj), acc1);
+            }
+            cst_all[(Kb % kPCstSlots) * 64 + cr * 32 + jj] = acc0 + acc1;
+          }
           fence_async_smem();
           mbar_arrive(&b_full[slot]);
+          if (Kb == 4) RTP_TRACE(17, bt == 0);
         }
         mbar_arrive(&stage_free[j & 1]);
       }
@@ -516,20 +539,11 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       for (int k = (q - kbase) & 1; k < g.n_tiles; k += 2) {
         any = true;
         const int K = kbase + k, u = (K >> 1) & 1;
-        float* cs_buf = cstq_all + (q * 2 + u) * 64;
-        // cst[r][jj] = au_b[jj] + sum_e cand[r][e] (Wc - Wsub)[e][jj] of the tile's two rows
-        if (tw < 64) {
-          const int cr = tw >> 5, jj = tw & 31;
-          const float* cv = cand + (2 * k + cr) * 32;
-          float acc = __ldg(p.au_b + jj);
-#pragma unroll 8
-          for (int e = 0; e < 32; ++e) acc = fmaf(cv[e], __ldg(p.au_wc + e * 32 + jj), acc);
-          cs_buf[cr * 32 + jj] = acc;
-        }
-        named_sync(1 + q, 128);
+        const float* cs_buf = cst_all + (K % kPCstSlots) * 64;      // written by the builders before MMA1(K) was issued
         rtp_wait(&d1_full[q], (K >> 1) & 1, 11);
         tc_fence_after();
         if (K == q) RTP_TRACE(3 + 7 * q, tw == 0);
+        if (K == 4) RTP_TRACE(12, tw == 0);
         // ---- gate: v = D_hi + D_lo + cst; s = sum_j v_j P_tj + |v_j| Q_tj
         float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
         {
@@ -575,7 +589,9 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(&w_ready[q][u]);
+        if (K == 4) RTP_TRACE(13, tw == 0);
         if (pend) pool_out();                               // the previous own tile's pooling MMAs finished long ago
+        if (K == 4) RTP_TRACE(14, tw == 0);
         pend = true; pend_K = K; pend_j = j; pend_k = k; pend_last = k + 2 >= g.n_tiles;
       }
       if (!any) {                                           // a one-tile group of the other consumer
@@ -623,8 +639,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     const uint32_t tTop = tbase + PT_TOP;
     const uint32_t s_xb = smem_u32(base + PO_XB), s_w2 = smem_u32(base + PO_W2);
     uint8_t* xb = base + PO_XB;
-    float* red = reinterpret_cast<float*>(xs + PX_RED);
-    float* zp = reinterpret_cast<float*>(xs + PX_ZP);
+    float* red = reinterpret_cast<float*>(base + PO_RED);
+    float* zp = reinterpret_cast<float*>(base + PO_ZP);
     uint32_t cphase = 0;
     bool w2_ready = false;
     for (int j = 0; j < n_my; ++j) {
@@ -642,7 +658,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         const int xr = tw >> 2, c8 = (tw & 3) * 8;
         float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0, p0 = u0, p1 = u0, c0 = u0, c1 = u0;
         if (xr < g.nrows) {
-          const int uid = sid[xr * 4];
+          const int uid = sid[xr * 4 + 2];
           u0 = ldg4(p.user + (size_t)uid * 32 + c8);
           u1 = ldg4(p.user + (size_t)uid * 32 + c8 + 4);
           const float4 h0 = *reinterpret_cast<const float4*>(pooled + xr * 64 + c8);
@@ -689,6 +705,16 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         const uint32_t chunk = (tw & 63) >> 3, within = (tw & 7) * 2;
 #pragma unroll
         for (int r8 = 0; r8 < 4; ++r8) {
+          // genre columns of Dense(128): G_u[userGenre1][unit] + G_m[movieGenre1][unit], all 16 loads of the
+          // chunk in flight together (a load per row inside the arithmetic below serialised 64 L2 round trips)
+          float gsum[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int2 gid = *reinterpret_cast<const int2*>(sid + (r8 * 8 + r) * 4);         // userGenre1, movieGenre1
+            const float gu = gid.x >= 0 ? __ldg(p.gtab_u + gid.x * 128 + tw) : 0.f;
+            const float gm = gid.y >= 0 ? __ldg(p.gtab_m + gid.y * 128 + tw) : 0.f;
+            gsum[r] = gu + gm;
+          }
           uint32_t d[8], d2[8];
           tmem_ld8(tTop + 8 * r8 + lane_base, d);              // W1 . X hi
           tmem_ld8(tTop + 32 + 8 * r8 + lane_base, d2);        // W1 . X lo
@@ -698,10 +724,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
             const int sr = r8 * 8 + r;
             const float4 n0 = *reinterpret_cast<const float4*>(nums + sr * 8);
             const float4 n1 = *reinterpret_cast<const float4*>(nums + sr * 8 + 4);
-            const int ug = sid[sr * 4 + 1], mg = sid[sr * 4 + 2];
             float v = (__uint_as_float(d[r]) + __uint_as_float(d2[r])) + b1;
-            if (ug >= 0) v += __ldg(p.gtab_u + ug * 128 + tw);
-            if (mg >= 0) v += __ldg(p.gtab_m + mg * 128 + tw);
+            v += gsum[r];
             v = fmaf(n0.x, w1n[0], v); v = fmaf(n0.y, w1n[1], v); v = fmaf(n0.z, w1n[2], v);
             v = fmaf(n0.w, w1n[3], v); v = fmaf(n1.x, w1n[4], v); v = fmaf(n1.y, w1n[5], v);
             v = fmaf(n1.z, w1n[6], v);
@@ -713,6 +737,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           }
         }
       }
+      if (j == 0) RTP_TRACE(22, tw == 0);
       mbar_arrive(&stage_free[s]);                            // numerics / ids / candidate rows consumed
       fence_async_smem();
       tc_fence_before();
@@ -740,6 +765,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       cphase ^= 1;
       __syncwarp();
       tc_fence_after();
+      if (j == 0) RTP_TRACE(23, tw == 0);
       // ---- layer-2 epilogue: rows 0..63 of D hold W2hi . (H1hi | H1lo), rows 64..127 W2lo . (...)
       {
         float dsum[32];

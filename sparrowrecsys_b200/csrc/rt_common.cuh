@@ -36,6 +36,19 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a system-dependent time before
+// it answers "not yet": a loop that polls SEVERAL barriers must not sit in one of them)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -269,8 +269,9 @@ class CTRModel:
         cand = np.ascontiguousarray(np.asarray(candidate_ids, np.int32).reshape(-1))
         n = cand.shape[0]
         k = max(0, min(int(size), n))
-        hist = np.ascontiguousarray(np.array([typed["userRatedMovie%d" % (t + 1)] for t in range(self.hist_cols)],
-                                             np.int32))
+        from .spec import history_keys
+        hkeys = history_keys(self.spec.hist_len) if self.spec.model in ("din", "dien") else ["userRatedMovie1"]
+        hist = np.ascontiguousarray(np.array([typed[k] for k in hkeys[:self.hist_cols]], np.int32))   # graph position order
         row = _lib.SrsUserRow()
         row.user_id = int(user_id)
         for g in range(5):
