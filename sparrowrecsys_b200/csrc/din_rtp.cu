@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane < 12) mbar_init(&a_empty[lane - 6], 1);
     else if (lane < 14) mbar_init(&b_full[lane - 12], 64);
     else if (lane < 16) mbar_init(&b_empty[lane - 14], 1);
-    if (lane == 0) { mbar_init(&b_full[2], 64); mbar_init(&b_empty[2], 1); }
     else if (lane < 18) mbar_init(&d1_full[lane - 16], 1);
     else if (lane < 20) mbar_init(&d1_free[lane - 18], 128);
     else if (lane < 24) mbar_init(&w_ready[(lane - 20) >> 1][(lane - 20) & 1], 128);
@@ -266,6 +265,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane < 4) mbar_init(&pooled_free[lane - 2], 128);
     else if (lane == 4) mbar_init(&wbar, 1);
     else if (lane == 5) mbar_init(&cbar, 1);
+    else if (lane == 6) mbar_init(&b_full[2], 64);
+    else if (lane == 7) mbar_init(&b_empty[2], 1);
     fence_mbar_init();
   }
   {
