@@ -533,6 +533,7 @@ def run_ours(args):
         from sparrowrecsys_b200 import sharding
         fused = sharding.FusedScoreGather(model, B, dev)           # symmetric buffers + peer pointers
         gather_note = fused.describe()
+        extra_launches_per_batch = 1                               # the one-warp wait kernel
 
         def launch(i, stream_ptr):                                 # noqa: F811 - the gathering launch
             fused.predict(structs[i % ring], stream_ptr)

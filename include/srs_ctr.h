@@ -130,6 +130,14 @@ const char* srs_last_error(void);
 int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors,
                      int32_t device, srs_model** out);
 
+/* Same, with kernel-variant options "key=value;key=value": din_impl = rtp | rt | tc | cudacore | rth,
+ * embmlp_impl / deepfm_impl = tc | cudacore, zero_copy_scores = 0 | 1.  Unknown keys are ignored; a
+ * forced variant that does not support the shape makes the call fail.  NULL / "" = the defaults
+ * (which srs_model_kernel_name reports).  The environment variables SRS_DIN_IMPL, SRS_EMBMLP_IMPL,
+ * SRS_DEEPFM_IMPL, SRS_ZERO_COPY_SCORES are read only for keys the string does not set. */
+int srs_model_create_ex(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors,
+                        int32_t device, const char* options, srs_model** out);
+
 void srs_model_destroy(srs_model* m);
 
 /* Forward pass with everything resident in HBM; asynchronous on `stream`

@@ -35,7 +35,7 @@ class SrsBatch(C.Structure):
                 ("user_genre", C.c_void_p), ("numerics", C.c_void_p), ("hist16", C.c_void_p)]
 
 
-EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_destroy",
+EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_create_ex", "srs_model_destroy",
            "srs_predict_device", "srs_predict_host", "srs_predict_host_batches", "srs_num_slots", "srs_predict_host_async",
            "srs_wait_slot", "srs_model_status", "srs_model_bytes_per_inference",
            "srs_model_kernel_name", "srs_model_set_sm_limit", "srs_launch_count", "srs_fill_uniform",
@@ -79,6 +79,9 @@ def load():
     lib.srs_model_create.restype = C.c_int
     lib.srs_model_create.argtypes = [C.POINTER(SrsSpec), C.POINTER(SrsTensor), C.c_int32,
                                      C.c_int32, C.POINTER(C.c_void_p)]
+    lib.srs_model_create_ex.restype = C.c_int
+    lib.srs_model_create_ex.argtypes = [C.POINTER(SrsSpec), C.POINTER(SrsTensor), C.c_int32,
+                                        C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.srs_model_destroy.restype = None
     lib.srs_model_destroy.argtypes = [C.c_void_p]
     lib.srs_predict_device.restype = C.c_int

@@ -60,6 +60,27 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// Kernel-variant options of the model being created: "key=value;key=value" handed to
+// srs_model_create_ex (keys: din_impl, embmlp_impl, deepfm_impl, zero_copy_scores, din_rth_ctas,
+// din_rth_bg).  The environment variables SRS_<KEY> remain as a tuning override of last resort.
+thread_local std::string g_create_opts;
+const char* opt(const char* key, const char* env_name) {
+  static thread_local std::string val;
+  const std::string& o = g_create_opts;
+  const std::string k = std::string(key) + "=";
+  size_t pos = 0;
+  while (pos < o.size()) {
+    size_t end = o.find(';', pos);
+    if (end == std::string::npos) end = o.size();
+    if (o.compare(pos, k.size(), k) == 0) {
+      val = o.substr(pos + k.size(), end - pos - k.size());
+      return val.c_str();
+    }
+    pos = end + 1;
+  }
+  return getenv(env_name);
+}
+
 #define CUDA_TRY(expr)                                                                   \
   do {                                                                                   \
     cudaError_t e__ = (expr);                                                            \
@@ -1375,7 +1396,7 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   srs_model* m = new srs_model();
   m->spec = *spec;
   m->device = device;
-  if (const char* zc = getenv("SRS_ZERO_COPY_SCORES")) {
+  if (const char* zc = opt("zero_copy_scores", "SRS_ZERO_COPY_SCORES")) {
     m->zero_copy_scores = atoi(zc) == 1;              // pipelined paths too (experimental)
     m->no_zero_copy = atoi(zc) == 0;
   }
@@ -1399,7 +1420,9 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     case SRS_WIDENDEEP: {
       rc = build_embmlp(B);
       // tensor-core path for the reference shape (E <= 12); SRS_EMBMLP_IMPL=cudacore|tc overrides
-      const char* impl = getenv("SRS_EMBMLP_IMPL");
+      const char* impl_c = opt("embmlp_impl", "SRS_EMBMLP_IMPL");
+      const std::string impl_s = impl_c ? impl_c : "";
+      const char* impl = impl_c ? impl_s.c_str() : nullptr;
       const bool fits = m->EP == 12;
       bool want = fits;
       if (impl && !strcmp(impl, "cudacore")) want = false;
@@ -1419,7 +1442,9 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
     case SRS_DEEPFM: {
       rc = build_deepfm(B);
       // tensor-core deep MLP when emb_dim pads to 16; SRS_DEEPFM_IMPL=cudacore|tc overrides
-      const char* impl = getenv("SRS_DEEPFM_IMPL");
+      const char* impl_c = opt("deepfm_impl", "SRS_DEEPFM_IMPL");
+      const std::string impl_s = impl_c ? impl_c : "";
+      const char* impl = impl_c ? impl_s.c_str() : nullptr;
       const bool fits = m->EP == 16;
       bool want = fits;
       if (impl && !strcmp(impl, "cudacore")) want = false;
@@ -1440,7 +1465,9 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
       // kernel selection (SRS_DIN_IMPL=cudacore|tc|rt overrides; tc / rt fail loudly on an unsupported shape):
       //   rt  row-tile kernels: E padded to 32 and T in 9..64 (din_rt), E padded to 64 and T in 9..256 (din_rt64)
       //   tc  per-pair tensor-core kernel, E padded to 32 and T in 9..128
-      const char* impl = getenv("SRS_DIN_IMPL");
+      const char* impl_c = opt("din_impl", "SRS_DIN_IMPL");
+      const std::string impl_s = impl_c ? impl_c : "";
+      const char* impl = impl_c ? impl_s.c_str() : nullptr;
       const bool fits_tc = m->EP == 32 && spec->hist_len <= 128;
       const bool fits_rt32 = m->EP == 32 && spec->hist_len <= 64;
       const bool fits_rt64 = m->EP == 64 && spec->hist_len <= 256;
@@ -1480,9 +1507,9 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
           // experimental kernel: its attribute setup stays off the path of every other model
           cudaError_t ea = setup_din_rth_attributes();
           if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rth attribute setup failed: %s", cudaGetErrorString(ea));
-          const char* cps = getenv("SRS_DIN_RTH_CTAS");
+          const char* cps = opt("din_rth_ctas", "SRS_DIN_RTH_CTAS");
           m->din_rt.ctas_per_sm = (cps && atoi(cps) == 2) ? 2 : 1;
-          const char* bg = getenv("SRS_DIN_RTH_BG");        // builder warp gathers too
+          const char* bg = opt("din_rth_bg", "SRS_DIN_RTH_BG");        // builder warp gathers too
           m->din_rt.nch = (bg && atoi(bg) == 1) ? 1 : 0;
           m->use_din_rt = false; m->use_din_rth = true; m->kernel_name = "din_rth_kernel";
         }
@@ -1516,6 +1543,14 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
   }
   *out = m;
   return SRS_OK;
+}
+
+int srs_model_create_ex(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors, int32_t device,
+                        const char* options, srs_model** out) {
+  g_create_opts = options ? options : "";
+  const int rc = srs_model_create(spec, tensors, n_tensors, device, out);
+  g_create_opts.clear();
+  return rc;
 }
 
 void srs_model_destroy(srs_model* m) {

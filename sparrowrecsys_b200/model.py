@@ -85,11 +85,12 @@ class CTRModel:
     """One CTR ranking model resident on one GPU."""
 
     def __init__(self, spec: ModelSpec, weights: Mapping[str, object], device: int = 0,
-                 narrow_ids: bool = False):
+                 narrow_ids: bool = False, options: Optional[Mapping[str, object]] = None):
         """`weights`: canonical name -> float32 numpy array (reference shapes), or a
         torch CUDA tensor for an embedding table that is already in HBM (used in
         place, see SRS_DEVICE_BORROWED in include/srs_ctr.h).  `narrow_ids`: host batches
-        carry the history ids as uint16 (`srs_batch::hist16`, n_movies <= 65536)."""
+        carry the history ids as uint16 (`srs_batch::hist16`, n_movies <= 65536).  `options`:
+        kernel-variant choices for `srs_model_create_ex`, e.g. {"din_impl": "rt"}."""
         self.spec = spec
         self.narrow_ids = bool(narrow_ids) and spec.n_movies <= 65536
         self.device = int(device)
@@ -120,8 +121,9 @@ class CTRModel:
                 tensors[i] = _lib.SrsTensor(name.encode(), a.ctypes.data, rows, cols, _lib.SRS_HOST)
         handle = C.c_void_p()
         sp = _spec_struct(spec)
-        _lib.check(lib.srs_model_create(C.byref(sp), tensors, len(shapes), self.device,
-                                        C.byref(handle)))
+        opts = ";".join("%s=%s" % (k, v) for k, v in (options or {}).items()).encode()
+        _lib.check(lib.srs_model_create_ex(C.byref(sp), tensors, len(shapes), self.device, opts or None,
+                                           C.byref(handle)))
         self._h = handle
         self._keep = [w for w in self._keep if not isinstance(w, np.ndarray)]  # host copies done
         self.hist_cols = spec.hist_len if spec.model in ("din", "dien") \
