@@ -96,7 +96,13 @@ class Sim:
             for k in range(n_tiles):
                 slot = Kg % NSA
                 if Kg >= NSA:
-                    yield from self.wait(self.a_empty[slot], ((Kg // NSA) + 1) & 1, Kg // NSA - 1)
+                    par = ((Kg // NSA) + 1) & 1
+                    while not self.a_empty[slot].passed(par):          # publish landed tiles before blocking
+                        if Dg < Kg:
+                            self.a_full[Dg % NSA].arrive(256)
+                            Dg += 1
+                        yield
+                    yield from self.wait(self.a_empty[slot], par, Kg // NSA - 1)
                 self.touch("A%d" % slot, "cp.async into the tile")
                 Kg += 1
                 if Kg - Dg > AHEAD:

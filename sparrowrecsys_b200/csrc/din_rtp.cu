@@ -309,12 +309,20 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     const uint32_t c = (uint32_t)(gt & 7);
     const int cell0 = gt >> 3;
     int Kg = 0, Dg = 0;
-    auto deliver_one = [&]() {
+    auto deliver_one = [&]() {                             // the oldest outstanding tile HAS landed: publish it
       fence_async_smem();
       if (Dg == 0) RTP_TRACE(24, tid == 0);
       if (Dg == 6) RTP_TRACE(25, tid == 0);
       mbar_arrive(&a_full[Dg % kPSlotsA]);
       ++Dg;
+    };
+    auto deliver_oldest = [&]() {                          // wait for the oldest outstanding tile, then publish it
+      const int pending = Kg - Dg;                         // 1 .. kPAhead + 1 commit groups in flight
+      if (pending >= 4) cp_async_wait<3>();
+      else if (pending == 3) cp_async_wait<2>();
+      else if (pending == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      deliver_one();
     };
     for (int j = 0; j < n_my; ++j) {
       const GroupGeom g = geom(j);
@@ -326,7 +334,15 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       const int* ids = ids_all + (j & 1) * (kPRows * kPIdsLd);
       for (int k = 0; k < g.n_tiles; ++k) {
         const int slot = Kg % kPSlotsA;
-        if (Kg >= kPSlotsA) rtp_wait(&a_empty[slot], ((Kg / kPSlotsA) + 1) & 1, 2);
+        if (Kg >= kPSlotsA) {
+          // No free slot yet: do not sit on tiles that have landed (the consumers that will free the slot may
+          // be waiting for exactly those) - publish them first, then wait.
+          const uint32_t par = ((Kg / kPSlotsA) + 1) & 1;
+          while (!mbar_test_wait(&a_empty[slot], par)) {
+            if (Dg < Kg) deliver_oldest();
+            else { rtp_wait(&a_empty[slot], par, 2); break; }
+          }
+        }
         uint8_t* A = ringA + slot * PA_SLOT;
         const int* idrow = ids + 2 * k * kPIdsLd;
 #pragma unroll
@@ -340,10 +356,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         }
         cp_async_commit();
         ++Kg;
-        if (Kg - Dg > kPAhead) {
-          cp_async_wait<kPAhead>();
-          deliver_one();
-        }
+        if (Kg - Dg > kPAhead) deliver_oldest();
         if (j == 0 && k == 0) RTP_TRACE(20, tid == 0);
       }
       mbar_arrive(&stage_free[j & 1]);                     // the ids were read when the copies were issued
