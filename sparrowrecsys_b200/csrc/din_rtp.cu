@@ -708,6 +708,19 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         }
         __syncwarp();
       }
+      // genre columns of Dense(128): G_u[userGenre1][unit] + G_m[movieGenre1][unit] per row slot.  The loads are L2
+      // round trips: chunk 0 is requested before the MMA wait, chunk c + 1 while chunk c is processed.
+      auto genre_sums = [&](int r8, float (&gs)[8]) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int2 gid = *reinterpret_cast<const int2*>(sid + (r8 * 8 + r) * 4);       // userGenre1, movieGenre1
+          const float gu = gid.x >= 0 ? __ldg(p.gtab_u + gid.x * 128 + tw) : 0.f;
+          const float gm = gid.y >= 0 ? __ldg(p.gtab_m + gid.y * 128 + tw) : 0.f;
+          gs[r] = gu + gm;
+        }
+      };
+      float gnext[8];
+      genre_sums(0, gnext);
       rtp_wait(&cbar, cphase, 13);
       cphase ^= 1;
       __syncwarp();
@@ -719,16 +732,10 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         const uint32_t chunk = (tw & 63) >> 3, within = (tw & 7) * 2;
 #pragma unroll
         for (int r8 = 0; r8 < 4; ++r8) {
-          // genre columns of Dense(128): G_u[userGenre1][unit] + G_m[movieGenre1][unit], all 16 loads of the
-          // chunk in flight together (a load per row inside the arithmetic below serialised 64 L2 round trips)
           float gsum[8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int2 gid = *reinterpret_cast<const int2*>(sid + (r8 * 8 + r) * 4);         // userGenre1, movieGenre1
-            const float gu = gid.x >= 0 ? __ldg(p.gtab_u + gid.x * 128 + tw) : 0.f;
-            const float gm = gid.y >= 0 ? __ldg(p.gtab_m + gid.y * 128 + tw) : 0.f;
-            gsum[r] = gu + gm;
-          }
+          for (int r = 0; r < 8; ++r) gsum[r] = gnext[r];
+          if (r8 < 3) genre_sums(r8 + 1, gnext);
           uint32_t d[8], d2[8];
           tmem_ld8(tTop + 8 * r8 + lane_base, d);              // W1 . X hi
           tmem_ld8(tTop + 32 + 8 * r8 + lane_base, d2);        // W1 . X lo
