@@ -368,67 +368,71 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     // this warpgroup and the top-MLP one keep the 80 they were launched with
     if (warp == 4) {
       // =================================== issuer ==========================================
+      // ONE textual site per MMA group inside one loop: when the activation-unit group was a lambda called from
+      // three places, the compiler kept a single out-of-line copy whose descriptors lived in vector registers and
+      // reached the tensor core through predicated R2UR moves - about 1 K cycles per tile instead of back-to-back
+      // UTCHMMA (ncu, round 2).  Loop index K is the tile whose pooling MMAs are issued; the activation-unit MMAs
+      // of tile K + 2 go out in the same iteration, before the pooling group if their operands are in place by
+      // then, else after it (never WAIT for them first: see rtp_protocol_sim.py, one-tile groups).
       int NT = 0;
       for (int j = 0; j < n_my; ++j) NT += geom(j).n_tiles;
-      auto mma1 = [&](int K) {
-        const int sa = K % kPSlotsA, sb = K % kPSlotsB, q = K & 1;
-        rtp_wait(&a_full[sa], (K / kPSlotsA) & 1, 3);
-        rtp_wait(&b_full[sb], (K / kPSlotsB) & 1, 4);
-        if (K >= 2) rtp_wait(&d1_free[q], ((K >> 1) - 1) & 1, 5);   // the accumulators of tile K - 2 are in registers
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t tD1 = tbase + PT_D1 + 128u * q;
-          const uint64_t ad = smem_desc_sw128(s_ringA + sa * PA_SLOT);
-          const uint64_t bd = smem_desc_sw64(s_ringB + sb * PB_SLOT);
-          mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
-          mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
-          mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
-          mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
-          mma_commit(&d1_full[q]);
-          mma_commit(&b_empty[sb]);
+      for (int K = -2; K < NT; ++K) {
+        const int Kn = K + 2;                               // tile of this iteration's activation-unit MMAs
+        const bool has_next = Kn < NT, has_pool = K >= 0;
+        const int sa = has_pool ? K % kPSlotsA : 0, q = K & 1, u = (K >> 1) & 1;
+        const int na = Kn % kPSlotsA, nb = Kn % kPSlotsB, nq = Kn & 1;
+        bool before = !has_pool;                            // tiles 0 and 1: nothing to pool yet
+        if (has_pool && has_next) {
+          for (uint32_t spins = 0; spins < (1u << 22); ++spins) {   // poll both; then the watchdog waits below
+            const int r = mbar_test_wait(&a_full[na], (Kn / kPSlotsA) & 1) && mbar_test_wait(&b_full[nb], (Kn / kPSlotsB) & 1) &&
+                          (Kn < 2 || mbar_test_wait(&d1_free[nq], ((Kn >> 1) - 1) & 1));
+            const int w = mbar_test_wait(&w_ready[q][u], (K >> 2) & 1);
+            const unsigned both = __shfl_sync(0xffffffffu, (unsigned)(r | (w << 1)), 0);
+            if (both & 1u) { before = true; break; }
+            if (both & 2u) break;
+          }
         }
-        __syncwarp();
-        if (K == 4) RTP_TRACE(15, lane == 0);
-        if (K == 6) RTP_TRACE(18, lane == 0);
-      };
-      if (0 < NT) mma1(0);
-      if (1 < NT) mma1(1);
-      // every operand of mma1(K) is there already?  (lane 0 decides for the warp)
-      auto mma1_ready = [&](int K) -> bool {
-        const int sa = K % kPSlotsA, sb = K % kPSlotsB, q = K & 1;
-        int ok = mbar_test_wait(&a_full[sa], (K / kPSlotsA) & 1) && mbar_test_wait(&b_full[sb], (K / kPSlotsB) & 1) &&
-                 (K < 2 || mbar_test_wait(&d1_free[q], ((K >> 1) - 1) & 1));
-        return __shfl_sync(0xffffffffu, ok, 0) != 0;
-      };
-      for (int K = 0; K < NT; ++K) {
-        const int sa = K % kPSlotsA, q = K & 1, u = (K >> 1) & 1;
-        // The accumulator buffer of tile K is in its consumer's registers half way through the gate
-        // (d1_free): if the operands of that consumer's next tile are in place, multiply it while the gate
-        // arithmetic of tile K runs.  Never WAIT for them here: tile K + 2 may belong to a group whose
-        // staging needs this tile's pooling MMAs to retire first (one-tile groups), see rtp_protocol_sim.py.
-        bool next_issued = !(K + 2 < NT);
-        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {   // poll both; then the watchdog wait below
-          if (!next_issued && mma1_ready(K + 2)) { mma1(K + 2); next_issued = true; }
-          const int w = mbar_test_wait(&w_ready[q][u], (K >> 2) & 1);
-          if (__shfl_sync(0xffffffffu, w, 0)) break;
-        }
-        rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t tD2 = tbase + PT_D2 + 32u * q + 16u * u;
-          const uint32_t s_b2 = smem_u32(b2s) + (q * 2 + u) * 2048;
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
+        for (int phase = 0; phase < 2; ++phase) {
+          if (has_next && (phase == 0) == before) {
+            rtp_wait(&a_full[na], (Kn / kPSlotsA) & 1, 3);
+            rtp_wait(&b_full[nb], (Kn / kPSlotsB) & 1, 4);
+            if (Kn >= 2) rtp_wait(&d1_free[nq], ((Kn >> 1) - 1) & 1, 5);   // the accumulators of tile Kn - 2 are in registers
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t tD1 = tbase + PT_D1 + 128u * nq;
+              const uint64_t ad = smem_desc_sw128(s_ringA + na * PA_SLOT);
+              const uint64_t bd = smem_desc_sw64(s_ringB + nb * PB_SLOT);
+              mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
+              mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
+              mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
+              mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
+              mma_commit(&d1_full[nq]);
+              mma_commit(&b_empty[nb]);
+            }
+            __syncwarp();
+            if (Kn == 4) RTP_TRACE(15, lane == 0);
+            if (Kn == 6) RTP_TRACE(18, lane == 0);
+          }
+          if (phase == 0 && has_pool) {
+            rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t tD2 = tbase + PT_D2 + 32u * q + 16u * u;
+              const uint32_t s_b2 = smem_u32(b2s) + (q * 2 + u) * 2048;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ringA + sa * PA_SLOT + r * 8192 + ks * 2048),
-                     smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
-          mma_commit(&d2_full[q][u]);
-          mma_commit(&a_empty[sa]);
+              for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ringA + sa * PA_SLOT + r * 8192 + ks * 2048),
+                         smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
+              mma_commit(&d2_full[q][u]);
+              mma_commit(&a_empty[sa]);
+            }
+            __syncwarp();
+            if (K == 4) RTP_TRACE(16, lane == 0);
+          }
         }
-        __syncwarp();
-        if (K == 4) RTP_TRACE(16, lane == 0);
-        if (!next_issued) mma1(K + 2);
       }
     } else if (warp == 5) {
       // =================================== loader ==========================================
