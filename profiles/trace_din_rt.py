@@ -29,7 +29,7 @@ names = {0: "entry", 1: "prologue", 2: "phase0", 3: "first_d1_ready", 4: "first_
          6: "layer1", 7: "group", 8: "exit"}
 if m.kernel_name == "din_rtp_kernel":   # slots: 3/10 first d1 of consumer 0/1, 4/11 consumers done, 5 first pooled group at the top MLP,
     names = {0: "entry", 1: "prologue", 21: "g.reg_dec", 20: "g.first_tile_issued", 24: "g.tile0_delivered", 25: "g.tile6_delivered",
-             3: "c0_first_d1", 10: "c1_first_d1", 17: "b.tile4_built", 15: "i.mma1(4)", 12: "c0.tile4_d1", 13: "c0.tile4_gate",
+             3: "c0_first_d1", 10: "c1_first_d1", 26: "i.entry", 27: "i.mma1(0)", 28: "b.tile0_built", 29: "b.tile3_built", 17: "b.tile4_built", 15: "i.mma1(4)", 12: "c0.tile4_d1", 13: "c0.tile4_gate",
              14: "c0.tile4_pooled_prev", 16: "i.pool(4)", 18: "i.mma1(6)", 5: "top.g0_pooled_ready", 6: "top.g0_layer1", 22: "top.g0_epi1",
              23: "top.g0_layer2", 7: "top.g0_done", 4: "c0_done", 11: "c1_done", 8: "exit"}
 for rep in range(3):

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   __shared__ uint64_t stage_free[2];        // every reader of staging buffer s is done with it (704 arrivals)
   __shared__ uint64_t pooled_ready[2];      // pooled rows of the group in buffer s are complete (256 arrivals)
   __shared__ uint64_t pooled_free[2];       // the top MLP has read them (128 arrivals)
+  __shared__ uint64_t started;              // the gatherers have requested their first tile (256 arrivals, once)
   __shared__ uint64_t wbar;                 // W2 image landed (once per launch)
   __shared__ uint64_t cbar;                 // top-MLP MMAs complete
   __shared__ uint32_t tmem_slot;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane == 5) mbar_init(&cbar, 1);
     else if (lane == 6) mbar_init(&b_full[2], 64);
     else if (lane == 7) mbar_init(&b_empty[2], 1);
+    else if (lane == 8) mbar_init(&started, kPGatherThreads);
     fence_mbar_init();
   }
   {
@@ -279,6 +281,12 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           make_uint4(0, 0, 0, 0);
     }
   }
+  // The gate tables P_t | Q_t (T x 256 bytes) go through shared memory - the X operand tile, unused until the
+  // first top MLP - so that an SM reads them from L2 once, not once per consumer thread (4x): at launch every SM
+  // asks for the same lines, and whatever the L2 has to serve then delays the first history tile.
+  for (int i = tid; i < T * 16; i += kPThreads)
+    cp_async16(base + PO_XB + i * 16, reinterpret_cast<const uint8_t*>(p.pq) + i * 16);
+  cp_async_commit();
   // groups 0 and 1 are staged by everybody (nobody has anything else to do yet); warps 6 / 7 take the rows
   if (n_my > 0) {
     if (warp == 6) stage_rows(0);
@@ -289,6 +297,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       if (n_my > 1) stage_hist(1, ti, kPThreads - 64);
     }
   }
+  cp_async_wait<0>();
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -357,6 +366,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         cp_async_commit();
         ++Kg;
         if (Kg - Dg > kPAhead) deliver_oldest();
+        if (Kg == 1) mbar_arrive(&started);                 // the top MLP may now load its weights
         if (j == 0 && k == 0) RTP_TRACE(20, tid == 0);
       }
       mbar_arrive(&stage_free[j & 1]);                     // the ids were read when the copies were issued
@@ -376,6 +386,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       // then, else after it (never WAIT for them first: see rtp_protocol_sim.py, one-tile groups).
       int NT = 0;
       for (int j = 0; j < n_my; ++j) NT += geom(j).n_tiles;
+      RTP_TRACE(26, lane == 0);
       for (int K = -2; K < NT; ++K) {
         const int Kn = K + 2;                               // tile of this iteration's activation-unit MMAs
         const bool has_next = Kn < NT, has_pool = K >= 0;
@@ -411,6 +422,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
               mma_commit(&b_empty[nb]);
             }
             __syncwarp();
+            if (Kn == 0) RTP_TRACE(27, lane == 0);
             if (Kn == 4) RTP_TRACE(15, lane == 0);
             if (Kn == 6) RTP_TRACE(18, lane == 0);
           }
@@ -454,6 +466,12 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         const float4 v = ldg4((part ? p.wpT : p.waT) + pj * 32 + 8 * (cq0 + cc) + 4 * h);
         rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
       }
+      // gate constants cst[r][j] = au_b[j] + sum_e cand[r][e] (Wc - Wsub)[e][j]: this thread keeps the 16 weights of
+      // ITS unit j = pj for ITS half of e (the same split as above) in registers; the two halves meet by one shuffle
+      float wcst[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) wcst[e] = __ldg(p.au_wc + (16 * (bt & 1) + e) * 32 + pj);
+      const float cst_bias = (bt & 1) ? 0.f : __ldg(p.au_b + pj);
       int Kb = 0;
       for (int j = 0; j < n_my; ++j) {
         const GroupGeom g = geom(j);
@@ -482,21 +500,31 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
               *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
               *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
             }
-          // gate constants of the tile: cst[r][jj] = au_b[jj] + sum_e cand[r][e] (Wc - Wsub)[e][jj], thread -> (r, jj).
-          // Slot Kb % 8: the gate of tile Kb - 8 finished before MMA1(Kb - 3) completed (b_empty above).
+          // gate constants of the tile (both rows).  Slot Kb % 8: the gate of tile Kb - 8 finished before
+          // MMA1(Kb - 3) completed (b_empty above).
           {
-            const int cr = bt >> 5, jj = bt & 31;
-            const float* cv = cand + (2 * k + cr) * 32;
-            float acc0 = __ldg(p.au_b + jj), acc1 = 0.f;
+            float a0 = cst_bias, a1 = cst_bias;
+            const float* cv0 = cand + (2 * k) * 32 + 16 * (bt & 1);
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              acc0 = fmaf(cv[e], __ldg(p.au_wc + e * 32 + jj), acc0);
-              acc1 = fmaf(cv[e + 1], __ldg(p.au_wc + (e + 1) * 32 + jj), acc1);
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 x0 = *reinterpret_cast<const float4*>(cv0 + 4 * e4);
+              const float4 x1 = *reinterpret_cast<const float4*>(cv0 + 32 + 4 * e4);
+              a0 = fmaf(x0.x, wcst[4 * e4], a0); a1 = fmaf(x1.x, wcst[4 * e4], a1);
+              a0 = fmaf(x0.y, wcst[4 * e4 + 1], a0); a1 = fmaf(x1.y, wcst[4 * e4 + 1], a1);
+              a0 = fmaf(x0.z, wcst[4 * e4 + 2], a0); a1 = fmaf(x1.z, wcst[4 * e4 + 2], a1);
+              a0 = fmaf(x0.w, wcst[4 * e4 + 3], a0); a1 = fmaf(x1.w, wcst[4 * e4 + 3], a1);
             }
-            cst_all[(Kb % kPCstSlots) * 64 + cr * 32 + jj] = acc0 + acc1;
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);        // lanes bt, bt ^ 1: the two halves of e for unit pj
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            if ((bt & 1) == 0) {
+              cst_all[(Kb % kPCstSlots) * 64 + pj] = a0;
+              cst_all[(Kb % kPCstSlots) * 64 + 32 + pj] = a1;
+            }
           }
           fence_async_smem();
           mbar_arrive(&b_full[slot]);
+          if (Kb == 0) RTP_TRACE(28, bt == 0);
+          if (Kb == 3) RTP_TRACE(29, bt == 0);
           if (Kb == 4) RTP_TRACE(17, bt == 0);
         }
         mbar_arrive(&stage_free[j & 1]);
@@ -509,10 +537,12 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     const int r_t = warp_w >> 1, t = tw & 63;             // this thread's tile row and position
     float rc[64];                                         // P_t[0..31] | Q_t[0..31] of its position
     {
-      const float* src = p.pq + (size_t)min(t, T - 1) * 64;      // positions >= T: any finite values do (w is forced to 0)
+      // from the copy the prologue left in the X tile region (the top MLP overwrites it after the first group's
+      // tiles, long after this); positions >= T: any finite values do (w is forced to 0)
+      const float* src = reinterpret_cast<const float*>(base + PO_XB) + (size_t)min(t, T - 1) * 64;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float4 v = ldg4(src + 4 * i);
+        const float4 v = *reinterpret_cast<const float4*>(src + 4 * i);
         rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
       }
     }
@@ -624,6 +654,9 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     RTP_TRACE(4 + 7 * q, tw == 0);
   } else {
     // =================================== top MLP (wg == 4) ===================================
+    // Its weights (48 KB + 32 KB per SM, the same lines for every SM) are not needed before the first group's
+    // tiles are done: ask for them only once the first history tile has been requested.
+    rtp_wait(&started, 0, 15);
     // W1^T -> tensor memory (A operand): this thread's lane = unit tw, 96 packed bf16 pairs
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.w1_tmem + (size_t)tw * 96);
