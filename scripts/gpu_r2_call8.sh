@@ -1,5 +1,5 @@
-mkdir -p gpurun_out/r2c8
-O=gpurun_out/r2c8
+mkdir -p gpurun_out/r2c9
+O=gpurun_out/r2c9
 timeout -k 5 200 python -m pytest tests/test_gpu_parity.py -k "rtp" -q -x --timeout 40 > $O/rtp_tests.log 2>&1; RTP=$?; echo "rtp tests rc=$RTP"; tail -8 $O/rtp_tests.log
 if [ $RTP -eq 0 ]; then
   for lim in 0 74; do SRS_DIN_IMPL=rtp timeout -k 5 50 python profiles/trace_din_rt.py 4096 $lim > $O/trace_rtp_$lim.txt 2>&1; echo "trace $lim rc=$?"; tail -4 $O/trace_rtp_$lim.txt | head -1; done
