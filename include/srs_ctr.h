@@ -284,6 +284,11 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
  * out.  No effect on results. */
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40);
 
+/* din_rtp_kernel only, with tracing enabled (srs_debug_din_trace): per-tile SM-clock timestamps of CTA 0,
+ * out512[kind * 64 + tile], kinds 0 gather issued, 1 delivered, 2 weight operand built, 3 activation-unit
+ * MMAs issued, 4 consumer sees the accumulators, 5 gate done, 6 pooling MMAs issued, 7 pooled rows read. */
+int srs_debug_din_timeline(srs_model* m, uint64_t* out512);
+
 /* Micro-benchmark behind the DIN kernel's MMA shape choice: SM cycles for a chain of n_mma
  * tcgen05.mma (M = 128, K = 16 bf16) with N in {32, 64, 128}, A from shared (0) or tensor (1)
  * memory, into one accumulator (two_acc bit 0 = 0) or alternating two (bit 0 = 1); bit 1 of

@@ -49,3 +49,16 @@ for rep in range(3):
             23: "p.tile2_built", 17: "c.d2_ready(warp1)", 18: "c.synced(warp1)", 24: "x_built", 25: "l1_issued", 30: "p0.rows_requested", 31: "p0.ids_stored", 32: "p0.pads_zeroed", 33: "p0.sync1", 34: "p0.gathers_issued", 35: "p0.cand_stored"}
     print("   second tile of consumer 0 / producer 0 (cycles since entry): " +
           " ".join("%s=%d" % (fine[i], t[i] - t[0]) for i in sorted(fine) if t[i]))
+
+if m.kernel_name == "din_rtp_kernel":
+    tl = (C.c_uint64 * 512)()
+    _lib.check(lib.srs_debug_din_timeline(m._h, tl))
+    a = np.array(tl[:], dtype=np.int64).reshape(8, 64)
+    t0 = int(np.array(buf[:], dtype=np.int64)[0])
+    kinds = ["issued", "delivered", "B_built", "mma1", "c_d1", "gate_done", "pool_mma", "pooled"]
+    print("per-tile timeline of CTA 0 (cycles since kernel entry)")
+    print("tile " + " ".join("%9s" % k for k in kinds))
+    for K in range(64):
+        if a[0, K] == 0:
+            break
+        print("%4d " % K + " ".join("%9d" % (a[i, K] - t0 if a[i, K] else -1) for i in range(8)))

@@ -42,7 +42,7 @@ EXPORTS = ("srs_abi_version", "srs_last_error", "srs_model_create", "srs_model_c
            "srs_cosine_scores_device", "srs_topk_device", "srs_rank_host", "srs_gather_create", "srs_gather_export",
            "srs_gather_connect", "srs_gather_destroy", "srs_predict_device_gather", "srs_gather_wait",
            "srs_gather_scores", "srs_gather_copy_scores", "srs_model_set_movie_features", "srs_rank_user_host",
-           "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_umma_bench")
+           "srs_selftest_umma", "srs_debug_din_trace", "srs_debug_din_timeline", "srs_debug_umma_bench")
 
 _lib = None
 
@@ -142,6 +142,8 @@ def load():
                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.srs_debug_din_trace.restype = C.c_int
     lib.srs_debug_din_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.srs_debug_din_timeline.restype = C.c_int
+    lib.srs_debug_din_timeline.argtypes = [C.c_void_p, C.c_void_p]
     lib.srs_debug_umma_bench.restype = C.c_int
     lib.srs_debug_umma_bench.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.srs_selftest_umma.restype = C.c_int

@@ -78,6 +78,13 @@ constexpr uint32_t PT_TOP = 320;                             // top-MLP accumula
 constexpr uint32_t PT_W1HI = 384, PT_W1LO = 432;             // W1^T as A operand: 48 + 48 columns (96 bf16 of K each)
 
 __device__ unsigned long long g_din_rtp_trace[40];
+// per-tile timeline of CTA 0 (debug): [kind][tile K < 64]; kinds: 0 gather issued, 1 delivered, 2 B built,
+// 3 MMA1 issued, 4 consumer sees D1, 5 gate done (w_ready), 6 pooling MMAs issued, 7 pooled read back
+__device__ unsigned long long g_din_rtp_tl[8 * 64];
+#define RTP_TL(kind, K, cond)                                                                   \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (K) < 64 && (cond)) g_din_rtp_tl[(kind) * 64 + (K)] = clock64(); \
+  } while (0)
 #define RTP_TRACE(slot, cond)                                                     \
   do {                                                                            \
     if (p.trace && blockIdx.x == 0 && (cond)) g_din_rtp_trace[slot] = clock64();  \
@@ -322,6 +329,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       fence_async_smem();
       if (Dg == 0) RTP_TRACE(24, tid == 0);
       if (Dg == 6) RTP_TRACE(25, tid == 0);
+      RTP_TL(1, Dg, tid == 0);
       mbar_arrive(&a_full[Dg % kPSlotsA]);
       ++Dg;
     };
@@ -364,6 +372,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           }
         }
         cp_async_commit();
+        RTP_TL(0, Kg, tid == 0);
         ++Kg;
         if (Kg - Dg > kPAhead) deliver_oldest();
         if (Kg == 1) mbar_arrive(&started);                 // the top MLP may now load its weights
@@ -422,6 +431,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
               mma_commit(&b_empty[nb]);
             }
             __syncwarp();
+            RTP_TL(3, Kn, lane == 0);
             if (Kn == 0) RTP_TRACE(27, lane == 0);
             if (Kn == 4) RTP_TRACE(15, lane == 0);
             if (Kn == 6) RTP_TRACE(18, lane == 0);
@@ -442,6 +452,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
               mma_commit(&a_empty[sa]);
             }
             __syncwarp();
+            RTP_TL(6, K, lane == 0);
             if (K == 4) RTP_TRACE(16, lane == 0);
           }
         }
@@ -523,6 +534,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           }
           fence_async_smem();
           mbar_arrive(&b_full[slot]);
+          RTP_TL(2, Kb, bt == 0);
           if (Kb == 0) RTP_TRACE(28, bt == 0);
           if (Kb == 3) RTP_TRACE(29, bt == 0);
           if (Kb == 4) RTP_TRACE(17, bt == 0);
@@ -575,6 +587,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         pooled[(2 * pend_k + 1) * 64 + m] = hi ? __uint_as_float(d[8]) + __uint_as_float(d[9]) : __uint_as_float(d[8]);
       }
       tc_fence_before();
+      RTP_TL(7, pend_K, tw == 0);
       if (pend_last) mbar_arrive(&pooled_ready[pend_j & 1]);
       pend = false;
     };
@@ -592,6 +605,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         tc_fence_after();
         if (K == q) RTP_TRACE(3 + 7 * q, tw == 0);
         if (K == 4) RTP_TRACE(12, tw == 0);
+        RTP_TL(4, K, tw == 0);
         // ---- gate: v = D_hi + D_lo + cst; s = sum_j v_j P_tj + |v_j| Q_tj
         float2 sa = make_float2(p.au_bout, 0.f), sb = make_float2(0.f, 0.f);
         {
@@ -637,6 +651,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(&w_ready[q][u]);
+        RTP_TL(5, K, tw == 0);
         if (K == 4) RTP_TRACE(13, tw == 0);
         if (pend) pool_out();                               // the previous own tile's pooling MMAs finished long ago
         if (K == 4) RTP_TRACE(14, tw == 0);
@@ -882,6 +897,9 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
 
 cudaError_t read_din_rtp_trace(unsigned long long* out40) {
   return cudaMemcpyFromSymbol(out40, g_din_rtp_trace, sizeof(unsigned long long) * 40);
+}
+cudaError_t read_din_rtp_timeline(unsigned long long* out512) {
+  return cudaMemcpyFromSymbol(out512, g_din_rtp_tl, sizeof(unsigned long long) * 512);
 }
 
 // Did a wait of an earlier launch time out (see rtp_wait)?  Copies the record {code, block, thread,

@@ -1975,6 +1975,15 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   return SRS_OK;
 }
 
+int srs_debug_din_timeline(srs_model* m, uint64_t* out512) {
+  if (!m || !out512) return fail(SRS_ERR_INVALID, "null argument");
+  if (!m->use_din_rtp) return fail(SRS_ERR_INVALID, "the per-tile timeline exists for din_rtp_kernel only");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(read_din_rtp_timeline(reinterpret_cast<unsigned long long*>(out512)));
+  return SRS_OK;
+}
+
 int srs_debug_umma_bench(int32_t N, int32_t n_mma, int32_t a_in_tmem, int32_t two_acc,
                          int32_t device, uint64_t* out2) {
   if (!out2 || (N != 32 && N != 64 && N != 128) || n_mma < 1 || n_mma > 4096)
