@@ -285,8 +285,9 @@ int srs_rank_user_host(srs_model* m, const srs_user_row* user, const int32_t* ca
 int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40);
 
 /* din_rtp_kernel only, with tracing enabled (srs_debug_din_trace): per-tile SM-clock timestamps of CTA 0,
- * out512[kind * 64 + tile], kinds 0 gather issued, 1 delivered, 2 weight operand built, 3 activation-unit
- * MMAs issued, 4 consumer sees the accumulators, 5 gate done, 6 pooling MMAs issued, 7 pooled rows read. */
+ * out[kind * 64 + tile] (12 x 64 values), kinds 0 gather issued, 1 delivered, 2 weight operand built, 3 activation-unit
+ * MMAs issued, 4 consumer sees the accumulators, 5 gate done, 6 pooling MMAs issued, 7 pooled rows read,
+ * 8-11 inside the issuer (wait passed, MMAs issued, commits done, iteration start). */
 int srs_debug_din_timeline(srs_model* m, uint64_t* out512);
 
 /* Micro-benchmark behind the DIN kernel's MMA shape choice: SM cycles for a chain of n_mma

@@ -39,7 +39,7 @@ class Sim:
         self.rng = random.Random(seed)
         self.groups = groups                      # tiles per group of this CTA
         b = Bar
-        self.a_full = [b("a_full%d" % i, 256) for i in range(NSA)]
+        self.a_full = [b("a_full%d" % i, 224) for i in range(NSA)]
         self.a_empty = [b("a_empty%d" % i, 1) for i in range(NSA)]
         self.b_full = [b("b_full%d" % i, 64) for i in range(NSB)]
         self.b_empty = [b("b_empty%d" % i, 1) for i in range(NSB)]
@@ -48,7 +48,7 @@ class Sim:
         self.w_ready = [[b("w_ready%d%d" % (q, u), 128) for u in range(2)] for q in range(2)]
         self.d2_full = [[b("d2_full%d%d" % (q, u), 1) for u in range(2)] for q in range(2)]
         self.staged = [b("staged%d" % i, 32) for i in range(2)]
-        self.stage_free = [b("stage_free%d" % i, 704) for i in range(2)]
+        self.stage_free = [b("stage_free%d" % i, 672) for i in range(2)]
         self.pooled_ready = [b("pooled_ready%d" % i, 256) for i in range(2)]
         self.pooled_free = [b("pooled_free%d" % i, 128) for i in range(2)]
         self.cbar = b("cbar", 1)
@@ -89,7 +89,7 @@ class Sim:
         for j, n_tiles in enumerate(self.groups):
             if j >= 2 and not self.staged[j & 1].passed(((j >> 1) - 1) & 1):
                 while Dg < Kg:                                 # the loader is late: deliver what has landed first
-                    self.a_full[Dg % NSA].arrive(256)
+                    self.a_full[Dg % NSA].arrive(224)
                     Dg += 1
                     yield
             yield from self.staged_wait(j)
@@ -99,20 +99,20 @@ class Sim:
                     par = ((Kg // NSA) + 1) & 1
                     while not self.a_empty[slot].passed(par):          # publish landed tiles before blocking
                         if Dg < Kg:
-                            self.a_full[Dg % NSA].arrive(256)
+                            self.a_full[Dg % NSA].arrive(224)
                             Dg += 1
                         yield
                     yield from self.wait(self.a_empty[slot], par, Kg // NSA - 1)
                 self.touch("A%d" % slot, "cp.async into the tile")
                 Kg += 1
                 if Kg - Dg > AHEAD:
-                    self.a_full[Dg % NSA].arrive(256)
+                    self.a_full[Dg % NSA].arrive(224)
                     Dg += 1
                 yield
-            self.stage_free[j & 1].arrive(256)
+            self.stage_free[j & 1].arrive(224)
             yield
         while Dg < Kg:
-            self.a_full[Dg % NSA].arrive(256)
+            self.a_full[Dg % NSA].arrive(224)
             Dg += 1
             yield
         self.finished.add("g")
@@ -134,13 +134,13 @@ class Sim:
             yield
         self.finished.add("b")
 
-    def issuer(self):
+    def issuer_mma1(self):                       # warp 4
         NT = sum(self.groups)
-
-        def mma1(K):
-            sa, sb, q = K % NSA, K % NSB, K & 1
-            yield from self.wait(self.a_full[sa], (K // NSA) & 1, K // NSA)
-            yield from self.wait(self.b_full[sb], (K // NSB) & 1, K // NSB)
+        sa = sb = pa = pb = 0
+        for K in range(NT):
+            q = K & 1
+            yield from self.wait(self.a_full[sa], pa, K // NSA)
+            yield from self.wait(self.b_full[sb], pb, K // NSB)
             if K >= 2:
                 yield from self.wait(self.d1_free[q], ((K >> 1) - 1) & 1, (K >> 1) - 1)
             self.touch("D1_%d" % q, "MMA1 overwrites the accumulators")
@@ -148,31 +148,27 @@ class Sim:
             self.commit(self.d1_full[q])
             self.commit(self.b_empty[sb])
             yield
-        if NT > 0:
-            yield from mma1(0)
-        if NT > 1:
-            yield from mma1(1)
-        def ready(K):                      # every operand of mma1(K) is there already (try_wait on all three)
-            sa, sb, q = K % NSA, K % NSB, K & 1
-            return (self.a_full[sa].passed((K // NSA) & 1) and self.b_full[sb].passed((K // NSB) & 1)
-                    and (K < 2 or self.d1_free[q].passed(((K >> 1) - 1) & 1)))
+            sa += 1
+            if sa == NSA:
+                sa, pa = 0, pa ^ 1
+            sb += 1
+            if sb == NSB:
+                sb, pb = 0, pb ^ 1
+        self.finished.add("i1")
+
+    def issuer_pool(self):                       # warp 5
+        NT = sum(self.groups)
+        sa = 0
         for K in range(NT):
-            sa, q, u = K % NSA, K & 1, (K >> 1) & 1
-            early = not (K + 2 < NT)               # "next_issued" of the kernel
-            while not self.w_ready[q][u].passed((K >> 2) & 1):     # poll both conditions
-                if not early and ready(K + 2):
-                    yield from mma1(K + 2)
-                    early = True
-                yield
+            q, u = K & 1, (K >> 1) & 1
             yield from self.wait(self.w_ready[q][u], (K >> 2) & 1, K >> 2)
             self.touch("D2_%d%d" % (q, u), "pooling MMA overwrites accumulators")
             self.issue_mma(["A%d" % sa, "W%d%d" % (q, u), "D2_%d%d" % (q, u)])
             self.commit(self.d2_full[q][u])
             self.commit(self.a_empty[sa])
             yield
-            if not early:
-                yield from mma1(K + 2)
-        self.finished.add("i")
+            sa = (sa + 1) % NSA
+        self.finished.add("i2")
 
     def loader(self):
         for j in range(2, len(self.groups)):
@@ -284,7 +280,7 @@ class Sim:
 
     # ---- scheduler --------------------------------------------------------------------------------
     def run(self, max_steps=400000):
-        actors = {"g": self.gatherers(), "b": self.builders(), "i": self.issuer(), "l": self.loader(),
+        actors = {"g": self.gatherers(), "b": self.builders(), "i1": self.issuer_mma1(), "i2": self.issuer_pool(), "l": self.loader(),
                   "c0": self.consumer(0), "c1": self.consumer(1), "t": self.top()}
         pipe = self.tensor_pipe()
         names = list(actors)

@@ -51,14 +51,14 @@ for rep in range(3):
           " ".join("%s=%d" % (fine[i], t[i] - t[0]) for i in sorted(fine) if t[i]))
 
 if m.kernel_name == "din_rtp_kernel":
-    tl = (C.c_uint64 * 512)()
+    tl = (C.c_uint64 * 768)()
     _lib.check(lib.srs_debug_din_timeline(m._h, tl))
-    a = np.array(tl[:], dtype=np.int64).reshape(8, 64)
+    a = np.array(tl[:], dtype=np.int64).reshape(12, 64)
     t0 = int(np.array(buf[:], dtype=np.int64)[0])
-    kinds = ["issued", "delivered", "B_built", "mma1", "c_d1", "gate_done", "pool_mma", "pooled"]
+    kinds = ["issued", "delivered", "B_built", "mma1", "c_d1", "gate_done", "pool_mma", "pooled", "i.waited", "i.mmas", "-", "i.iter"]
     print("per-tile timeline of CTA 0 (cycles since kernel entry)")
     print("tile " + " ".join("%9s" % k for k in kinds))
     for K in range(64):
         if a[0, K] == 0:
             break
-        print("%4d " % K + " ".join("%9d" % (a[i, K] - t0 if a[i, K] else -1) for i in range(8)))
+        print("%4d " % K + " ".join("%9d" % (a[i, K] - t0 if a[i, K] else -1) for i in range(12)))

@@ -60,7 +60,8 @@ class SrsError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # SRS_CTR_LIB: an alternative build of the library (kernel-tuning experiments: profiles/exp/build_variants.py)
+    return os.environ.get("SRS_CTR_LIB") or _build.LIB
 
 
 def load():

@@ -45,7 +45,7 @@ constexpr int kPSlotsA = 6;                 // history tiles in flight or being 
 constexpr int kPSlotsB = 3;                 // per-row weight operands
 constexpr int kPCstSlots = 8;               // per-tile constants of the gate (see the builders)
 constexpr int kPAhead = 3;                  // tiles a gatherer keeps in flight before it delivers one
-constexpr int kPGatherThreads = 256;
+constexpr int kPGatherThreads = 224;        // warps 0-3 and 20-22
 constexpr int kPIdsLd = 64;                 // ints per row of the staged history ids
 
 // shared memory (offsets from the 1024-aligned base)
@@ -80,45 +80,63 @@ constexpr uint32_t PT_W1HI = 384, PT_W1LO = 432;             // W1^T as A operan
 __device__ unsigned long long g_din_rtp_trace[40];
 // per-tile timeline of CTA 0 (debug): [kind][tile K < 64]; kinds: 0 gather issued, 1 delivered, 2 B built,
 // 3 MMA1 issued, 4 consumer sees D1, 5 gate done (w_ready), 6 pooling MMAs issued, 7 pooled read back
-__device__ unsigned long long g_din_rtp_tl[8 * 64];
+__device__ unsigned long long g_din_rtp_tl[12 * 64];   // + 8 issuer: pool wait passed, 9 pool MMAs issued, 10 pool commits done, 11 iteration start
+#ifdef RTP_TIMELINE
 #define RTP_TL(kind, K, cond)                                                                   \
   do {                                                                                          \
     if (p.trace && blockIdx.x == 0 && (K) < 64 && (cond)) g_din_rtp_tl[(kind) * 64 + (K)] = clock64(); \
   } while (0)
+#else
+#define RTP_TL(kind, K, cond) do { } while (0)
+#endif
+// Tracing is compiled in only with -DRTP_TIMELINE (profiles/exp/build_variants.py): every probe costs the
+// single-warp roles (issuers, builders) a few dependent instructions per tile, and those roles are latency-
+// bound on their own instruction stream (~8 cycles per instruction: ncu / timeline of round 2).
+#ifdef RTP_TIMELINE
 #define RTP_TRACE(slot, cond)                                                     \
   do {                                                                            \
     if (p.trace && blockIdx.x == 0 && (cond)) g_din_rtp_trace[slot] = clock64();  \
   } while (0)
+#else
+#define RTP_TRACE(slot, cond) do { } while (0)
+#endif
 
 // Every mbarrier wait of this kernel goes through rtp_wait: a wait that lasts longer than any
 // legitimate one (2^28 cycles = 0.14 s) records who waited for what and raises g_din_rtp_abort, after
 // which every wait in the grid returns at once - a protocol error ends the launch with wrong scores
 // and a diagnosis (srs_model_status / srs_debug_din_trace slots 32..36) instead of hanging the GPU.
 __device__ unsigned int g_din_rtp_abort;
-__device__ __forceinline__ void rtp_wait_slow(uint64_t* bar, uint32_t parity, int code) {
-  const long long t0 = clock64();
+// SLEEP_NS > 0: back off between polls (waits that are not latency-critical - the top MLP waiting for a whole
+// group of tiles, the loader - would otherwise keep the SM's barrier unit and issue slots busy for nothing).
+__device__ __forceinline__ void rtp_record_timeout(int code, uint32_t parity) {
+  if (atomicCAS(&g_din_rtp_abort, 0u, 1u) == 0u) {
+    g_din_rtp_trace[32] = 1ull;
+    g_din_rtp_trace[33] = (unsigned long long)code;
+    g_din_rtp_trace[34] = (unsigned long long)blockIdx.x;
+    g_din_rtp_trace[35] = (unsigned long long)threadIdx.x;
+    g_din_rtp_trace[36] = (unsigned long long)parity;
+    __threadfence();
+  }
+}
+template <int SLEEP_NS>
+__device__ __forceinline__ void rtp_wait_loop(uint64_t* bar, uint32_t parity, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0) {
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++spins & 1023u) == 0) {
       if (*reinterpret_cast<volatile unsigned int*>(&g_din_rtp_abort)) return;
-      if (clock64() - t0 > (1ll << 28)) {
-        if (atomicCAS(&g_din_rtp_abort, 0u, 1u) == 0u) {
-          g_din_rtp_trace[32] = 1ull;
-          g_din_rtp_trace[33] = (unsigned long long)code;
-          g_din_rtp_trace[34] = (unsigned long long)blockIdx.x;
-          g_din_rtp_trace[35] = (unsigned long long)threadIdx.x;
-          g_din_rtp_trace[36] = (unsigned long long)parity;
-          __threadfence();
-        }
+      if (spins >= (SLEEP_NS > 0 ? (1u << 19) : (1u << 24))) {       // far beyond any legitimate wait
+        rtp_record_timeout(code, parity);
         return;
       }
     }
   }
 }
-__device__ __forceinline__ void rtp_wait(uint64_t* bar, uint32_t parity, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  rtp_wait_slow(bar, parity, code);
-}
+// (an out-of-line watchdog loop would keep the hot loops smaller, but one call anywhere in the kernel makes
+// ptxas fail to allocate the consumers' 120 registers)
+__device__ __forceinline__ void rtp_wait(uint64_t* bar, uint32_t parity, int code) { rtp_wait_loop<0>(bar, parity, code); }
+__device__ __forceinline__ void rtp_wait_lazy(uint64_t* bar, uint32_t parity, int code) { rtp_wait_loop<200>(bar, parity, code); }
+__device__ __forceinline__ void rtp_wait_inl(uint64_t* bar, uint32_t parity, int code) { rtp_wait_loop<0>(bar, parity, code); }
 
 __device__ __forceinline__ void rtp_store_x4(uint8_t* tile, int block, int row, int col, float4 v) {
   const uint32_t off = block * 8192u + sw128_offset(row, col >> 3) + ((col & 4) ? 8u : 0u);
@@ -143,7 +161,7 @@ struct GroupGeom {
 __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_constant__ DinRtParams p,
                                                                BatchView b) {
   extern __shared__ uint8_t raw[];
-  __shared__ uint64_t a_full[kPSlotsA];     // history rows of the tile have landed (256 gatherer arrivals)
+  __shared__ uint64_t a_full[kPSlotsA];     // history rows of the tile have landed (224 gatherer arrivals)
   __shared__ uint64_t a_empty[kPSlotsA];    // the pooling MMAs reading the slot have completed
   __shared__ uint64_t b_full[kPSlotsB];     // weight operand built (64 builder arrivals)
   __shared__ uint64_t b_empty[kPSlotsB];    // the activation-unit MMAs reading it have completed
@@ -152,7 +170,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   __shared__ uint64_t w_ready[2][2];        // consumer q, buffer u: pooling weights written (128 arrivals)
   __shared__ uint64_t d2_full[2][2];        // consumer q, buffer u: pooled accumulators ready
   __shared__ uint64_t staged[2];            // staging buffer s holds the ids / candidate rows of a group (32 arrivals)
-  __shared__ uint64_t stage_free[2];        // every reader of staging buffer s is done with it (704 arrivals)
+  __shared__ uint64_t stage_free[2];        // every reader of staging buffer s is done with it (672 arrivals)
   __shared__ uint64_t pooled_ready[2];      // pooled rows of the group in buffer s are complete (256 arrivals)
   __shared__ uint64_t pooled_free[2];       // the top MLP has read them (128 arrivals)
   __shared__ uint64_t started;              // the gatherers have requested their first tile (256 arrivals, once)
@@ -234,18 +252,16 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       if (mg < 0) mg = -1;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p.user + (size_t)uid * 32));
     }
-    float4 c4[8];
+    // candidate row: 8 x 16-byte cp.async (no registers; the chunk order is rotated per lane so that the
+    // 32 rows, 128 bytes apart, do not hit the same banks); the caller commits / waits
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4)
-      c4[q4] = live ? ldg4(p.movie + (size_t)cid * 32 + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {                          // rotate the chunk per lane: conflict-free stores
+    for (int q4 = 0; q4 < 8; ++q4) {
       const int qq = (q4 + lane) & 7;
-      float4 v = c4[0];
-#pragma unroll
-      for (int z = 1; z < 8; ++z) if (qq == z) v = c4[z];
-      *reinterpret_cast<float4*>(cand + lane * 32 + 4 * qq) = v;
+      if (live) cp_async16(cand + lane * 32 + 4 * qq, p.movie + (size_t)cid * 32 + 4 * qq);
+      else *reinterpret_cast<float4*>(cand + lane * 32 + 4 * qq) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     *reinterpret_cast<float4*>(nums + lane * 8) = make_float4(nv[0], nv[1], nv[2], nv[3]);
     *reinterpret_cast<float4*>(nums + lane * 8 + 4) = make_float4(nv[4], nv[5], nv[6], 0.f);
     *reinterpret_cast<int4*>(sid + lane * 4) = make_int4(ug, mg, uid, 0);
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane < 24) mbar_init(&w_ready[(lane - 20) >> 1][(lane - 20) & 1], 128);
     else if (lane < 28) mbar_init(&d2_full[(lane - 24) >> 1][(lane - 24) & 1], 1);
     else if (lane < 30) mbar_init(&staged[lane - 28], 32);
-    else if (lane < 32) mbar_init(&stage_free[lane - 30], 256 + 64 + 256 + 128);
+    else if (lane < 32) mbar_init(&stage_free[lane - 30], kPGatherThreads + 64 + 256 + 128);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -316,14 +332,24 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   const int first_loader_group = 2;
   // parity helpers: the n-th completion (n = 0, 1, ...) of an mbarrier is observed with parity n & 1
   auto staged_wait = [&](int j) { if (j >= first_loader_group) rtp_wait(&staged[j & 1], ((j >> 1) - 1) & 1, 1); };
+  auto staged_wait_inl = [&](int j) { if (j >= first_loader_group) rtp_wait_inl(&staged[j & 1], ((j >> 1) - 1) & 1, 1); };
 
   if (wg == 0 || wg == 5) {
-    // =================================== gatherers =========================================
     reg_dec<40>();
+    if (warp == 23) {
+      // =================================== loader ==========================================
+      for (int j = first_loader_group; j < n_my; ++j) {
+        rtp_wait_lazy(&stage_free[j & 1], ((j >> 1) - 1) & 1, 7);  // every reader of group j - 2 is done
+        stage_rows(j);
+        stage_hist(j, lane, 32);
+        mbar_arrive(&staged[j & 1]);
+      }
+    } else {
+    // =================================== gatherers (warps 0-3, 20-22) =========================
     RTP_TRACE(21, tid == 0);
-    const int gt = wg == 0 ? tid : tid - 512;              // 0..255
+    const int gt = wg == 0 ? tid : tid - 512;              // 0..223
     const uint32_t c = (uint32_t)(gt & 7);
-    const int cell0 = gt >> 3;
+    const int cell0 = gt >> 3;                             // 0..27; copy n of a tile moves cell cell0 + 28 n
     int Kg = 0, Dg = 0;
     auto deliver_one = [&]() {                             // the oldest outstanding tile HAS landed: publish it
       fence_async_smem();
@@ -363,8 +389,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         uint8_t* A = ringA + slot * PA_SLOT;
         const int* idrow = ids + 2 * k * kPIdsLd;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int cell = cell0 + 32 * n;
+        for (int n = 0; n < 5; ++n) {
+          const int cell = cell0 + (kPGatherThreads / 8) * n;
           if (cell < 2 * T) {
             const int r = cell >= T ? 1 : 0, pos = cell - r * T;
             cp_async16(A + (uint32_t)(r * 64 + pos) * 128u + ((c ^ (uint32_t)(pos & 7)) << 4),
@@ -382,88 +408,67 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     }
     cp_async_wait<0>();
     while (Dg < Kg) deliver_one();
+    }
   } else if (wg == 1) {
     // registers: the CTA's pool is what it was LAUNCHED with (768 x 80): 480 per thread slot = 40 + 40 + 80 + 120 + 120 + 80;
     // this warpgroup and the top-MLP one keep the 80 they were launched with
     if (warp == 4) {
-      // =================================== issuer ==========================================
-      // ONE textual site per MMA group inside one loop: when the activation-unit group was a lambda called from
-      // three places, the compiler kept a single out-of-line copy whose descriptors lived in vector registers and
-      // reached the tensor core through predicated R2UR moves - about 1 K cycles per tile instead of back-to-back
-      // UTCHMMA (ncu, round 2).  Loop index K is the tile whose pooling MMAs are issued; the activation-unit MMAs
-      // of tile K + 2 go out in the same iteration, before the pooling group if their operands are in place by
-      // then, else after it (never WAIT for them first: see rtp_protocol_sim.py, one-tile groups).
+      // ============================ issuer of the activation-unit MMAs ==========================
+      // Two issuer warps (this one and warp 5): one warp issuing both MMA groups of every tile in order needed
+      // ~1.4 K cycles per tile - it is latency-bound on its own dependent instruction stream (~8 cycles per
+      // instruction), not on the tensor pipe - and, being in order, it could deadlock one-tile groups.  The
+      // two streams are independent: this one needs the tile, its weight operand and the accumulator buffer.
+      // Slot counters and phase bits are kept incrementally: no division in the loop.
       int NT = 0;
       for (int j = 0; j < n_my; ++j) NT += geom(j).n_tiles;
-      RTP_TRACE(26, lane == 0);
-      for (int K = -2; K < NT; ++K) {
-        const int Kn = K + 2;                               // tile of this iteration's activation-unit MMAs
-        const bool has_next = Kn < NT, has_pool = K >= 0;
-        const int sa = has_pool ? K % kPSlotsA : 0, q = K & 1, u = (K >> 1) & 1;
-        const int na = Kn % kPSlotsA, nb = Kn % kPSlotsB, nq = Kn & 1;
-        bool before = !has_pool;                            // tiles 0 and 1: nothing to pool yet
-        if (has_pool && has_next) {
-          for (uint32_t spins = 0; spins < (1u << 22); ++spins) {   // poll both; then the watchdog waits below
-            const int r = mbar_test_wait(&a_full[na], (Kn / kPSlotsA) & 1) && mbar_test_wait(&b_full[nb], (Kn / kPSlotsB) & 1) &&
-                          (Kn < 2 || mbar_test_wait(&d1_free[nq], ((Kn >> 1) - 1) & 1));
-            const int w = mbar_test_wait(&w_ready[q][u], (K >> 2) & 1);
-            const unsigned both = __shfl_sync(0xffffffffu, (unsigned)(r | (w << 1)), 0);
-            if (both & 1u) { before = true; break; }
-            if (both & 2u) break;
-          }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int K = 0; K < NT; ++K) {
+        const int q = K & 1;
+        rtp_wait(&a_full[sa], pa, 3);
+        rtp_wait(&b_full[sb], pb, 4);
+        if (K >= 2) rtp_wait(&d1_free[q], ((K >> 1) - 1) & 1, 5);   // the accumulators of tile K - 2 are in registers
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tD1 = tbase + PT_D1 + 128u * q;
+          const uint64_t ad = smem_desc_sw128(s_ringA + sa * PA_SLOT);
+          const uint64_t bd = smem_desc_sw64(s_ringB + sb * PB_SLOT);
+          mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
+          mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
+          mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
+          mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
+          mma_commit(&d1_full[q]);
+          mma_commit(&b_empty[sb]);
         }
-#pragma unroll
-        for (int phase = 0; phase < 2; ++phase) {
-          if (has_next && (phase == 0) == before) {
-            rtp_wait(&a_full[na], (Kn / kPSlotsA) & 1, 3);
-            rtp_wait(&b_full[nb], (Kn / kPSlotsB) & 1, 4);
-            if (Kn >= 2) rtp_wait(&d1_free[nq], ((Kn >> 1) - 1) & 1, 5);   // the accumulators of tile Kn - 2 are in registers
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t tD1 = tbase + PT_D1 + 128u * nq;
-              const uint64_t ad = smem_desc_sw128(s_ringA + na * PA_SLOT);
-              const uint64_t bd = smem_desc_sw64(s_ringB + nb * PB_SLOT);
-              mma_ss(tD1, ad + 0, bd + 0, idesc_bf16(128, 128), 0);     // H_hi . [W_hi | W_lo]
-              mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
-              mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
-              mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
-              mma_commit(&d1_full[nq]);
-              mma_commit(&b_empty[nb]);
-            }
-            __syncwarp();
-            RTP_TL(3, Kn, lane == 0);
-            if (Kn == 0) RTP_TRACE(27, lane == 0);
-            if (Kn == 4) RTP_TRACE(15, lane == 0);
-            if (Kn == 6) RTP_TRACE(18, lane == 0);
-          }
-          if (phase == 0 && has_pool) {
-            rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t tD2 = tbase + PT_D2 + 32u * q + 16u * u;
-              const uint32_t s_b2 = smem_u32(b2s) + (q * 2 + u) * 2048;
-#pragma unroll
-              for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ringA + sa * PA_SLOT + r * 8192 + ks * 2048),
-                         smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
-              mma_commit(&d2_full[q][u]);
-              mma_commit(&a_empty[sa]);
-            }
-            __syncwarp();
-            RTP_TL(6, K, lane == 0);
-            if (K == 4) RTP_TRACE(16, lane == 0);
-          }
-        }
+        __syncwarp();
+        RTP_TL(3, K, lane == 0);
+        if (++sa == kPSlotsA) { sa = 0; pa ^= 1u; }
+        if (++sb == kPSlotsB) { sb = 0; pb ^= 1u; }
       }
     } else if (warp == 5) {
-      // =================================== loader ==========================================
-      for (int j = first_loader_group; j < n_my; ++j) {
-        rtp_wait(&stage_free[j & 1], ((j >> 1) - 1) & 1, 7);  // every reader of group j - 2 is done
-        stage_rows(j);
-        stage_hist(j, lane, 32);
-        mbar_arrive(&staged[j & 1]);
+      // ============================ issuer of the pooling MMAs ==================================
+      int NT = 0;
+      for (int j = 0; j < n_my; ++j) NT += geom(j).n_tiles;
+      int sa = 0;
+      for (int K = 0; K < NT; ++K) {
+        const int q = K & 1, u = (K >> 1) & 1;
+        rtp_wait(&w_ready[q][u], (K >> 2) & 1, 6);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tD2 = tbase + PT_D2 + 32u * q + 16u * u;
+          const uint32_t s_b2 = smem_u32(b2s) + (q * 2 + u) * 2048;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ss(tD2 + 8 * r, smem_desc_mn_sw128(s_ringA + sa * PA_SLOT + r * 8192 + ks * 2048),
+                     smem_desc_sw128(s_b2 + r * 1024) + 2 * ks, idesc_mn(64, 8, 1), ks > 0);
+          mma_commit(&d2_full[q][u]);
+          mma_commit(&a_empty[sa]);
+        }
+        __syncwarp();
+        RTP_TL(6, K, lane == 0);
+        if (++sa == kPSlotsA) sa = 0;
       }
     } else {
       // =================================== builders ========================================
@@ -565,13 +570,13 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     int pool_group = -1;                                  // group this thread last wrote pooled rows of
     auto pooled_buffer_wait = [&](int j) {                // before the first pooled write of group j
       if (pool_group != j) {
-        if (j >= 2) rtp_wait(&pooled_free[j & 1], ((j >> 1) - 1) & 1, 9);
+        if (j >= 2) rtp_wait_inl(&pooled_free[j & 1], ((j >> 1) - 1) & 1, 9);
         pool_group = j;
       }
     };
     auto pool_out = [&]() {
       const int u = (pend_K >> 1) & 1;
-      rtp_wait(&d2_full[q][u], (pend_K >> 2) & 1, 10);
+      rtp_wait_inl(&d2_full[q][u], (pend_K >> 2) & 1, 10);
       tc_fence_after();
       pooled_buffer_wait(pend_j);
       // D2 row m = 16 warp_w + lane (lane < 16): m < 32 -> hi e = m, else lo e = m - 32;
@@ -594,14 +599,14 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     int kbase = 0;
     for (int j = 0; j < n_my; ++j) {
       const GroupGeom g = geom(j);
-      staged_wait(j);
+      staged_wait_inl(j);
       const float* cand = cand_all + (j & 1) * (kPRows * 32);
       bool any = false;
       for (int k = (q - kbase) & 1; k < g.n_tiles; k += 2) {
         any = true;
         const int K = kbase + k, u = (K >> 1) & 1;
         const float* cs_buf = cst_all + (K % kPCstSlots) * 64;      // written by the builders before MMA1(K) was issued
-        rtp_wait(&d1_full[q], (K >> 1) & 1, 11);
+        rtp_wait_inl(&d1_full[q], (K >> 1) & 1, 11);
         tc_fence_after();
         if (K == q) RTP_TRACE(3 + 7 * q, tw == 0);
         if (K == 4) RTP_TRACE(12, tw == 0);
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     // =================================== top MLP (wg == 4) ===================================
     // Its weights (48 KB + 32 KB per SM, the same lines for every SM) are not needed before the first group's
     // tiles are done: ask for them only once the first history tile has been requested.
-    rtp_wait(&started, 0, 15);
+    rtp_wait_lazy(&started, 0, 15);
     // W1^T -> tensor memory (A operand): this thread's lane = unit tw, 96 packed bf16 pairs
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.w1_tmem + (size_t)tw * 96);
@@ -713,7 +718,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       const GroupGeom g = geom(j);
       const int s = j & 1;
       staged_wait(j);
-      rtp_wait(&pooled_ready[s], (j >> 1) & 1, 12);
+      rtp_wait_lazy(&pooled_ready[s], (j >> 1) & 1, 12);
       if (j == 0) RTP_TRACE(5, tw == 0);
       const float* cand = cand_all + s * (kPRows * 32);
       const float* pooled = pooled_all + s * (kPRows * 64);
@@ -898,8 +903,8 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
 cudaError_t read_din_rtp_trace(unsigned long long* out40) {
   return cudaMemcpyFromSymbol(out40, g_din_rtp_trace, sizeof(unsigned long long) * 40);
 }
-cudaError_t read_din_rtp_timeline(unsigned long long* out512) {
-  return cudaMemcpyFromSymbol(out512, g_din_rtp_tl, sizeof(unsigned long long) * 512);
+cudaError_t read_din_rtp_timeline(unsigned long long* out768) {
+  return cudaMemcpyFromSymbol(out768, g_din_rtp_tl, sizeof(unsigned long long) * 768);
 }
 
 // Did a wait of an earlier launch time out (see rtp_wait)?  Copies the record {code, block, thread,

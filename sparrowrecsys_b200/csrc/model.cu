@@ -1975,7 +1975,7 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   return SRS_OK;
 }
 
-int srs_debug_din_timeline(srs_model* m, uint64_t* out512) {
+int srs_debug_din_timeline(srs_model* m, uint64_t* out512) {   /* 12 x 64 values */
   if (!m || !out512) return fail(SRS_ERR_INVALID, "null argument");
   if (!m->use_din_rtp) return fail(SRS_ERR_INVALID, "the per-tile timeline exists for din_rtp_kernel only");
   CUDA_TRY(cudaSetDevice(m->device));
