@@ -16,7 +16,7 @@ interleavings.  Checked:
 import random
 import sys
 
-NSA, NSB, AHEAD = 6, 3, 3
+NSA, NSB, AHEAD = 6, 3, 2
 
 
 class Bar:
@@ -39,7 +39,7 @@ class Sim:
         self.rng = random.Random(seed)
         self.groups = groups                      # tiles per group of this CTA
         b = Bar
-        self.a_full = [b("a_full%d" % i, 224) for i in range(NSA)]
+        self.a_full = [b("a_full%d" % i, 96 if i & 1 else 128) for i in range(NSA)]
         self.a_empty = [b("a_empty%d" % i, 1) for i in range(NSA)]
         self.b_full = [b("b_full%d" % i, 64) for i in range(NSB)]
         self.b_empty = [b("b_empty%d" % i, 1) for i in range(NSB)]
@@ -84,38 +84,44 @@ class Sim:
             j & 1, self.stage_gen[j & 1], j)
 
     # ---- actors -------------------------------------------------------------------------------------
-    def gatherers(self):
-        Kg = Dg = 0
+    def gatherers(self, team):                   # team 0: even tiles (128 threads), team 1: odd tiles (96)
+        n_thr = 128 if team == 0 else 96
+        Kg = Dg = 0                              # own tiles issued / delivered
+        slot_of = lambda n: (2 * n + team) % NSA
+        kbase = 0
         for j, n_tiles in enumerate(self.groups):
             if j >= 2 and not self.staged[j & 1].passed(((j >> 1) - 1) & 1):
                 while Dg < Kg:                                 # the loader is late: deliver what has landed first
-                    self.a_full[Dg % NSA].arrive(224)
+                    self.a_full[slot_of(Dg)].arrive(n_thr)
                     Dg += 1
                     yield
             yield from self.staged_wait(j)
-            for k in range(n_tiles):
-                slot = Kg % NSA
-                if Kg >= NSA:
-                    par = ((Kg // NSA) + 1) & 1
+            for k in range((team - kbase) & 1, n_tiles, 2):
+                K = kbase + k
+                slot = K % NSA
+                assert slot == slot_of(Kg)
+                if K >= NSA:
+                    par = ((K // NSA) + 1) & 1
                     while not self.a_empty[slot].passed(par):          # publish landed tiles before blocking
                         if Dg < Kg:
-                            self.a_full[Dg % NSA].arrive(224)
+                            self.a_full[slot_of(Dg)].arrive(n_thr)
                             Dg += 1
                         yield
-                    yield from self.wait(self.a_empty[slot], par, Kg // NSA - 1)
+                    yield from self.wait(self.a_empty[slot], par, K // NSA - 1)
                 self.touch("A%d" % slot, "cp.async into the tile")
                 Kg += 1
                 if Kg - Dg > AHEAD:
-                    self.a_full[Dg % NSA].arrive(224)
+                    self.a_full[slot_of(Dg)].arrive(n_thr)
                     Dg += 1
                 yield
-            self.stage_free[j & 1].arrive(224)
+            self.stage_free[j & 1].arrive(n_thr)
+            kbase += n_tiles
             yield
         while Dg < Kg:
-            self.a_full[Dg % NSA].arrive(224)
+            self.a_full[slot_of(Dg)].arrive(n_thr)
             Dg += 1
             yield
-        self.finished.add("g")
+        self.finished.add("g%d" % team)
 
     def builders(self):
         Kb = 0
@@ -280,7 +286,7 @@ class Sim:
 
     # ---- scheduler --------------------------------------------------------------------------------
     def run(self, max_steps=400000):
-        actors = {"g": self.gatherers(), "b": self.builders(), "i1": self.issuer_mma1(), "i2": self.issuer_pool(), "l": self.loader(),
+        actors = {"g0": self.gatherers(0), "g1": self.gatherers(1), "b": self.builders(), "i1": self.issuer_mma1(), "i2": self.issuer_pool(), "l": self.loader(),
                   "c0": self.consumer(0), "c1": self.consumer(1), "t": self.top()}
         pipe = self.tensor_pipe()
         names = list(actors)

@@ -55,7 +55,7 @@ if m.kernel_name == "din_rtp_kernel":
     _lib.check(lib.srs_debug_din_timeline(m._h, tl))
     a = np.array(tl[:], dtype=np.int64).reshape(12, 64)
     t0 = int(np.array(buf[:], dtype=np.int64)[0])
-    kinds = ["issued", "delivered", "B_built", "mma1", "c_d1", "gate_done", "pool_mma", "pooled", "i.waited", "i.mmas", "-", "i.iter"]
+    kinds = ["issued", "delivered", "B_built", "mma1", "c_d1", "gate_done", "pool_mma", "pooled", "i.a_full", "i.waits", "i.mmas", "i.iter"]
     print("per-tile timeline of CTA 0 (cycles since kernel entry)")
     print("tile " + " ".join("%9s" % k for k in kinds))
     for K in range(64):

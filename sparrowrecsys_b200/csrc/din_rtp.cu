@@ -44,7 +44,8 @@ constexpr int kPRows = 32;                  // row slots per group = N/2 of the 
 constexpr int kPSlotsA = 6;                 // history tiles in flight or being consumed
 constexpr int kPSlotsB = 3;                 // per-row weight operands
 constexpr int kPCstSlots = 8;               // per-tile constants of the gate (see the builders)
-constexpr int kPAhead = 3;                  // tiles a gatherer keeps in flight before it delivers one
+constexpr int kPAhead = 2;                  // OWN tiles a gather team keeps in flight before it delivers one
+constexpr int kPMaxCopies = 11;             // copies per thread and tile: 2 x 64 cells x 8 chunks / 96 threads
 constexpr int kPGatherThreads = 224;        // warps 0-3 and 20-22
 constexpr int kPIdsLd = 64;                 // ints per row of the staged history ids
 
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (warp == 1) {                                       // one mbarrier per lane
-    if (lane < 6) mbar_init(&a_full[lane], kPGatherThreads);
+    if (lane < 6) mbar_init(&a_full[lane], (lane & 1) ? 96 : 128);        // slot parity = tile parity = gather team
     else if (lane < 12) mbar_init(&a_empty[lane - 6], 1);
     else if (lane < 14) mbar_init(&b_full[lane - 12], 64);
     else if (lane < 16) mbar_init(&b_empty[lane - 14], 1);
@@ -346,27 +347,40 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       }
     } else {
     // =================================== gatherers (warps 0-3, 20-22) =========================
+    // Two TEAMS, one per tile parity: team 0 = warps 0-3 (even tiles), team 1 = warps 20-22 (odd tiles).
+    // A gather warp is latency-bound on its own instruction stream (~10 cycles per instruction, timeline of
+    // round 2): what counts is instructions per tile PER WARP, so the tiles are split between the teams instead
+    // of the copies of every tile among all warps, and each thread keeps the shared-memory offset of its copies
+    // in registers (the id index is offset >> 7): LDS id, IMAD.WIDE, LDGSTS per copy.
     RTP_TRACE(21, tid == 0);
-    const int gt = wg == 0 ? tid : tid - 512;              // 0..223
-    const uint32_t c = (uint32_t)(gt & 7);
-    const int cell0 = gt >> 3;                             // 0..27; copy n of a tile moves cell cell0 + 28 n
-    int Kg = 0, Dg = 0;
-    auto deliver_one = [&]() {                             // the oldest outstanding tile HAS landed: publish it
+    const int team = wg == 0 ? 0 : 1;
+    const int lt = team == 0 ? tid : tid - 640;            // thread of the team: 0..127 / 0..95
+    const int tsize = team == 0 ? 128 : 96;
+    const uint32_t c16 = (uint32_t)(lt & 7) * 16u;
+    uint32_t dofs[kPMaxCopies];                            // byte offset in the A tile, 0xFFFFFFFF: no copy
+#pragma unroll
+    for (int n = 0; n < kPMaxCopies; ++n) {
+      const int cell = (lt >> 3) + (tsize >> 3) * n;       // cells: row 0 positions 0..T-1, then row 1
+      const int r = cell >= T ? 1 : 0, pos = cell - r * T;
+      dofs[n] = cell < 2 * T ? (uint32_t)(r * 64 + pos) * 128u + ((((uint32_t)(lt & 7)) ^ (uint32_t)(pos & 7)) << 4)
+                             : 0xFFFFFFFFu;
+    }
+    int Kg = 0, Dg = 0;                                    // OWN tiles issued / delivered (tile index = 2 * n + team)
+    auto slot_of = [&](int n_own) { return (2 * n_own + team) % kPSlotsA; };
+    auto deliver_one = [&]() {                             // the oldest outstanding own tile HAS landed: publish it
       fence_async_smem();
-      if (Dg == 0) RTP_TRACE(24, tid == 0);
-      if (Dg == 6) RTP_TRACE(25, tid == 0);
-      RTP_TL(1, Dg, tid == 0);
-      mbar_arrive(&a_full[Dg % kPSlotsA]);
+      RTP_TL(1, 2 * Dg + team, lt == 0);
+      mbar_arrive(&a_full[slot_of(Dg)]);
       ++Dg;
     };
     auto deliver_oldest = [&]() {                          // wait for the oldest outstanding tile, then publish it
       const int pending = Kg - Dg;                         // 1 .. kPAhead + 1 commit groups in flight
-      if (pending >= 4) cp_async_wait<3>();
-      else if (pending == 3) cp_async_wait<2>();
+      if (pending >= 3) cp_async_wait<2>();
       else if (pending == 2) cp_async_wait<1>();
       else cp_async_wait<0>();
       deliver_one();
     };
+    int kbase = 0;
     for (int j = 0; j < n_my; ++j) {
       const GroupGeom g = geom(j);
       if (j >= first_loader_group && !mbar_test_wait(&staged[j & 1], ((j >> 1) - 1) & 1)) {
@@ -375,36 +389,36 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         staged_wait(j);
       }
       const int* ids = ids_all + (j & 1) * (kPRows * kPIdsLd);
-      for (int k = 0; k < g.n_tiles; ++k) {
-        const int slot = Kg % kPSlotsA;
-        if (Kg >= kPSlotsA) {
+      for (int k = (team - kbase) & 1; k < g.n_tiles; k += 2) {      // this team's tiles of the group
+        const int K = kbase + k;
+        const int slot = K % kPSlotsA;
+        if (K >= kPSlotsA) {
           // No free slot yet: do not sit on tiles that have landed (the consumers that will free the slot may
           // be waiting for exactly those) - publish them first, then wait.
-          const uint32_t par = ((Kg / kPSlotsA) + 1) & 1;
+          const uint32_t par = ((K / kPSlotsA) + 1) & 1;
           while (!mbar_test_wait(&a_empty[slot], par)) {
             if (Dg < Kg) deliver_oldest();
             else { rtp_wait(&a_empty[slot], par, 2); break; }
           }
         }
         uint8_t* A = ringA + slot * PA_SLOT;
-        const int* idrow = ids + 2 * k * kPIdsLd;
+        const int* idrow = ids + 2 * k * kPIdsLd;          // ids of the tile's two rows: [64 | 64]
 #pragma unroll
-        for (int n = 0; n < 5; ++n) {
-          const int cell = cell0 + (kPGatherThreads / 8) * n;
-          if (cell < 2 * T) {
-            const int r = cell >= T ? 1 : 0, pos = cell - r * T;
-            cp_async16(A + (uint32_t)(r * 64 + pos) * 128u + ((c ^ (uint32_t)(pos & 7)) << 4),
-                       p.movie_split + (size_t)idrow[r * kPIdsLd + pos] * 128 + c * 16u);
+        for (int n = 0; n < kPMaxCopies; ++n) {
+          if (dofs[n] != 0xFFFFFFFFu) {
+            const uint32_t d = dofs[n];
+            cp_async16(A + d, p.movie_split + (size_t)idrow[d >> 7] * 128 + c16);
           }
         }
         cp_async_commit();
-        RTP_TL(0, Kg, tid == 0);
+        RTP_TL(0, K, lt == 0);
         ++Kg;
         if (Kg - Dg > kPAhead) deliver_oldest();
-        if (Kg == 1) mbar_arrive(&started);                 // the top MLP may now load its weights
-        if (j == 0 && k == 0) RTP_TRACE(20, tid == 0);
+        if (K == 0) RTP_TRACE(20, tid == 0);
       }
+      if (j == 0) mbar_arrive(&started);                   // the top MLP may now load its weights
       mbar_arrive(&stage_free[j & 1]);                     // the ids were read when the copies were issued
+      kbase += g.n_tiles;
     }
     cp_async_wait<0>();
     while (Dg < Kg) deliver_one();
@@ -425,9 +439,12 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
       uint32_t pa = 0, pb = 0;
       for (int K = 0; K < NT; ++K) {
         const int q = K & 1;
+        RTP_TL(11, K, lane == 0);
         rtp_wait(&a_full[sa], pa, 3);
+        RTP_TL(8, K, lane == 0);
         rtp_wait(&b_full[sb], pb, 4);
         if (K >= 2) rtp_wait(&d1_free[q], ((K >> 1) - 1) & 1, 5);   // the accumulators of tile K - 2 are in registers
+        RTP_TL(9, K, lane == 0);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD1 = tbase + PT_D1 + 128u * q;
@@ -437,6 +454,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
           mma_ss(tD1, ad + 2, bd + 2, idesc_bf16(128, 128), 1);
           mma_ss(tD1, ad + 4, bd + 0, idesc_bf16(128, 64), 1);      // H_lo . W_hi
           mma_ss(tD1, ad + 6, bd + 2, idesc_bf16(128, 64), 1);
+          RTP_TL(10, K, true);
           mma_commit(&d1_full[q]);
           mma_commit(&b_empty[sb]);
         }
