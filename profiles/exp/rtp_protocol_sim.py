@@ -39,16 +39,16 @@ class Sim:
         self.rng = random.Random(seed)
         self.groups = groups                      # tiles per group of this CTA
         b = Bar
-        self.a_full = [b("a_full%d" % i, 96 if i & 1 else 128) for i in range(NSA)]
+        self.a_full = [b("a_full%d" % i, 64) for i in range(NSA)]
         self.a_empty = [b("a_empty%d" % i, 1) for i in range(NSA)]
-        self.b_full = [b("b_full%d" % i, 64) for i in range(NSB)]
+        self.b_full = [b("b_full%d" % i, 128) for i in range(NSB)]
         self.b_empty = [b("b_empty%d" % i, 1) for i in range(NSB)]
         self.d1_full = [b("d1_full%d" % i, 1) for i in range(2)]
         self.d1_free = [b("d1_free%d" % i, 128) for i in range(2)]
         self.w_ready = [[b("w_ready%d%d" % (q, u), 128) for u in range(2)] for q in range(2)]
         self.d2_full = [[b("d2_full%d%d" % (q, u), 1) for u in range(2)] for q in range(2)]
         self.staged = [b("staged%d" % i, 32) for i in range(2)]
-        self.stage_free = [b("stage_free%d" % i, 672) for i in range(2)]
+        self.stage_free = [b("stage_free%d" % i, 640) for i in range(2)]
         self.pooled_ready = [b("pooled_ready%d" % i, 256) for i in range(2)]
         self.pooled_free = [b("pooled_free%d" % i, 128) for i in range(2)]
         self.cbar = b("cbar", 1)
@@ -85,7 +85,7 @@ class Sim:
 
     # ---- actors -------------------------------------------------------------------------------------
     def gatherers(self, team):                   # team 0: even tiles (128 threads), team 1: odd tiles (96)
-        n_thr = 128 if team == 0 else 96
+        n_thr = 64
         Kg = Dg = 0                              # own tiles issued / delivered
         slot_of = lambda n: (2 * n + team) % NSA
         kbase = 0
@@ -133,10 +133,10 @@ class Sim:
                     yield from self.wait(self.b_empty[slot], ((Kb // NSB) + 1) & 1, Kb // NSB - 1)
                 self.touch("B%d" % slot, "builder writes W_r")
                 assert self.stage_gen[j & 1] == j
-                self.b_full[slot].arrive(64)
+                self.b_full[slot].arrive(128)
                 Kb += 1
                 yield
-            self.stage_free[j & 1].arrive(64)
+            self.stage_free[j & 1].arrive(128)
             yield
         self.finished.add("b")
 

@@ -45,8 +45,9 @@ constexpr int kPSlotsA = 6;                 // history tiles in flight or being 
 constexpr int kPSlotsB = 3;                 // per-row weight operands
 constexpr int kPCstSlots = 8;               // per-tile constants of the gate (see the builders)
 constexpr int kPAhead = 2;                  // OWN tiles a gather team keeps in flight before it delivers one
-constexpr int kPMaxCopies = 11;             // copies per thread and tile: 2 x 64 cells x 8 chunks / 96 threads
-constexpr int kPGatherThreads = 224;        // warps 0-3 and 20-22
+constexpr int kPMaxCopies = 16;             // copies per thread and tile: 2 x 64 cells x 8 chunks / 64 threads
+constexpr int kPGatherThreads = 128;        // warps 0-3: two teams of two warps
+constexpr int kPBuilderThreads = 128;       // warps 20-23
 constexpr int kPIdsLd = 64;                 // ints per row of the staged history ids
 
 // shared memory (offsets from the 1024-aligned base)
@@ -69,6 +70,7 @@ constexpr uint32_t PX_BYTES = PX_CST + kPCstSlots * 256;
 // layer-2 scratch lies over the X / H1 operand tile (dead once the layer-2 MMAs have completed)
 constexpr uint32_t PO_RED = PO_XB;                           // f32 [64][32]
 constexpr uint32_t PO_ZP = PO_XB + 8192;                     // f32 [4][32]
+static_assert((kPCstSlots & (kPCstSlots - 1)) == 0, "constants ring is indexed with a mask");
 static_assert(PX_B2 % 1024 == 0 && (PO_X + PX_B2) % 1024 == 0, "pooling-weight operand tiles are 1024-byte aligned");
 constexpr uint32_t P_SMEM = PO_X + PX_BYTES;
 static_assert(P_SMEM + 1024 <= 232448, "does not fit the 227 KB of one CTA");
@@ -273,16 +275,16 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   asm volatile("griddepcontrol.wait;" ::: "memory");    // inputs may come from the previous kernel
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (warp == 1) {                                       // one mbarrier per lane
-    if (lane < 6) mbar_init(&a_full[lane], (lane & 1) ? 96 : 128);        // slot parity = tile parity = gather team
+    if (lane < 6) mbar_init(&a_full[lane], 64);            // one gather team (two warps) per tile parity
     else if (lane < 12) mbar_init(&a_empty[lane - 6], 1);
-    else if (lane < 14) mbar_init(&b_full[lane - 12], 64);
+    else if (lane < 14) mbar_init(&b_full[lane - 12], kPBuilderThreads);
     else if (lane < 16) mbar_init(&b_empty[lane - 14], 1);
     else if (lane < 18) mbar_init(&d1_full[lane - 16], 1);
     else if (lane < 20) mbar_init(&d1_free[lane - 18], 128);
     else if (lane < 24) mbar_init(&w_ready[(lane - 20) >> 1][(lane - 20) & 1], 128);
     else if (lane < 28) mbar_init(&d2_full[(lane - 24) >> 1][(lane - 24) & 1], 1);
     else if (lane < 30) mbar_init(&staged[lane - 28], 32);
-    else if (lane < 32) mbar_init(&stage_free[lane - 30], kPGatherThreads + 64 + 256 + 128);
+    else if (lane < 32) mbar_init(&stage_free[lane - 30], kPGatherThreads + kPBuilderThreads + 256 + 128);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     else if (lane < 4) mbar_init(&pooled_free[lane - 2], 128);
     else if (lane == 4) mbar_init(&wbar, 1);
     else if (lane == 5) mbar_init(&cbar, 1);
-    else if (lane == 6) mbar_init(&b_full[2], 64);
+    else if (lane == 6) mbar_init(&b_full[2], kPBuilderThreads);
     else if (lane == 7) mbar_init(&b_empty[2], 1);
     else if (lane == 8) mbar_init(&started, kPGatherThreads);
     fence_mbar_init();
@@ -335,27 +337,18 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
   auto staged_wait = [&](int j) { if (j >= first_loader_group) rtp_wait(&staged[j & 1], ((j >> 1) - 1) & 1, 1); };
   auto staged_wait_inl = [&](int j) { if (j >= first_loader_group) rtp_wait_inl(&staged[j & 1], ((j >> 1) - 1) & 1, 1); };
 
-  if (wg == 0 || wg == 5) {
+  if (wg == 0) {
     reg_dec<40>();
-    if (warp == 23) {
-      // =================================== loader ==========================================
-      for (int j = first_loader_group; j < n_my; ++j) {
-        rtp_wait_lazy(&stage_free[j & 1], ((j >> 1) - 1) & 1, 7);  // every reader of group j - 2 is done
-        stage_rows(j);
-        stage_hist(j, lane, 32);
-        mbar_arrive(&staged[j & 1]);
-      }
-    } else {
-    // =================================== gatherers (warps 0-3, 20-22) =========================
-    // Two TEAMS, one per tile parity: team 0 = warps 0-3 (even tiles), team 1 = warps 20-22 (odd tiles).
+    // =================================== gatherers (warps 0-3) ==================================
+    // Two TEAMS, one per tile parity: team 0 = warps 0-1 (even tiles), team 1 = warps 2-3 (odd tiles).
     // A gather warp is latency-bound on its own instruction stream (~10 cycles per instruction, timeline of
     // round 2): what counts is instructions per tile PER WARP, so the tiles are split between the teams instead
     // of the copies of every tile among all warps, and each thread keeps the shared-memory offset of its copies
     // in registers (the id index is offset >> 7): LDS id, IMAD.WIDE, LDGSTS per copy.
     RTP_TRACE(21, tid == 0);
-    const int team = wg == 0 ? 0 : 1;
-    const int lt = team == 0 ? tid : tid - 640;            // thread of the team: 0..127 / 0..95
-    const int tsize = team == 0 ? 128 : 96;
+    const int team = warp >> 1;
+    const int lt = tid & 63;                               // thread of the team
+    const int tsize = 64;
     const uint32_t c16 = (uint32_t)(lt & 7) * 16u;
     uint32_t dofs[kPMaxCopies];                            // byte offset in the A tile, 0xFFFFFFFF: no copy
 #pragma unroll
@@ -422,11 +415,21 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     }
     cp_async_wait<0>();
     while (Dg < Kg) deliver_one();
-    }
+    cp_async_wait<0>();
+    while (Dg < Kg) deliver_one();
   } else if (wg == 1) {
-    // registers: the CTA's pool is what it was LAUNCHED with (768 x 80): 480 per thread slot = 40 + 40 + 80 + 120 + 120 + 80;
-    // this warpgroup and the top-MLP one keep the 80 they were launched with
-    if (warp == 4) {
+    // registers: the CTA's pool is what it was LAUNCHED with (768 x 80): 480 per thread slot =
+    // 40 (gatherers) + 40 (here: issuers, loader) + 120 + 120 (consumers) + 80 (top MLP) + 80 (builders)
+    reg_dec<40>();
+    if (warp == 6) {
+      // =================================== loader ==========================================
+      for (int j = first_loader_group; j < n_my; ++j) {
+        rtp_wait_lazy(&stage_free[j & 1], ((j >> 1) - 1) & 1, 7);  // every reader of group j - 2 is done
+        stage_rows(j);
+        stage_hist(j, lane, 32);
+        mbar_arrive(&staged[j & 1]);
+      }
+    } else if (warp == 4) {
       // ============================ issuer of the activation-unit MMAs ==========================
       // Two issuer warps (this one and warp 5): one warp issuing both MMA groups of every tile in order needed
       // ~1.4 K cycles per tile - it is latency-bound on its own dependent instruction stream (~8 cycles per
@@ -488,83 +491,7 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
         RTP_TL(6, K, lane == 0);
         if (++sa == kPSlotsA) sa = 0;
       }
-    } else {
-      // =================================== builders ========================================
-      // B operand of every tile: W_r = (Wsub+Wh) + diag(c_r) Wp, bf16 hi / lo.
-      //   rc[16 c + 0..7] = (Wsub+Wh)[8 cq .. 8 cq + 7][j], rc[16 c + 8..15] = Wp[..][j], j = bt >> 1, cq = 2 (bt & 1) + c
-      const int bt = tid - 192, pj = bt >> 1, cq0 = 2 * (bt & 1);
-      float rc[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                                     // index 4 i = 16 c + 8 part + 4 h
-        const int cc = i >> 2, part = (i >> 1) & 1, h = i & 1;
-        const float4 v = ldg4((part ? p.wpT : p.waT) + pj * 32 + 8 * (cq0 + cc) + 4 * h);
-        rc[4 * i] = v.x; rc[4 * i + 1] = v.y; rc[4 * i + 2] = v.z; rc[4 * i + 3] = v.w;
-      }
-      // gate constants cst[r][j] = au_b[j] + sum_e cand[r][e] (Wc - Wsub)[e][j]: this thread keeps the 16 weights of
-      // ITS unit j = pj for ITS half of e (the same split as above) in registers; the two halves meet by one shuffle
-      float wcst[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) wcst[e] = __ldg(p.au_wc + (16 * (bt & 1) + e) * 32 + pj);
-      const float cst_bias = (bt & 1) ? 0.f : __ldg(p.au_b + pj);
-      int Kb = 0;
-      for (int j = 0; j < n_my; ++j) {
-        const GroupGeom g = geom(j);
-        staged_wait(j);
-        const float* cand = cand_all + (j & 1) * (kPRows * 32);
-        for (int k = 0; k < g.n_tiles; ++k, ++Kb) {
-          const int slot = Kb % kPSlotsB;
-          if (Kb >= kPSlotsB) rtp_wait(&b_empty[slot], ((Kb / kPSlotsB) + 1) & 1, 8);
-          uint8_t* Bt = ringB + slot * PB_SLOT;
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int cq = cq0 + cc;
-              const float* cv = cand + (2 * k + r) * 32 + 8 * cq;
-              const float4 c0 = *reinterpret_cast<const float4*>(cv), c1 = *reinterpret_cast<const float4*>(cv + 4);
-              const float* wa = rc + 16 * cc;
-              const float* wp = rc + 16 * cc + 8;
-              const float2 v0 = fma2(make_float2(c0.x, c0.y), make_float2(wp[0], wp[1]), make_float2(wa[0], wa[1]));
-              const float2 v1 = fma2(make_float2(c0.z, c0.w), make_float2(wp[2], wp[3]), make_float2(wa[2], wa[3]));
-              const float2 v2 = fma2(make_float2(c1.x, c1.y), make_float2(wp[4], wp[5]), make_float2(wa[4], wa[5]));
-              const float2 v3 = fma2(make_float2(c1.z, c1.w), make_float2(wp[6], wp[7]), make_float2(wa[6], wa[7]));
-              const Split2 s0 = split_pack(v0.x, v0.y), s1 = split_pack(v1.x, v1.y);
-              const Split2 s2 = split_pack(v2.x, v2.y), s3 = split_pack(v3.x, v3.y);
-              const uint32_t n = r * 32 + pj;
-              *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
-              *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
-            }
-          // gate constants of the tile (both rows).  Slot Kb % 8: the gate of tile Kb - 8 finished before
-          // MMA1(Kb - 3) completed (b_empty above).
-          {
-            float a0 = cst_bias, a1 = cst_bias;
-            const float* cv0 = cand + (2 * k) * 32 + 16 * (bt & 1);
-#pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 x0 = *reinterpret_cast<const float4*>(cv0 + 4 * e4);
-              const float4 x1 = *reinterpret_cast<const float4*>(cv0 + 32 + 4 * e4);
-              a0 = fmaf(x0.x, wcst[4 * e4], a0); a1 = fmaf(x1.x, wcst[4 * e4], a1);
-              a0 = fmaf(x0.y, wcst[4 * e4 + 1], a0); a1 = fmaf(x1.y, wcst[4 * e4 + 1], a1);
-              a0 = fmaf(x0.z, wcst[4 * e4 + 2], a0); a1 = fmaf(x1.z, wcst[4 * e4 + 2], a1);
-              a0 = fmaf(x0.w, wcst[4 * e4 + 3], a0); a1 = fmaf(x1.w, wcst[4 * e4 + 3], a1);
-            }
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);        // lanes bt, bt ^ 1: the two halves of e for unit pj
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            if ((bt & 1) == 0) {
-              cst_all[(Kb % kPCstSlots) * 64 + pj] = a0;
-              cst_all[(Kb % kPCstSlots) * 64 + 32 + pj] = a1;
-            }
-          }
-          fence_async_smem();
-          mbar_arrive(&b_full[slot]);
-          RTP_TL(2, Kb, bt == 0);
-          if (Kb == 0) RTP_TRACE(28, bt == 0);
-          if (Kb == 3) RTP_TRACE(29, bt == 0);
-          if (Kb == 4) RTP_TRACE(17, bt == 0);
-        }
-        mbar_arrive(&stage_free[j & 1]);
-      }
-    }
+    }                                                      // warp 7 has no role
   } else if (wg == 2 || wg == 3) {
     // =================================== consumers ===========================================
     reg_inc<120>();
@@ -690,6 +617,68 @@ __global__ void __launch_bounds__(kPThreads, 1) din_rtp_kernel(const __grid_cons
     }
     if (pend) pool_out();
     RTP_TRACE(4 + 7 * q, tw == 0);
+  } else if (wg == 5) {
+    // =================================== builders (warps 20-23) ==============================
+    // B operand of every tile: W_r = (Wsub+Wh) + diag(c_r) Wp, bf16 hi / lo, and the gate constants of its two
+    // rows.  Four warps: a builder warp is latency-bound on its own instruction stream like every single-warp
+    // role here (two warps needed 1.4 K cycles per tile).  Thread -> (unit pj, 8-wide chunk cq of e):
+    //   rc[0..7] = (Wsub+Wh)[8 cq ..][pj], rc[8..15] = Wp[8 cq ..][pj], wcst[0..7] = (Wc - Wsub)[8 cq ..][pj]
+    const int bt = tid - 640, pj = bt >> 2, cq = bt & 3;
+    float rc[16], wcst[8];
+    {
+      const float4 a0 = ldg4(p.waT + pj * 32 + 8 * cq), a1 = ldg4(p.waT + pj * 32 + 8 * cq + 4);
+      const float4 p0 = ldg4(p.wpT + pj * 32 + 8 * cq), p1 = ldg4(p.wpT + pj * 32 + 8 * cq + 4);
+      rc[0] = a0.x; rc[1] = a0.y; rc[2] = a0.z; rc[3] = a0.w; rc[4] = a1.x; rc[5] = a1.y; rc[6] = a1.z; rc[7] = a1.w;
+      rc[8] = p0.x; rc[9] = p0.y; rc[10] = p0.z; rc[11] = p0.w; rc[12] = p1.x; rc[13] = p1.y; rc[14] = p1.z; rc[15] = p1.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wcst[e] = __ldg(p.au_wc + (8 * cq + e) * 32 + pj);
+    }
+    const float cst_bias = __ldg(p.au_b + pj);
+    int Kb = 0, slot = 0;
+    uint32_t pe = 1;                                       // parity to wait with on b_empty: ((Kb / 3) + 1) & 1, kept incrementally
+    for (int j = 0; j < n_my; ++j) {
+      const GroupGeom g = geom(j);
+      staged_wait(j);
+      const float* cand = cand_all + (j & 1) * (kPRows * 32);
+      for (int k = 0; k < g.n_tiles; ++k, ++Kb) {
+        if (Kb >= kPSlotsB) rtp_wait(&b_empty[slot], pe, 8);
+        uint8_t* Bt = ringB + slot * PB_SLOT;
+        float part[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* cv = cand + (2 * k + r) * 32 + 8 * cq;
+          const float4 c0 = *reinterpret_cast<const float4*>(cv), c1 = *reinterpret_cast<const float4*>(cv + 4);
+          const float2 v0 = fma2(make_float2(c0.x, c0.y), make_float2(rc[8], rc[9]), make_float2(rc[0], rc[1]));
+          const float2 v1 = fma2(make_float2(c0.z, c0.w), make_float2(rc[10], rc[11]), make_float2(rc[2], rc[3]));
+          const float2 v2 = fma2(make_float2(c1.x, c1.y), make_float2(rc[12], rc[13]), make_float2(rc[4], rc[5]));
+          const float2 v3 = fma2(make_float2(c1.z, c1.w), make_float2(rc[14], rc[15]), make_float2(rc[6], rc[7]));
+          const Split2 s0 = split_pack(v0.x, v0.y), s1 = split_pack(v1.x, v1.y);
+          const Split2 s2 = split_pack(v2.x, v2.y), s3 = split_pack(v3.x, v3.y);
+          const uint32_t n = r * 32 + pj;
+          *reinterpret_cast<uint4*>(Bt + sw64_offset(n, cq)) = make_uint4(s0.hi, s1.hi, s2.hi, s3.hi);
+          *reinterpret_cast<uint4*>(Bt + sw64_offset(64 + n, cq)) = make_uint4(s0.lo, s1.lo, s2.lo, s3.lo);
+          // gate constant of the row: this thread's 8 of the 32 terms of cst[r][pj]
+          float a = c0.x * wcst[0];
+          a = fmaf(c0.y, wcst[1], a); a = fmaf(c0.z, wcst[2], a); a = fmaf(c0.w, wcst[3], a);
+          a = fmaf(c1.x, wcst[4], a); a = fmaf(c1.y, wcst[5], a); a = fmaf(c1.z, wcst[6], a); a = fmaf(c1.w, wcst[7], a);
+          part[r] = a;
+        }
+        // the four chunks of a unit sit in adjacent lanes.  Slot Kb % 8 of the constants ring: the gate of tile
+        // Kb - 8 finished before MMA1(Kb - 3) completed (b_empty above).
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float a = part[r];
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          if (cq == 0) cst_all[(Kb & (kPCstSlots - 1)) * 64 + r * 32 + pj] = a + cst_bias;
+        }
+        fence_async_smem();
+        mbar_arrive(&b_full[slot]);
+        RTP_TL(2, Kb, bt == 0);
+        if (++slot == kPSlotsB) { slot = 0; pe ^= 1u; }
+      }
+      mbar_arrive(&stage_free[j & 1]);
+    }
   } else {
     // =================================== top MLP (wg == 4) ===================================
     // Its weights (48 KB + 32 KB per SM, the same lines for every SM) are not needed before the first group's
