@@ -542,7 +542,7 @@ def run_ours(args):
     S = max(1, args.streams) if gather_mode is None else 1
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     side = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
-    half_sm_kernel = model.kernel_name in ("din_rth_kernel",)      # two CTAs of it fit on an SM
+    half_sm_kernel = False                                         # (no kernel fits two CTAs per SM at present)
     if args.sm_limit is not None:
         sm_limit = args.sm_limit
     else:

@@ -130,7 +130,7 @@ const char* srs_last_error(void);
 int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_tensors,
                      int32_t device, srs_model** out);
 
-/* Same, with kernel-variant options "key=value;key=value": din_impl = rtp | rt | tc | cudacore | rth,
+/* Same, with kernel-variant options "key=value;key=value": din_impl = rt | rtp | tc | cudacore,
  * embmlp_impl / deepfm_impl = tc | cudacore, zero_copy_scores = 0 | 1.  Unknown keys are ignored; a
  * forced variant that does not support the shape makes the call fail.  NULL / "" = the defaults
  * (which srs_model_kernel_name reports).  The environment variables SRS_DIN_IMPL, SRS_EMBMLP_IMPL,
@@ -208,9 +208,9 @@ int64_t srs_model_bytes_per_inference(const srs_model* m);
 /* Name of the kernel variant srs_predict_* dispatches to for this model.  DIN has four
  * (din_rt_kernel / din_rt64_kernel: tcgen05 row tiles; din_tc_kernel: tcgen05 per pair;
  * din_kernel: CUDA cores); the choice follows the shape and can be forced with the environment
- * variable SRS_DIN_IMPL = rt | tc | cudacore read by srs_model_create (a forced variant that does
- * not support the shape makes srs_model_create fail; rth selects the experimental half-SM row-tile
- * kernel din_rth_kernel, see csrc/din_rth.cu).  SRS_EMBMLP_IMPL and SRS_DEEPFM_IMPL
+ * variable SRS_DIN_IMPL = rt | rtp | tc | cudacore read by srs_model_create (a forced variant that does
+ * not support the shape makes srs_model_create fail; rtp selects din_rtp_kernel, the row-tile kernel with
+ * the phases of consecutive row groups pipelined, see csrc/din_rtp.cu).  SRS_EMBMLP_IMPL and SRS_DEEPFM_IMPL
  * (tc | cudacore) do the same for EmbeddingMLP / Wide&Deep and DeepFM. */
 const char* srs_model_kernel_name(const srs_model* m);
 

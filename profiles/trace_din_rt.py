@@ -14,7 +14,7 @@ from sparrowrecsys_b200.weights import init_weights
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 spec = baseline_spec("cfg3_din")
 m = CTRModel(spec, init_weights(spec, 2), 0)
-assert m.kernel_name in ("din_rt_kernel", "din_rth_kernel", "din_rtp_kernel"), m.kernel_name   # SRS_DIN_IMPL=rth / rtp
+assert m.kernel_name in ("din_rt_kernel", "din_rtp_kernel"), m.kernel_name   # SRS_DIN_IMPL=rtp: the pipelined kernel
 if len(sys.argv) > 2:
     m.set_sm_limit(int(sys.argv[2]))
 db = m.to_device(synthetic_features(spec, B, seed=1))

@@ -1,5 +1,5 @@
-mkdir -p gpurun_out/r2c15
-O=gpurun_out/r2c15
+mkdir -p gpurun_out/r2c16
+O=gpurun_out/r2c16
 timeout -k 5 200 python -m pytest tests/test_gpu_parity.py -k "rtp" -q -x --timeout 40 > $O/rtp_tests.log 2>&1; RTP=$?; echo "rtp tests rc=$RTP"; tail -8 $O/rtp_tests.log
 if [ $RTP -eq 0 ]; then
   SRS_CTR_LIB=$PWD/sparrowrecsys_b200/variants/libsrs_ctr_tl.so SRS_DIN_IMPL=rtp timeout -k 5 50 python profiles/trace_din_rt.py 4096 74 > $O/trace_tl.txt 2>&1; echo "trace rc=$?"

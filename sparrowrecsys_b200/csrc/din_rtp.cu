@@ -44,7 +44,10 @@ constexpr int kPRows = 32;                  // row slots per group = N/2 of the 
 constexpr int kPSlotsA = 6;                 // history tiles in flight or being consumed
 constexpr int kPSlotsB = 3;                 // per-row weight operands
 constexpr int kPCstSlots = 8;               // per-tile constants of the gate (see the builders)
-constexpr int kPAhead = 2;                  // OWN tiles a gather team keeps in flight before it delivers one
+#ifndef RTP_AHEAD
+#define RTP_AHEAD 0
+#endif
+constexpr int kPAhead = RTP_AHEAD;          // OWN tiles a gather team keeps in flight before it delivers one
 constexpr int kPMaxCopies = 16;             // copies per thread and tile: 2 x 64 cells x 8 chunks / 64 threads
 constexpr int kPGatherThreads = 128;        // warps 0-3: two teams of two warps
 constexpr int kPBuilderThreads = 128;       // warps 20-23

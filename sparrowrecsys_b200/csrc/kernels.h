@@ -230,7 +230,6 @@ struct DinRtParams {
   int nch;                   // din_rt64: 128-position chunks per row (1 or 2)
   int num_sms;
   int trace;
-  int ctas_per_sm;           // din_rth: 1 (co-residency comes from other streams' launches) or 2
   // din_rtp (pipelined row-tile kernel): layer-1 weights as a tensor-memory A operand and the genre
   // columns of the top MLP folded into fp32 tables
   const uint32_t* w1_tmem;   // [128 units][48 words hi | 48 words lo]: packed bf16 pairs of W1^T over
@@ -244,9 +243,6 @@ cudaError_t launch_din_rt(const DinRtParams& p, const BatchView& b, cudaStream_t
 cudaError_t launch_split_table(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t read_din_rt_trace(unsigned long long* out40);
 cudaError_t setup_din_rt_attributes();
-cudaError_t launch_din_rth(const DinRtParams& p, const BatchView& b, cudaStream_t s);
-cudaError_t setup_din_rth_attributes();
-cudaError_t read_din_rth_trace(unsigned long long* out40);
 cudaError_t launch_din_rtp(const DinRtParams& p, const BatchView& b, cudaStream_t s);
 cudaError_t setup_din_rtp_attributes();
 cudaError_t read_din_rtp_trace(unsigned long long* out40);

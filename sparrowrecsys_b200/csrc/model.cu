@@ -22,7 +22,6 @@ cudaError_t setup_din_attributes();
 cudaError_t setup_dien_attributes();
 cudaError_t setup_din_tc_attributes();
 cudaError_t setup_din_rt_attributes();
-cudaError_t setup_din_rth_attributes();
 cudaError_t setup_din_rtp_attributes();
 cudaError_t setup_din_rt64_attributes();
 cudaError_t setup_embmlp_tc_attributes();
@@ -61,8 +60,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // Kernel-variant options of the model being created: "key=value;key=value" handed to
-// srs_model_create_ex (keys: din_impl, embmlp_impl, deepfm_impl, zero_copy_scores, din_rth_ctas,
-// din_rth_bg).  The environment variables SRS_<KEY> remain as a tuning override of last resort.
+// srs_model_create_ex (keys: din_impl, embmlp_impl, deepfm_impl, zero_copy_scores).  The environment variables SRS_<KEY> remain as a tuning override of last resort.
 thread_local std::string g_create_opts;
 const char* opt(const char* key, const char* env_name) {
   static thread_local std::string val;
@@ -136,7 +134,6 @@ struct srs_model {
   DinRtParams din_rt{};
   bool use_din_rt = false;
   bool use_din_rt64 = false;         // din_rt holds the parameters of din_rt64_kernel
-  bool use_din_rth = false;          // din_rt holds the parameters; the half-SM kernel runs them
   bool use_din_rtp = false;          // din_rt holds the parameters; the pipelined row-tile kernel runs them
   EmbMlpTcParams emb_tc{};
   bool use_emb_tc = false;
@@ -1159,7 +1156,6 @@ int launch(srs_model* m, const BatchView& v, cudaStream_t stream) {
     case SRS_DEEPFM_V2: e = launch_deepfm2(m->fm2, v, stream); break;
     case SRS_DIN:
       e = m->use_din_rt64 ? launch_din_rt64(m->din_rt, v, stream)
-          : m->use_din_rth ? launch_din_rth(m->din_rt, v, stream)
           : m->use_din_rtp ? launch_din_rtp(m->din_rt, v, stream)
           : m->use_din_rt ? launch_din_rt(m->din_rt, v, stream)
           : m->use_din_tc ? launch_din_tc(m->din_tc, v, stream)
@@ -1479,12 +1475,6 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
         if (!fits_tc && rc == SRS_OK) rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=tc needs 16 < emb_dim <= 32 and hist_len <= 128");
         want_tc = true; want_rt = false;
       }
-      const bool want_rth = impl && !strcmp(impl, "rth");       // experimental half-SM row-tile kernel
-      if (want_rth) {
-        if (!fits_rt32 && rc == SRS_OK)
-          rc = fail(SRS_ERR_INVALID, "SRS_DIN_IMPL=rth needs 16 < emb_dim <= 32 and hist_len <= 64");
-        want_rt = true; want_tc = false;
-      }
       const bool want_rtp = impl && !strcmp(impl, "rtp");       // pipelined row-tile kernel (din_rtp.cu)
       if (want_rtp) {
         if (!fits_rt32 && rc == SRS_OK)
@@ -1503,16 +1493,6 @@ int srs_model_create(const srs_spec* spec, const srs_tensor* tensors, int32_t n_
       if (rc == SRS_OK && want_rt && fits_rt32) {
         rc = build_din_rt(B);
         if (rc == SRS_OK) { m->use_din_rt = true; m->kernel_name = "din_rt_kernel"; }
-        if (rc == SRS_OK && want_rth) {
-          // experimental kernel: its attribute setup stays off the path of every other model
-          cudaError_t ea = setup_din_rth_attributes();
-          if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rth attribute setup failed: %s", cudaGetErrorString(ea));
-          const char* cps = opt("din_rth_ctas", "SRS_DIN_RTH_CTAS");
-          m->din_rt.ctas_per_sm = (cps && atoi(cps) == 2) ? 2 : 1;
-          const char* bg = opt("din_rth_bg", "SRS_DIN_RTH_BG");        // builder warp gathers too
-          m->din_rt.nch = (bg && atoi(bg) == 1) ? 1 : 0;
-          m->use_din_rt = false; m->use_din_rth = true; m->kernel_name = "din_rth_kernel";
-        }
         if (rc == SRS_OK && want_rtp) {
           cudaError_t ea = setup_din_rtp_attributes();
           if (ea != cudaSuccess) rc = fail(SRS_ERR_CUDA, "din_rtp attribute setup failed: %s", cudaGetErrorString(ea));
@@ -1967,8 +1947,7 @@ int srs_debug_din_trace(srs_model* m, int32_t enable, uint64_t* out40) {
   m->din_rt.trace = enable;
   if (out40) {
     CUDA_TRY(cudaDeviceSynchronize());
-    if (m->use_din_rth) CUDA_TRY(read_din_rth_trace(reinterpret_cast<unsigned long long*>(out40)));
-    else if (m->use_din_rtp) CUDA_TRY(read_din_rtp_trace(reinterpret_cast<unsigned long long*>(out40)));
+    if (m->use_din_rtp) CUDA_TRY(read_din_rtp_trace(reinterpret_cast<unsigned long long*>(out40)));
     else if (m->use_din_rt) CUDA_TRY(read_din_rt_trace(reinterpret_cast<unsigned long long*>(out40)));
     else CUDA_TRY(read_din_tc_trace(reinterpret_cast<unsigned long long*>(out40)));
   }

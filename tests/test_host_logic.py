@@ -221,21 +221,6 @@ def test_abi_argument_validation_needs_no_device():
         default_spec("dien", emb_dim=33)                     # one lane per state element
 
 
-def test_din_rth_barrier_protocol_model():
-    """The experimental half-SM DIN kernel (csrc/din_rth.cu) has not run on a GPU yet; its
-    mbarrier protocol is checked here on a CPU model under random interleavings
-    (profiles/exp/rth_protocol_sim.py: no deadlock, no parity aliasing, no operand hazard)."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location(
-        "rth_protocol_sim", os.path.join(ROOT, "profiles", "exp", "rth_protocol_sim.py"))
-    sim = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(sim)
-    for shape in ([1], [2], [14], [3, 3, 3], [16, 1, 5, 16]):
-        for seed in range(8):
-            sim.Sim(shape, seed).run()
-            sim.Sim(shape, seed, builder_gathers=True).run()
-
-
 def test_din_rtp_barrier_protocol_model():
     """din_rtp_kernel (csrc/din_rtp.cu) orders seven roles with nothing but mbarriers across group
     boundaries; its protocol is checked on a CPU model under random interleavings
