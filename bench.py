@@ -554,8 +554,10 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         for i in range(min(8, ring)):                 # first touches / module load
             launch(i, stream.cuda_stream)
+            if gather_buf is not None:
+                dist.all_gather_into_tensor(gather_buf, out[i % ring])     # communicator set-up outside the capture
         stream.synchronize()
-        if not args.no_graph and gather_mode != "nccl":
+        if not args.no_graph:                          # (NCCL all-gathers are captured too: torch supports it)
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
@@ -565,6 +567,8 @@ def run_ours(args):
                     branches = [cur] + side
                     for i in range(ring):
                         launch(i, branches[i % S].cuda_stream)
+                        if gather_buf is not None:
+                            dist.all_gather_into_tensor(gather_buf, out[i % ring])
                     for sd in side:                       # join
                         cur.wait_stream(sd)
                 graph = g

@@ -161,8 +161,9 @@ int srs_predict_device(srs_model* m, const srs_batch* batch, float* probs, float
  *   3. per call: srs_predict_device_gather (asynchronous on `stream`), then srs_gather_wait on the
  *      stream that consumes the scores, then srs_gather_scores for the device pointer of the full
  *      [world * slice_rows] vector (valid until the call after the next one: two buffers alternate).
- * Every rank must make the same sequence of calls.  Not capturable in a CUDA graph (the step
- * counter is a kernel argument). */
+ * Every rank must make the same sequence of calls.  The step counters live on the device, so a
+ * sequence of an EVEN number of predict / wait pairs can be captured in a CUDA graph and replayed
+ * (the buffer parity of each pair is fixed at capture). */
 typedef struct srs_gather srs_gather;
 int srs_gather_create(int32_t device, int32_t world, int32_t rank, int64_t slice_rows, srs_gather** out);
 int srs_gather_export(srs_gather* g, void* handle64);

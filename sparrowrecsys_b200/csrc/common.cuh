@@ -41,9 +41,9 @@ struct BatchView {
   float* peer_probs[7];
   int n_peers;
   int n_sig;                    // ranks to signal (0: no in-kernel signal)
-  uint32_t sig_step;
   uint32_t* sig_flags[8];       // flag word of THIS rank in every rank's flag array (own included)
-  unsigned int* sig_counter;    // local: CTAs of this launch that have finished
+  unsigned int* sig_counter;    // local: [0] CTAs of this launch that have finished, [1] steps signalled so far (the
+                                // step number lives on the device so that a captured CUDA graph can be replayed)
 };
 
 __device__ __forceinline__ void store_score(const BatchView& b, int row, float v) {
@@ -61,9 +61,10 @@ __device__ __forceinline__ void gather_signal_tail(const BatchView& b) {
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(b.sig_counter, 1u) + 1u;
     if (done == gridDim.x) {
-      *b.sig_counter = 0u;
+      b.sig_counter[0] = 0u;
+      const uint32_t step = ++b.sig_counter[1];
       __threadfence_system();
-      for (int k = 0; k < b.n_sig; ++k) *reinterpret_cast<volatile uint32_t*>(b.sig_flags[k]) = b.sig_step;
+      for (int k = 0; k < b.n_sig; ++k) *reinterpret_cast<volatile uint32_t*>(b.sig_flags[k]) = step;
     }
   }
 }

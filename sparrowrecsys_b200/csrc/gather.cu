@@ -26,22 +26,30 @@ struct PeerGather {
   uint8_t* local = nullptr;           // own allocation
   uint8_t* base[8] = {nullptr};       // every rank's allocation in this process' address space (own included)
   bool opened[8] = {false};
-  unsigned int* counter = nullptr;    // local: finished CTAs of the launch in flight
-  uint32_t step = 0;
+  unsigned int* counter = nullptr;    // local device words: [0] finished CTAs of the launch in flight, [1] steps signalled,
+                                      // [2] steps waited for (device-side so that captured graphs can be replayed)
+  uint32_t step = 0;                  // host copy: only its parity (which buffer) is used
 
   float* buffer(int r, int parity) const { return reinterpret_cast<float*>(base[r] + (size_t)parity * buf_bytes); }
   uint32_t* flags(int r) const { return reinterpret_cast<uint32_t*>(base[r] + 2 * buf_bytes); }
 };
 
-__global__ void gather_signal_kernel(uint32_t step, int n, uint32_t* f0, uint32_t* f1, uint32_t* f2, uint32_t* f3,
-                                     uint32_t* f4, uint32_t* f5, uint32_t* f6, uint32_t* f7) {
+__global__ void gather_signal_kernel(unsigned int* counter, int n, uint32_t* f0, uint32_t* f1, uint32_t* f2,
+                                     uint32_t* f3, uint32_t* f4, uint32_t* f5, uint32_t* f6, uint32_t* f7) {
   uint32_t* f[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+  __shared__ uint32_t step_s;
+  if (threadIdx.x == 0) step_s = ++counter[1];
+  __syncthreads();
   __threadfence_system();
-  if (threadIdx.x < n) *reinterpret_cast<volatile uint32_t*>(f[threadIdx.x]) = step;
+  if (threadIdx.x < n) *reinterpret_cast<volatile uint32_t*>(f[threadIdx.x]) = step_s;
 }
 
-// one warp: lane r polls the flag of rank r until it has reached `step` (wrap-safe compare)
-__global__ void gather_wait_kernel(const uint32_t* flags, int n, uint32_t step) {
+// one warp: lane r polls the flag of rank r until it has reached this rank's own count of waits (wrap-safe compare)
+__global__ void gather_wait_kernel(const uint32_t* flags, int n, unsigned int* counter) {
+  __shared__ uint32_t step_s;
+  if (threadIdx.x == 0) step_s = ++counter[2];
+  __syncthreads();
+  const uint32_t step = step_s;
   if (threadIdx.x < n) {
     const volatile uint32_t* f = flags + threadIdx.x;
     while ((int32_t)(*f - step) < 0) {
@@ -62,8 +70,8 @@ cudaError_t gather_create(int device, int world, int rank, int64_t slice_rows, P
   const size_t total = 2 * g->buf_bytes + 256;
   e = cudaMalloc(&g->local, total);
   if (e == cudaSuccess) e = cudaMemset(g->local, 0, total);
-  if (e == cudaSuccess) e = cudaMalloc(&g->counter, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(g->counter, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&g->counter, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(g->counter, 0, 4 * sizeof(unsigned int));
   if (e != cudaSuccess) { cudaFree(g->local); cudaFree(g->counter); delete g; return e; }
   g->base[rank] = g->local;
   *out = g;
@@ -121,7 +129,6 @@ int gather_begin_step(PeerGather* g, BatchView& v, bool in_kernel_signal) {
   v.n_sig = 0;
   if (in_kernel_signal) {
     for (int r = 0; r < g->world; ++r) v.sig_flags[v.n_sig++] = g->flags(r) + g->rank;
-    v.sig_step = g->step;
     v.sig_counter = g->counter;
   }
   return parity;
@@ -130,13 +137,13 @@ int gather_begin_step(PeerGather* g, BatchView& v, bool in_kernel_signal) {
 cudaError_t gather_signal(PeerGather* g, cudaStream_t s) {
   uint32_t* f[8] = {nullptr};
   for (int r = 0; r < g->world; ++r) f[r] = g->flags(r) + g->rank;
-  gather_signal_kernel<<<1, 32, 0, s>>>(g->step, g->world, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
+  gather_signal_kernel<<<1, 32, 0, s>>>(g->counter, g->world, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
   ++g_launch_count;
   return cudaGetLastError();
 }
 
 cudaError_t gather_wait(PeerGather* g, cudaStream_t s) {
-  gather_wait_kernel<<<1, 32, 0, s>>>(g->flags(g->rank), g->world, g->step);
+  gather_wait_kernel<<<1, 32, 0, s>>>(g->flags(g->rank), g->world, g->counter);
   ++g_launch_count;
   return cudaGetLastError();
 }
