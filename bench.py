@@ -535,8 +535,25 @@ def run_ours(args):
         gather_note = fused.describe()
         extra_launches_per_batch = 1                               # the one-warp wait kernel
 
+        # The forward kernels run back to back on the launch stream; the wait for the N slices of step i - what a
+        # consumer of the gathered scores does - runs on a second stream.  Forward i + 2 reuses the gather buffer
+        # of step i, so it waits for that step's wait (two buffers alternate).
+        wait_stream = torch.cuda.Stream(device=dev)
+        fwd_done = [torch.cuda.Event() for _ in range(2)]
+        waited = [torch.cuda.Event() for _ in range(2)]
+        fused_state = {"n": 0}
+
         def launch(i, stream_ptr):                                 # noqa: F811 - the gathering launch
-            fused.predict(structs[i % ring], stream_ptr)
+            n = fused_state["n"]
+            cur = torch.cuda.current_stream()
+            if n >= 2:
+                cur.wait_event(waited[n & 1])                      # the consumer is done with this buffer
+            fused.predict(structs[i % ring], stream_ptr, wait=False)
+            fwd_done[n & 1].record(cur)
+            wait_stream.wait_event(fwd_done[n & 1])
+            fused.wait(wait_stream.cuda_stream)
+            waited[n & 1].record(wait_stream)
+            fused_state["n"] = n + 1
 
     stream = torch.cuda.Stream(device=dev)
     S = max(1, args.streams) if gather_mode is None else 1
@@ -557,9 +574,12 @@ def run_ours(args):
             if gather_buf is not None:
                 dist.all_gather_into_tensor(gather_buf, out[i % ring])     # communicator set-up outside the capture
         stream.synchronize()
-        if not args.no_graph:                          # (NCCL all-gathers are captured too: torch supports it)
+        if not args.no_graph and gather_mode != "nccl":   # (capturing the NCCL all-gathers hung on the box: direct launches)
             try:
                 g = torch.cuda.CUDAGraph()
+                if gather_mode == "fused":
+                    torch.cuda.synchronize()
+                    fused_state["n"] = 0                  # no waits on events recorded outside the capture
                 with torch.cuda.graph(g, stream=stream):
                     cur = torch.cuda.current_stream()
                     for sd in side:                       # fork: S branches, batch i on branch i % S
@@ -571,6 +591,8 @@ def run_ours(args):
                             dist.all_gather_into_tensor(gather_buf, out[i % ring])
                     for sd in side:                       # join
                         cur.wait_stream(sd)
+                    if gather_mode == "fused":
+                        cur.wait_stream(wait_stream)
                 graph = g
                 launch_mode = "one replay per step of a CUDA graph of %d launches (one per batch of the dataset)" % ring
                 if S > 1:
@@ -594,6 +616,8 @@ def run_ours(args):
                         dist.all_gather_into_tensor(gather_buf, out[i % ring])
                 for sd in side:
                     stream.wait_stream(sd)
+                if gather_mode == "fused":
+                    stream.wait_stream(wait_stream)
 
         run_steps(max(args.warmup, 3))
         stream.synchronize()

@@ -7,10 +7,10 @@ timeout -k 10 600 python -m pytest tests/test_multi_gpu.py -m gpu -q --timeout 6
 run() { # name, extra args
   timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline $2 > $O/bench_n${N}_$1.json 2> $O/bench_n${N}_$1.err; echo "bench $1 rc=$?"
 }
-run plain ""
+run plain "--no-e2e"
 run gather_nccl "--gather nccl --no-e2e"
 run gather_fused "--gather fused --no-e2e"
-run plain_s1_nograph "--streams 1 --no-graph --no-e2e"
+run plain_s1 "--streams 1 --no-e2e"
 for f in $O/bench_n${N}_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
