@@ -56,9 +56,10 @@ __device__ __forceinline__ void store_score(const BatchView& b, int row, float v
 // on the peers - and the step number goes out to the flag words the waiters poll.
 __device__ __forceinline__ void gather_signal_tail(const BatchView& b) {
   if (b.n_sig == 0) return;
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();                           // the CTA's score stores happen-before this barrier ...
   if (threadIdx.x == 0) {
+    __threadfence_system();                  // ... and one cumulative system-scope fence publishes them (a fence in
+                                             // every thread cost ~10 us per launch over NVLink)
     const unsigned int done = atomicAdd(b.sig_counter, 1u) + 1u;
     if (done == gridDim.x) {
       b.sig_counter[0] = 0u;
