@@ -113,6 +113,9 @@ def parse_args():
                     help="CTAs per launch with --streams S > 1 (default: SMs/S for kernels that hold a whole "
                          "SM per CTA, 0 = no limit for kernels that fit two CTAs per SM)")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--history", default=None, choices=["uniform", "zipf"],
+                    help="distribution of the history ids (default: uniform for cfg 5 - the L2-defeating worst case "
+                         "BASELINE.md asks for - Zipf(1.05) otherwise)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.batch is None:
@@ -145,7 +148,8 @@ def shared_config(args, spec, world):
             "global_batch": world * args.batch,
             "inputs": "synthetic MovieLens-20M-shaped rows (seeded): %s movie ids, history 0-padded to T "
                       "(padding included, as in the reference), random-init weights of the reference "
-                      "architecture (seed 2)" % ("uniform" if args.workload == "cfg5_din" else "Zipf(1.05)")}
+                      "architecture (seed 2)" % ("uniform" if ((args.history == "uniform") if args.history
+                                                                 else args.workload == "cfg5_din") else "Zipf(1.05)")}
 
 
 def make_weights(spec, device=None):
@@ -486,7 +490,7 @@ def run_ours(args):
     W, _table = make_weights(spec, dev)               # same weights on every rank (replicated)
     model = CTRModel(spec, W, device=local_rank)
     T = model.hist_cols
-    uniform_hist = args.workload == "cfg5_din"        # worst case for the 25.6 GB table: defeats L2
+    uniform_hist = (args.history == "uniform") if args.history else args.workload == "cfg5_din"   # worst case for the 25.6 GB table: defeats L2
 
     # ---- resident dataset: R distinct batches, footprint >> L2 ----------------------
     probe = encode_batch(spec, synthetic_features(spec, 8, seed=0))

@@ -98,6 +98,57 @@ def test_din_long_history_wide_embedding():
     _compare(spec, W, feats, logit_atol=5e-4)
 
 
+def test_din_cfg5_at_the_real_vocabulary():
+    """BASELINE cfg 5 as stated: V = 10^8 movies, E = 64, T = 200 - a 25.6 GB table generated in place in HBM
+    (srs_fill_uniform) and borrowed by the model.  The oracle cannot hold that table: it regenerates exactly the
+    rows the batch touches with the same counter-based formula (oracle.fill_uniform), remaps the ids to that
+    compact table and runs the reference graph on it."""
+    import torch
+    from dataclasses import replace
+    from sparrowrecsys_b200 import _lib
+    from sparrowrecsys_b200.spec import baseline_spec
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 70e9:
+        pytest.skip("needs ~55 GB of free HBM (25.6 GB table + its pre-split copy)")
+    spec = baseline_spec("cfg5_din")
+    B = 96
+    W = init_weights(spec, 4, skip=("embedding",))
+    feats = synthetic_features(spec, B, seed=9, uniform_history=True)
+    # DIN.py:95,125: the ids pass through a float32 numeric_column before the Embedding casts them back, so above
+    # 2^24 an id selects the row of its float32 rounding (99 999 937 -> 99 999 936); ids that would round to
+    # 10^8 = num_buckets are kept out (TF would assert)
+    top = 99_999_992
+    for k in ["movieId"] + ["userRatedMovie%d" % (t + 1) for t in range(spec.hist_len)]:
+        feats[k] = np.minimum(np.asarray(feats[k]), top).astype(np.int32)
+    feats["movieId"][:4] = [top, 0, 1, 99_999_937]                       # the ends of the table, an inexact id
+    dev = torch.device("cuda", 0)
+    table = torch.empty(spec.n_movies, spec.emb_dim, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().srs_fill_uniform(table.data_ptr(), table.numel(), 1234, -0.05, 0.05, 0, None))
+    torch.cuda.synchronize()
+    Wd = dict(W)
+    Wd["embedding"] = table
+    with _model(spec, Wd) as m:
+        assert m.kernel_name == "din_rt64_kernel"
+        p, z = m.predict_with_logits(feats)
+    del table
+    torch.cuda.empty_cache()
+    # the oracle side: compact table of the touched rows
+    keys = ["movieId"] + ["userRatedMovie%d" % (k + 1) for k in range(spec.hist_len)]
+    rt = lambda a: np.asarray(a).astype(np.float32).astype(np.int64)      # the float32 round trip of the graph
+    touched = np.unique(np.concatenate([rt(feats[k]) for k in keys]))
+    E = spec.emb_dim
+    flat = (touched[:, None] * E + np.arange(E)[None, :]).reshape(-1)
+    small = replace(spec, n_movies=int(touched.shape[0]))
+    Wo = dict(W)
+    Wo["embedding"] = O.fill_uniform(flat, 1234, -0.05, 0.05).reshape(-1, E)
+    fo = dict(feats)
+    for k in keys:
+        fo[k] = np.searchsorted(touched, rt(feats[k])).astype(np.int32)
+    po, zo = O.forward(small, Wo, fo)
+    assert np.abs(z - zo).max() <= 5e-4, "logit err %g" % np.abs(z - zo).max()
+    assert np.abs(p - po).max() <= PROB_ATOL, "prob err %g" % np.abs(p - po).max()
+
+
 @pytest.mark.parametrize("E,T", [(10, 5), (16, 7), (32, 33), (12, 64), (8, 1)])
 def test_din_shapes(E, T):
     spec = default_spec("din", emb_dim=E, hist_len=T, n_movies=5000, n_users=3000)
