@@ -804,6 +804,10 @@ def run_ours(args):
 
 
 def main():
+    # a run that an outer `timeout` ends leaves the Python stacks of all threads on stderr
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -195,16 +195,23 @@ def synthetic_features(spec: ModelSpec, batch: int, seed: int, *, zipf_a: float 
     rng = np.random.default_rng(seed)
     B = batch
 
+    # DIN.py:95,125 feeds the movie ids through float32: above 2**24 an id is rounded, and the last few
+    # ids of a 10**8 vocabulary round UP to the vocabulary size (out of range in the reference too).
+    # Draw only ids whose float32 image is still inside the vocabulary (no change for V <= 2**24).
+    top = spec.n_movies
+    while int(np.float32(top - 1)) >= spec.n_movies:
+        top -= 1
+
     def movie_ids(n):
         if uniform_history:
-            return rng.integers(1, spec.n_movies, size=n, dtype=np.int64)
+            return rng.integers(1, top, size=n, dtype=np.int64)
         # Zipf over ranks 1..V-1 by inverse-CDF on a truncated power law
         u = rng.random(n)
         V = spec.n_movies - 1
         a = zipf_a
         # continuous approximation of truncated zipf: x = ((V^(1-a)-1)u+1)^(1/(1-a))
         x = ((V ** (1.0 - a) - 1.0) * u + 1.0) ** (1.0 / (1.0 - a))
-        return np.clip(np.floor(x).astype(np.int64), 1, V)
+        return np.clip(np.floor(x).astype(np.int64), 1, top - 1)
 
     f: Dict[str, np.ndarray] = {}
     f["movieId"] = movie_ids(B).astype(np.int32)
