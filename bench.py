@@ -297,12 +297,17 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)"
 
 
-def ncu_traffic(kernel_name):
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu summary of
-    the benched configuration (profiles/ncu_bench_summary.json: {kernel: {...}}), or None."""
+def ncu_traffic(workload, kernel_name, batch):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu summary of this
+    workload (profiles/ncu_bench_summary.json, written by profiles/summarize_r02.py from one
+    `ncu --set full` capture of `bench.py --workload W`), or None when the capture was of another
+    kernel or batch size."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_bench_summary.json")) as f:
-            return json.load(f)[kernel_name].get("dram_bytes_per_launch")
+            rec = json.load(f)[workload]
+        if rec.get("kernel") != kernel_name or int(rec.get("batch", -1)) != int(batch):
+            return None
+        return rec.get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -449,7 +454,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -771,7 +776,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic(model.kernel_name),
+                         "traffic": ncu_traffic(args.workload, model.kernel_name, B),
                          "algorithmic_bytes_per_launch": bpi * B, "launch_us": launch_us,
                          "peak_source": peak_src},
         }
@@ -796,19 +801,38 @@ def run_ours(args):
                                                        "the device")
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(args, spec, feats)
-        print(json.dumps(line))
+        emit(line)
     model.close()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE line of stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     # a run that an outer `timeout` ends leaves the Python stacks of all threads on stderr
     import faulthandler
     import signal
     faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
     args = parse_args()
+    # stdout carries the JSON line and nothing else: whatever libraries print there (NCCL's version banner
+    # comes from C code) goes to stderr instead
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

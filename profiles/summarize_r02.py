@@ -24,6 +24,15 @@ EXTRA = ["sm__icc_request_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t
 S.KEYS.extend(k for k in EXTRA if k not in S.KEYS)
 
 
+# capture name -> bench workload (the captures ran `bench.py --workload W` at its default batch)
+WORKLOAD_OF = {"ncu_cfg1_embmlp_tc": "cfg1_embeddingmlp", "ncu_cfg2_deepfm2": "cfg2_deepfm_v2",
+               "ncu_cfg2_deepfm_tc": "cfg2_deepfm", "ncu_cfg3_din_rt": "cfg3_din", "ncu_cfg4_ncf": "cfg4_neuralcf",
+               "ncu_cfg4_widendeep": "cfg4_widendeep", "ncu_cfg5_din_rt64": "cfg5_din", "ncu_ref_dien": "ref_dien"}
+sys.path.insert(0, ROOT)
+import bench   # noqa: E402
+BENCH_BATCH = {w: v[0] for w, v in bench.WORKLOADS.items()}
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r2f1")
     out_dir = os.path.join(ROOT, "profiles", "r02")
@@ -40,10 +49,9 @@ def main():
         d = json.load(open(out))
         d["report"] = os.path.relpath(rep, ROOT)
         json.dump(d, open(out, "w"), indent=1)
-        kernel = d["kernel"].split("(")[0].split("::")[-1].split("<")[0]
-        if "wide" in name:
-            kernel += "<wide&deep>"
-        summary.setdefault(kernel, {k: d.get(k) for k in (
+        kernel = d["kernel"].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
+        workload = WORKLOAD_OF[name]
+        summary[workload] = dict(kernel=kernel, batch=BENCH_BATCH[workload], **{k: d.get(k) for k in (
             "duration_us", "dram_bytes_per_launch", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -53,9 +61,9 @@ def main():
     lc = os.path.join(src, "launches_cfg3_default.csv")
     if os.path.exists(lc):
         S.launches(lc, os.path.join(out_dir, "launches_cfg3_default.txt"))
-    for f in glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(src, "*.log")) + \\
+    for f in glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(src, "*.log")) + \
             glob.glob(os.path.join(src, "smi.txt")):
-        if os.path.getsize(f) < 300000:
+        if 0 < os.path.getsize(f) < 300000:
             subprocess.call(["cp", f, os.path.join(out_dir, os.path.basename(f))])
 
 

@@ -22,6 +22,39 @@
 
 namespace srs {
 
+// ---- debugging aid (-DRT64_WATCHDOG, profiles/exp/rt64_hang_probe.py): every mbarrier wait of this file gives up
+// after ~2^22 polls, records {source line, block, thread, parity} and lets the launch run to its end (with
+// invalid scores); srs_model_status() then reports the records instead of the process hanging.
+__device__ unsigned int g_rt64_abort;
+__device__ unsigned int g_rt64_nrec;
+__device__ unsigned long long g_rt64_rec[64];
+#ifdef RT64_WATCHDOG
+__device__ __noinline__ void rt64_record(int line, uint32_t parity) {
+  const unsigned int m = __activemask();
+  if ((threadIdx.x & 31) != __ffs(m) - 1) return;        // one record per waiting warp
+  atomicExch(&g_rt64_abort, 1u);
+  const unsigned int i = atomicAdd(&g_rt64_nrec, 1u);
+  if (i < 16u) {
+    g_rt64_rec[4 * i] = (unsigned long long)line;
+    g_rt64_rec[4 * i + 1] = (unsigned long long)blockIdx.x;
+    g_rt64_rec[4 * i + 2] = (unsigned long long)threadIdx.x | ((unsigned long long)m << 32);
+    g_rt64_rec[4 * i + 3] = (unsigned long long)parity;
+  }
+  __threadfence();
+}
+__device__ __forceinline__ void rt64_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const bool aborted = *reinterpret_cast<volatile unsigned int*>(&g_rt64_abort) != 0;
+      if (spins >= (1u << 22) || (aborted && spins >= (1u << 20))) { rt64_record(line, parity); return; }
+      if (aborted) return;
+    }
+  }
+}
+#define mbar_wait(bar, par) rt64_wait_dbg(bar, par, __LINE__)
+#endif
+
 constexpr int k64Threads = 512;
 constexpr int k64Rows = 32;                 // row slots per group = N/2 of the top-MLP MMAs
 constexpr int k64Slots = 4;
@@ -617,6 +650,27 @@ cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cuda
   split_table64_kernel<<<(unsigned)blocks, threads, 0, s>>>(src, reinterpret_cast<uint32_t*>(dst), n_pairs);
   ++g_launch_count;
   return cudaGetLastError();
+}
+
+#ifdef RT64_WATCHDOG
+#undef mbar_wait
+#endif
+
+// *n = number of timed-out waits recorded since the last call (always 0 unless built with -DRT64_WATCHDOG)
+cudaError_t take_din_rt64_abort(int* n, unsigned long long* rec64) {
+  unsigned int flag = 0, cnt = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&flag, g_rt64_abort, sizeof(flag));
+  if (e != cudaSuccess) return e;
+  *n = 0;
+  if (!flag) return cudaSuccess;
+  e = cudaMemcpyFromSymbol(&cnt, g_rt64_nrec, sizeof(cnt));
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(rec64, g_rt64_rec, sizeof(unsigned long long) * 64);
+  if (e != cudaSuccess) return e;
+  *n = (int)(cnt < 16u ? cnt : 16u);
+  flag = 0;
+  e = cudaMemcpyToSymbol(g_rt64_abort, &flag, sizeof(flag));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_rt64_nrec, &flag, sizeof(flag));
+  return e;
 }
 
 size_t din_rt64_smem_bytes() { return 1024 + RING64 + Q64_BYTES; }

@@ -249,6 +249,7 @@ cudaError_t read_din_rtp_trace(unsigned long long* out40);
 cudaError_t take_din_rtp_abort(int* aborted, unsigned long long* rec4);
 cudaError_t read_din_rtp_timeline(unsigned long long* out768);
 cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s);
+cudaError_t take_din_rt64_abort(int* n, unsigned long long* rec64);   // debugging builds (-DRT64_WATCHDOG) only
 cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cudaStream_t s);
 cudaError_t setup_din_rt64_attributes();
 cudaError_t launch_din_tc(const DinTcParams& p, const BatchView& b, cudaStream_t s);

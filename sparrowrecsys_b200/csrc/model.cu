@@ -1735,6 +1735,19 @@ int srs_model_status(srs_model* m) {
       return fail(SRS_ERR_CUDA, "din_rtp_kernel: an mbarrier wait timed out (wait code %llu, block %llu, thread %llu, "
                   "parity %llu); the scores of that launch are invalid", rec[0], rec[1], rec[2], rec[3]);
   }
+  if (m->spec.kind == SRS_DIN) {                     // -DRT64_WATCHDOG builds of din_rt64.cu only
+    int n = 0;
+    unsigned long long rec[64];
+    CUDA_TRY(take_din_rt64_abort(&n, rec));
+    if (n > 0) {
+      char msg[900];
+      int at = snprintf(msg, sizeof(msg), "din_rt64_kernel: %d mbarrier wait(s) timed out [line/block/thread/parity]:", n);
+      for (int i = 0; i < n && at < (int)sizeof(msg) - 60; ++i)
+        at += snprintf(msg + at, sizeof(msg) - at, " %llu/%llu/%llu/%llu", rec[4 * i], rec[4 * i + 1],
+                       rec[4 * i + 2] & 0xffffffffull, rec[4 * i + 3]);
+      return fail(SRS_ERR_CUDA, "%s", msg);
+    }
+  }
   int flags[kErrWords] = {0};
   CUDA_TRY(cudaMemcpy(flags, m->err_flag, kErrWords * sizeof(int), cudaMemcpyDeviceToHost));
   bool any = false;
