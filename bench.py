@@ -104,6 +104,8 @@ def parse_args():
                     help="exchange the scores after every launch (N > 1): torch NCCL all-gather, or the "
                          "kernel storing into the peers' gather buffers (fused)")
     ap.add_argument("--no-graph", action="store_true", help="launch directly instead of CUDA graphs")
+    ap.add_argument("--graph", action="store_true",
+                    help="cfg5_din only: replay a CUDA graph although that is off by default there (see below)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=None,
@@ -120,6 +122,10 @@ def parse_args():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = WORKLOADS[args.workload][0]
+    # cfg 5 launches directly: CUDA-graph replays of din_rt64_kernel on the 10^8-row table did not finish in
+    # 11 of 19 runs on the B200 (direct launches: 4 of 4 finished, same throughput; profiles/r02/rt64_pdl/)
+    if args.workload == "cfg5_din" and not args.graph:
+        args.no_graph = True
     if args.streams is None:
         # batches in flight side by side (steady-state throughput is quoted
         # with batches in flight, single-call latency separately).  cfg 5 launches fill the machine.

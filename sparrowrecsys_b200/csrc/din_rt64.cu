@@ -53,6 +53,11 @@ __device__ __forceinline__ void rt64_wait_dbg(uint64_t* bar, uint32_t parity, in
   }
 }
 #define mbar_wait(bar, par) rt64_wait_dbg(bar, par, __LINE__)
+#elif defined(RT64_SLEEP_NS)
+__device__ __forceinline__ void rt64_wait_sleep(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(RT64_SLEEP_NS);
+}
+#define mbar_wait(bar, par) rt64_wait_sleep(bar, par)
 #endif
 
 constexpr int k64Threads = 512;
@@ -652,7 +657,7 @@ cudaError_t launch_split_table64(const float* src, void* dst, int64_t rows, cuda
   return cudaGetLastError();
 }
 
-#ifdef RT64_WATCHDOG
+#if defined(RT64_WATCHDOG) || defined(RT64_SLEEP_NS)
 #undef mbar_wait
 #endif
 
@@ -675,8 +680,7 @@ cudaError_t take_din_rt64_abort(int* n, unsigned long long* rec64) {
 
 size_t din_rt64_smem_bytes() { return 1024 + RING64 + Q64_BYTES; }
 
-cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s) {
-  if (b.B <= 0) return cudaSuccess;
+static cudaError_t launch_din_rt64_once(const DinRtParams& p, const BatchView& b, cudaStream_t s) {
   DinRtParams q = p;
   const int waves = (b.B + k64Rows * p.num_sms - 1) / (k64Rows * p.num_sms);
   int rpg = (b.B + waves * p.num_sms - 1) / (waves * p.num_sms);
@@ -693,9 +697,40 @@ cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+#ifdef RT64_NO_PDL                     // (experiment switch: profiles/r02/rt64_pdl/README.md)
+  cfg.numAttrs = 0;
+#else
   cfg.numAttrs = 1;
+#endif
   ++g_launch_count;
   return cudaLaunchKernelEx(&cfg, din_rt64_kernel, q, b);
+}
+
+// RT64_CHUNK_GROUPS > 0: a call is split into launches of at most that many row groups per CTA
+#ifndef RT64_CHUNK_GROUPS
+#define RT64_CHUNK_GROUPS 0
+#endif
+
+cudaError_t launch_din_rt64(const DinRtParams& p, const BatchView& b, cudaStream_t s) {
+  if (b.B <= 0) return cudaSuccess;
+  const int64_t max_rows = RT64_CHUNK_GROUPS > 0 ? (int64_t)RT64_CHUNK_GROUPS * p.num_sms * k64Rows : (int64_t)b.B;
+  if (b.B <= max_rows) return launch_din_rt64_once(p, b, s);
+  for (int64_t lo = 0; lo < b.B; lo += max_rows) {
+    BatchView c = b;
+    c.B = (int)((b.B - lo) < max_rows ? (b.B - lo) : max_rows);
+    c.movie_id = b.movie_id + lo;
+    c.user_id = b.user_id + lo;
+    c.hist = b.hist + lo * b.hist_stride;
+    c.movie_genre = b.movie_genre + lo * 3;
+    c.user_genre = b.user_genre + lo * 5;
+    c.numerics = b.numerics + lo * kNumNumerics;
+    c.probs = b.probs + lo;
+    if (b.logits) c.logits = b.logits + lo;
+    for (int k = 0; k < b.n_peers; ++k) c.peer_probs[k] = b.peer_probs[k] + lo;
+    cudaError_t e = launch_din_rt64_once(p, c, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t setup_din_rt64_attributes() {
