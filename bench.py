@@ -123,7 +123,7 @@ def parse_args():
     if args.batch is None:
         args.batch = WORKLOADS[args.workload][0]
     # cfg 5 launches directly: CUDA-graph replays of din_rt64_kernel on the 10^8-row table did not finish in
-    # 11 of 19 runs on the B200 (direct launches: 4 of 4 finished, same throughput; profiles/r02/rt64_pdl/)
+    # 11 of 18 runs on the B200 (direct launches: 4 of 4 finished, same throughput; profiles/r02/rt64_hang/)
     if args.workload == "cfg5_din" and not args.graph:
         args.no_graph = True
     if args.streams is None:

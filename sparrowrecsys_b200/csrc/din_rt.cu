@@ -100,6 +100,15 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
   __shared__ uint64_t empty[kRtSlots];      // both MMAs of the tile in the slot have completed
   __shared__ uint64_t d1_full[3];           // tile K: activation-unit accumulators in buffer K % 3 ready
   __shared__ uint64_t w_ready[2];           // consumer q: pooling weights written (128 arrivals)
+#ifdef SRS_WREADY_SPLIT
+  // one barrier per (consumer, pooled buffer): see din_rt64.cu and profiles/exp/rt_protocol_sim.py
+  __shared__ uint64_t w_ready_u1[2];
+#define W_READY(q, u) ((u) ? &w_ready_u1[q] : &w_ready[q])
+#define W_READY_PAR(K) (((K) >> 2) & 1)
+#else
+#define W_READY(q, u) (&w_ready[q])
+#define W_READY_PAR(K) (((K) >> 1) & 1)
+#endif
   __shared__ uint64_t d2_full[2][2];        // consumer q, buffer u: pooled accumulators ready
   __shared__ uint32_t tmem_slot;
 
@@ -170,6 +179,9 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
     else if (l < 2 * kRtSlots + 9) mbar_init(&d2_full[(l - 2 * kRtSlots - 5) >> 1][(l - 2 * kRtSlots - 5) & 1], 1);
     else if (l == 2 * kRtSlots + 9) mbar_init(&wbar, 1);
     else if (l == 2 * kRtSlots + 10) mbar_init(&cbar, 1);
+#ifdef SRS_WREADY_SPLIT
+    else if (l < 2 * kRtSlots + 13) mbar_init(&w_ready_u1[l - 2 * kRtSlots - 11], 128);
+#endif
     fence_mbar_init();
   }
   // per-thread constants of the roles
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
       if (2 < n_tiles) mma1(2);
       for (int k = 0; k < n_tiles; ++k) {
         const int K = kbase + k, slot = K % kRtSlots, q = K & 1, u = (K >> 1) & 1;
-        mbar_wait(&w_ready[q], (K >> 1) & 1);
+        mbar_wait(W_READY(q, u), W_READY_PAR(K));
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD2 = tbase + TMC_D2 + 32u * q + 16u * u;
@@ -472,7 +484,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) din_rt_kernel(const __grid_cons
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&w_ready[q]);
+        mbar_arrive(W_READY(q, u));
         if (k == first + 2) RT_TRACE(11, tid == 256);
         if (k - 2 >= 0) pool_out(k - 2);                    // the previous tile's pooling MMAs finished long ago
         if (k == first + 2) RT_TRACE(16, tid == 256);

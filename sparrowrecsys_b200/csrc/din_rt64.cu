@@ -110,6 +110,19 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
   __shared__ uint64_t empty[k64Slots];      // both MMA groups of the tile in the slot have completed
   __shared__ uint64_t d1_full[3];           // tile K: gate accumulators in buffer K % 3 ready
   __shared__ uint64_t w_ready[2];           // consumer q: pooling weights written (128 arrivals)
+#ifdef SRS_WREADY_SPLIT
+  // One barrier per (consumer, pooled buffer).  The four warps of a consumer are not synchronised with each
+  // other: a warp that finds the accumulators of its next tile ready can arrive for tile K + 2 while a sibling is
+  // still gating tile K, and with ONE barrier per consumer that arrival completes tile K's phase for the sibling
+  // (profiles/exp/rt_protocol_sim.py --single-wready: mixed phases, then parity aliasing on d1_full and a
+  // deadlock).  With the split, the early arrival lands on the other buffer's barrier.
+  __shared__ uint64_t w_ready_u1[2];
+#define W_READY(q, u) ((u) ? &w_ready_u1[q] : &w_ready[q])
+#define W_READY_PAR(K) (((K) >> 2) & 1)
+#else
+#define W_READY(q, u) (&w_ready[q])
+#define W_READY_PAR(K) (((K) >> 1) & 1)
+#endif
   __shared__ uint64_t d2_full[2][2];        // consumer q, buffer u: pooled accumulators ready
   __shared__ uint32_t tmem_slot;
 
@@ -163,6 +176,9 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
     for (int i = 0; i < 3; ++i) mbar_init(&d1_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&w_ready[i], 128);
+#ifdef SRS_WREADY_SPLIT
+      mbar_init(&w_ready_u1[i], 128);
+#endif
       mbar_init(&d2_full[i][0], 1); mbar_init(&d2_full[i][1], 1);
     }
     fence_mbar_init();
@@ -372,7 +388,7 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
       if (2 < n_tiles) mma1(2);
       for (int k = 0; k < n_tiles; ++k) {
         const int K = kbase + k, slot = K % k64Slots, q = K & 1, u = (K >> 1) & 1;
-        mbar_wait(&w_ready[q], (K >> 1) & 1);
+        mbar_wait(W_READY(q, u), W_READY_PAR(K));
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tD2 = tbase + T64_D2 + 32u * q + 16u * u;
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(k64Threads, 1) din_rt64_kernel(const __grid_co
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&w_ready[q]);
+        mbar_arrive(W_READY(q, u));
         if (k - 2 >= 0) pool_out(k - 2);
       }
       {
@@ -697,7 +713,7 @@ static cudaError_t launch_din_rt64_once(const DinRtParams& p, const BatchView& b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-#ifdef RT64_NO_PDL                     // (experiment switch: profiles/r02/rt64_pdl/README.md)
+#ifdef RT64_NO_PDL                     // (experiment switch: profiles/r02/rt64_hang/README.md)
   cfg.numAttrs = 0;
 #else
   cfg.numAttrs = 1;

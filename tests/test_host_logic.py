@@ -234,3 +234,20 @@ def test_din_rtp_barrier_protocol_model():
     for shape in ([1], [14], [14, 14, 14], [1, 1, 1, 1, 1, 1], [2, 1, 3, 1, 1, 2], [16, 1, 5, 16, 1, 1, 7]):
         for seed in range(10):
             sim.Sim(shape, seed).run()
+
+
+def test_row_tile_barrier_protocol_model():
+    """din_rt_kernel / din_rt64_kernel share one mbarrier protocol; profiles/exp/rt_protocol_sim.py runs it on the
+    CPU with warp-level actors under random interleavings.  The shipped kernels keep ONE pooling-weights barrier
+    per consumer (w_ready[q]); the model shows what that allows when a consumer warp lags its siblings by a tile
+    or the issuer is late - a phase completed by arrivals of two different tiles, then parity aliasing and a
+    deadlock - and that one barrier per (consumer, pooled buffer) (-DSRS_WREADY_SPLIT, the form din_rtp uses)
+    has none of it.  DESIGN.md section 9 item 1."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "rt_protocol_sim", os.path.join(ROOT, "profiles", "exp", "rt_protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    assert sim.check(False, runs=21) == []
+    broken = sim.check(True, runs=21)
+    assert broken and any("different tiles" in m or "Deadlock" in m or "meant completion" in m for _, _, m in broken)
