@@ -86,7 +86,7 @@ def metric_name(workload):
     return METRIC if workload == WORKLOAD else "CTR inferences/sec (%s)" % WORKLOADS[workload][1]
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -119,7 +119,7 @@ def parse_args():
                     help="distribution of the history ids (default: uniform for cfg 5 - the L2-defeating worst case "
                          "BASELINE.md asks for - Zipf(1.05) otherwise)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     if args.batch is None:
         args.batch = WORKLOADS[args.workload][0]
     # cfg 5 launches directly: CUDA-graph replays of din_rt64_kernel on the 10^8-row table did not finish in

@@ -239,8 +239,10 @@ class Sim:
         return tuple((x.done, x.pending) for x in bars) + tuple(self.group_sync) + (len(self.pipe), self.ticks)
 
 
-def check(single, runs=300, seed0=0, verbose=False):
-    """Returns the list of (seed, shape, message) failures."""
+def check(single, runs=300, seed0=0, verbose=False, slots=4):
+    """Returns the list of (seed, shape, message) failures.  slots: 4 = din_rt64's ring, 8 = din_rt's."""
+    global SLOTS
+    SLOTS = slots
     failures = []
     shapes = [[64], [56, 56], [14, 14, 14], [64, 64, 64], [2, 6, 2], [7, 5], [100]]
     stalls = [lambda r: 0,
@@ -260,6 +262,10 @@ def check(single, runs=300, seed0=0, verbose=False):
 
 if __name__ == "__main__":
     single = "--single-wready" in sys.argv
-    f = check(single, verbose=True)
-    print("%s protocol: %d of 300 random schedules failed" % ("single-w_ready" if single else "w_ready[q][u]", len(f)))
-    sys.exit(1 if f and not single else 0)
+    bad = 0
+    for slots in (4, 8):
+        f = check(single, verbose=True, slots=slots)
+        print("%d-slot ring, %s protocol: %d of 300 random schedules failed" % (
+            slots, "single-w_ready" if single else "w_ready[q][u]", len(f)))
+        bad += len(f)
+    sys.exit(1 if bad and not single else 0)
