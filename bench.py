@@ -38,6 +38,9 @@ collective (weak scaling: 4096 rows per GPU per launch); `--gather` adds the exc
 that a ranking call spanning GPUs needs (`--gather nccl`: torch NCCL all-gather per launch;
 `--gather fused`: the kernel's epilogue stores its scores into every peer's gather buffer over
 NVLink).  Each rank binds to the CPUs of its GPU's NUMA node before it allocates pinned memory.
+`--workload cfg5_din` (10^8-row table) launches directly instead of replaying a graph (`--graph`
+restores the replay; why: DESIGN.md section 6).  stdout carries the one JSON line and nothing else;
+an outer `timeout` (SIGTERM) makes the script dump its Python stacks to stderr first.
 """
 from __future__ import annotations
 
