@@ -13,7 +13,12 @@ graphs from the reference scripts plus the TF semantics recorded in SURVEY.md
 section 8a.  What *does* anchor it: the reference's shipped trained weights
 (`modeldata/neuralcf/{001,002}`, `modeldata/MLPRec/005`) on the bundled
 `testSamples.csv` rows reproduce the known answers recorded in SURVEY.md
-section 8c (tests/test_oracle_golden.py), computed by an independent restatement.
+section 8c (tests/test_oracle_golden.py), computed by an independent restatement,
+and - round 2 - the outputs of the reference's own serialised `serving_default`
+functions (`saved_model.pb` of those three exports, evaluated node by node by
+`oracle/savedmodel_graph.py`; `tests/golden/savedmodel_graph_vectors.json`): for
+`neuralcf_forward` and the shipped form of `twotowers_forward` the graph wiring is
+TensorFlow's, not a reading of the script.  The other graphs stay unpinned.
 
 All paths below are relative to
 /root/reference/TFRecModel/src/com/sparrowrecsys/offline/tensorflow/.

@@ -1,0 +1,256 @@
+"""Evaluate the serving function of a reference SavedModel straight from its `saved_model.pb` - TEST INFRASTRUCTURE.
+
+The reference ships three trained exports (`src/main/resources/webroot/modeldata/neuralcf/{001,002}`, `MLPRec/005`).
+TensorFlow cannot run here, but the graph TensorFlow serialised can be read: this module decodes the protobuf
+without schemas (field numbers of saved_model.proto / meta_graph.proto / graph.proto / function.proto /
+node_def.proto / attr_value.proto / tensor.proto), follows `serving_default` -> signature wrapper ->
+`__inference__wrapped_model_*`, binds every resource argument of that function to its checkpoint tensor through the
+export's own `__inference__traced_restore_*` function, and evaluates the function node by node in float32.
+
+What is interpreted from the graph, not from the Python script: which placeholder and which table feed each
+DenseFeatures block, the order of the concatenation, which kernel / bias every MatMul / BiasAdd reads, the
+activations, the Dot / Squeeze tail, the output tensor.  What is restated: the body of a DenseFeatures block with one
+identity-categorical embedding column (`safe_embedding_lookup_sparse`, combiner "mean", over exactly one id per row)
+is taken as "row `id` of the table the block's ResourceGather reads" instead of executing its ~90 sparse ops.
+
+Used by `tests/golden/make_savedmodel_graph_vectors.py` (writes `tests/golden/savedmodel_graph_vectors.json`) and
+`tests/test_oracle_golden.py`; never imported by the product.
+"""
+import os
+import struct
+
+import numpy as np
+
+
+# ---- schema-less protobuf ---------------------------------------------------------------------------------
+def _varint(b, p):
+    r = s = 0
+    while True:
+        c = b[p]
+        p += 1
+        r |= (c & 0x7F) << s
+        s += 7
+        if c < 0x80:
+            return r, p
+
+
+def fields(b):
+    p, out = 0, []
+    while p < len(b):
+        k, p = _varint(b, p)
+        f, w = k >> 3, k & 7
+        if w == 0:
+            v, p = _varint(b, p)
+        elif w == 2:
+            n, p = _varint(b, p)
+            v = b[p:p + n]
+            p += n
+        elif w == 5:
+            v = b[p:p + 4]
+            p += 4
+        elif w == 1:
+            v = b[p:p + 8]
+            p += 8
+        else:
+            raise ValueError("wire type %d" % w)
+        out.append((f, w, v))
+    return out
+
+
+def get(fs, f):
+    return [v for (ff, _, v) in fs if ff == f]
+
+
+def _packed_varints(v):
+    if isinstance(v, int):
+        return [v]
+    out, p = [], 0
+    while p < len(v):
+        x, p = _varint(v, p)
+        out.append(x)
+    return out
+
+
+def _signed(x, bits=64):
+    return x - (1 << bits) if x >= 1 << (bits - 1) else x
+
+
+def tensor_proto(buf):
+    """TensorProto -> numpy (the dtypes these graphs use)."""
+    f = fields(buf)
+    dtype = get(f, 1)[0]
+    shape = [_signed(get(fields(d), 1)[0]) if get(fields(d), 1) else 0 for d in get(fields(get(f, 2)[0]), 2)] if get(f, 2) else []
+    content = get(f, 4)
+    if dtype == 7:                                   # DT_STRING
+        return np.array([s.decode() for s in get(f, 8)], dtype=object).reshape(shape)
+    np_t = {1: np.float32, 3: np.int32, 9: np.int64, 10: np.bool_}[dtype]
+    if content:
+        return np.frombuffer(content[0], dtype=np_t).reshape(shape).copy()
+    if dtype == 1:
+        vals = [x for v in get(f, 5) for x in (struct.unpack("<%df" % (len(v) // 4), v) if isinstance(v, bytes) else [v])]
+    elif dtype == 3:
+        vals = [_signed(x) for v in get(f, 7) for x in _packed_varints(v)]
+    elif dtype == 9:
+        vals = [_signed(x) for v in get(f, 10) for x in _packed_varints(v)]
+    else:
+        vals = [x for v in get(f, 11) for x in _packed_varints(v)]
+    n = int(np.prod(shape)) if shape else 1
+    if len(vals) == 1 and n > 1:
+        vals = vals * n
+    return np.array(vals, dtype=np_t).reshape(shape)
+
+
+class Node:
+    def __init__(self, buf):
+        f = fields(buf)
+        self.name = get(f, 1)[0].decode()
+        self.op = get(f, 2)[0].decode()
+        self.inputs = [i.decode() for i in get(f, 3)]
+        self.attr = {}
+        for a in get(f, 5):
+            e = fields(a)
+            self.attr[get(e, 1)[0].decode()] = fields(get(e, 2)[0]) if get(e, 2) else []
+
+    def data_inputs(self):
+        return [i for i in self.inputs if not i.startswith("^")]
+
+    def func(self, key="f"):
+        return get(fields(get(self.attr[key], 10)[0]), 1)[0].decode()
+
+    def b(self, key, default=False):
+        v = get(self.attr.get(key, []), 5)
+        return bool(v[0]) if v else default
+
+    def ints(self, key):
+        lst = get(self.attr.get(key, []), 1)
+        return [_signed(x) for v in get(fields(lst[0]), 3) for x in _packed_varints(v)] if lst else []
+
+
+class Function:
+    def __init__(self, buf):
+        f = fields(buf)
+        sig = fields(get(f, 1)[0])
+        self.name = get(sig, 1)[0].decode()
+        self.args = [get(fields(a), 1)[0].decode() for a in get(sig, 2)]
+        self.outs = [get(fields(a), 1)[0].decode() for a in get(sig, 3)]
+        self.nodes = {}
+        for n in get(f, 3):
+            nd = Node(n)
+            self.nodes[nd.name] = nd
+        self.ret = {get(fields(r), 1)[0].decode(): get(fields(r), 2)[0].decode() for r in get(f, 4)}
+
+
+class ServingGraph:
+    """The `serving_default` computation of one export, with its variables bound."""
+
+    def __init__(self, savedmodel_dir, read_variables):
+        sm = fields(open(os.path.join(savedmodel_dir, "saved_model.pb"), "rb").read())
+        mg = fields(get(sm, 2)[0])
+        gd = fields(get(mg, 2)[0])
+        top = [Node(n) for n in get(gd, 1)]
+        self.funcs = {}
+        for fb in get(fields(get(gd, 2)[0]), 1):
+            fn = Function(fb)
+            self.funcs[fn.name] = fn
+        calls = [n for n in top if n.op in ("StatefulPartitionedCall", "PartitionedCall")]
+        sig_call = [n for n in calls if n.func().startswith("__inference_signature_wrapper")]
+        assert len(sig_call) == 1
+        wrapper = self.funcs[sig_call[0].func()]
+        inner = [n for n in wrapper.nodes.values() if n.op == "StatefulPartitionedCall"]
+        assert len(inner) == 1 and inner[0].data_inputs() == wrapper.args, "the wrapper forwards its arguments in order"
+        self.fn = self.funcs[inner[0].func()]
+        assert self.fn.name.startswith("__inference__wrapped_model")
+        bound = dict(zip(self.fn.args, sig_call[0].data_inputs()))      # function argument -> top-level node name
+        self.placeholders = {a: v[len("serving_default_"):] for a, v in bound.items() if v.startswith("serving_default_")}
+        var_of_arg = {a: v for a, v in bound.items() if a not in self.placeholders}
+        # variable node -> checkpoint key, read off the export's own restore function
+        rest_call = [n for n in calls if n.func().startswith("__inference__traced_restore")][0]
+        rest = self.funcs[rest_call.func()]
+        node_of_arg = dict(zip(rest.args, rest_call.data_inputs()))
+        names = tensor_proto(get(rest.nodes["RestoreV2/tensor_names"].attr["value"], 8)[0]).reshape(-1)
+        key_of_var = {}
+        for n in rest.nodes.values():
+            if n.op != "AssignVariableOp":
+                continue
+            res, val = n.data_inputs()
+            src = rest.nodes[val.split(":")[0]].data_inputs()[0]         # Identity_k <- RestoreV2:tensors:k
+            if not src.startswith("RestoreV2:tensors:"):
+                continue
+            key_of_var[node_of_arg[res]] = names[int(src.rsplit(":", 1)[1])]
+        ckpt = read_variables(os.path.join(savedmodel_dir, "variables"))
+        # checkpoint keys are object-graph paths: "<path>/.ATTRIBUTES/VARIABLE_VALUE", "/" inside a name escaped as ".S"
+        strip = lambda k: (k[:-len("/.ATTRIBUTES/VARIABLE_VALUE")] if k.endswith("/.ATTRIBUTES/VARIABLE_VALUE") else k).replace(".S", "/")
+        self.variables = {a: np.asarray(ckpt[strip(key_of_var[v])], dtype=np.float32) for a, v in var_of_arg.items()}
+        self.variable_names = {a: (v, strip(key_of_var[v])) for a, v in var_of_arg.items()}
+        self.trace = []                                                  # (node, op) in evaluation order
+
+    # ---- evaluation -----------------------------------------------------------------------------------------
+    def _dense_features(self, scope, feeds):
+        """One DenseFeatures block with a single identity-categorical embedding column (see the module docstring):
+        the placeholder and the table are read off the graph."""
+        inside = [n for n in self.fn.nodes.values() if n.name.startswith(scope + "/")]
+        gathers = [n for n in inside if n.op == "ResourceGather"]
+        assert len(gathers) == 1, "%s: expected one embedding column, found %d" % (scope, len(gathers))
+        table = self.variables[gathers[0].data_inputs()[0]]
+        fed = {i for n in inside for i in n.data_inputs() if i in self.placeholders}
+        assert len(fed) == 1, "%s reads placeholders %s" % (scope, sorted(fed))
+        ph = self.placeholders[fed.pop()]
+        self.trace.append((scope, "DenseFeatures[%s -> %s]" % (ph, self.variable_names[gathers[0].data_inputs()[0]][0])))
+        ids = np.asarray(feeds[ph]).astype(np.int64).reshape(-1)
+        assert ids.min() >= 0 and ids.max() < table.shape[0]
+        return table[ids]
+
+    def run(self, feeds):
+        """feeds: {placeholder name (e.g. "movieId"): 1-D array}.  Returns the function's output array."""
+        memo = {}
+        self.trace = []
+
+        def ev(ref):
+            if ref in memo:
+                return memo[ref]
+            name = ref.split(":")[0]
+            if name in self.placeholders:
+                out = np.asarray(feeds[self.placeholders[name]])
+            elif name in self.variables:
+                out = name                                               # a resource handle
+            else:
+                n = self.fn.nodes[name]
+                if name.endswith("/concat/concat") and name.split("/")[-3].startswith("dense_features"):   # DenseFeatures output
+                    out = self._dense_features(name[:-len("/concat/concat")], feeds)
+                else:
+                    x = [ev(i) for i in n.data_inputs()]
+                    if n.op == "Const":
+                        out = tensor_proto(get(n.attr["value"], 8)[0])
+                    elif n.op == "ReadVariableOp":
+                        out = self.variables[x[0]]
+                    elif n.op == "Identity":
+                        out = x[0]
+                    elif n.op == "ConcatV2":
+                        out = np.concatenate(x[:-1], axis=int(x[-1]))
+                    elif n.op == "MatMul":
+                        a = x[0].T if n.b("transpose_a") else x[0]
+                        b = x[1].T if n.b("transpose_b") else x[1]
+                        out = (a.astype(np.float32) @ b.astype(np.float32)).astype(np.float32)
+                    elif n.op == "BiasAdd":
+                        out = (x[0] + x[1]).astype(np.float32)
+                    elif n.op == "Relu":
+                        out = np.maximum(x[0], np.float32(0))
+                    elif n.op == "Sigmoid":
+                        out = (1.0 / (1.0 + np.exp(-x[0].astype(np.float64)))).astype(np.float32)
+                    elif n.op == "ExpandDims":
+                        out = np.expand_dims(x[0], int(x[1]))
+                    elif n.op == "BatchMatMulV2":
+                        a = np.swapaxes(x[0], -1, -2) if n.b("adj_x") else x[0]
+                        b = np.swapaxes(x[1], -1, -2) if n.b("adj_y") else x[1]
+                        out = np.matmul(a.astype(np.float32), b.astype(np.float32)).astype(np.float32)
+                    elif n.op == "Squeeze":
+                        dims = n.ints("squeeze_dims")
+                        out = np.squeeze(x[0], axis=tuple(dims)) if dims else np.squeeze(x[0])
+                    else:
+                        raise NotImplementedError("op %s (%s)" % (n.op, n.name))
+                    self.trace.append((n.name, n.op))
+            memo[ref] = out
+            return out
+
+        assert len(self.fn.outs) == 1
+        return ev(self.fn.ret[self.fn.outs[0]])

@@ -1,0 +1,52 @@
+"""Golden vectors from the reference's own serialised graphs (run where /root/reference exists):
+
+    python tests/golden/make_savedmodel_graph_vectors.py
+
+For each shipped export (`modeldata/neuralcf/{002,001}`, `modeldata/MLPRec/005`) `oracle/savedmodel_graph.py`
+reads `saved_model.pb`, follows `serving_default` to the `__inference__wrapped_model_*` function TensorFlow wrote,
+binds its variables through the export's restore function and evaluates it on the (movieId, userId) pairs of
+`samples_head.csv` plus the pair `HttpClient.main` posts (`online/util/HttpClient.java:110-147`).  Written to
+`savedmodel_graph_vectors.json`: inputs, outputs, the variable binding and the op trace - what
+`tests/test_oracle_golden.py::test_oracle_matches_the_serialised_serving_graphs` holds the oracle to.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import savedmodel_graph as G                               # noqa: E402
+from sparrowrecsys_b200 import bundle, features                        # noqa: E402
+
+REF = "/root/reference/src/main/resources/webroot/"
+EXPORTS = {"neuralcf_002": "modeldata/neuralcf/002", "neuralcf_001": "modeldata/neuralcf/001",
+           "mlprec_005": "modeldata/MLPRec/005"}
+
+
+def vectors():
+    rows = features.load_samples_csv(os.path.join(HERE, "samples_head.csv"))
+    movie = np.concatenate([np.asarray(rows["movieId"]), [52, 53]]).astype(np.int64)
+    user = np.concatenate([np.asarray(rows["userId"]), [10351, 10351]]).astype(np.int64)
+    out = {}
+    for name, rel in EXPORTS.items():
+        g = G.ServingGraph(REF + rel, bundle.read_variables)
+        feeds = {ph: np.zeros(len(movie), np.int64) for ph in g.placeholders.values()}   # unused inputs of MLPRec/005
+        feeds["movieId"], feeds["userId"] = movie, user
+        y = g.run(feeds).reshape(-1)
+        out[name] = {
+            "export": rel, "function": g.fn.name, "placeholders": sorted(g.placeholders.values()),
+            "variables": {v: k for (v, k) in g.variable_names.values()},
+            "trace": [[n, op] for n, op in g.trace],
+            "movieId": movie.tolist(), "userId": user.tolist(),
+            "output": [float(np.float32(v)) for v in y],
+        }
+    return out
+
+
+if __name__ == "__main__":
+    with open(os.path.join(HERE, "savedmodel_graph_vectors.json"), "w") as f:
+        json.dump(vectors(), f, indent=0)
+    print("wrote savedmodel_graph_vectors.json")

@@ -56,6 +56,24 @@ def test_twotowers_shipped_weights_known_answers(head_rows):
     assert np.array_equal(p, z)
 
 
+@pytest.mark.parametrize("name", ["neuralcf_002", "neuralcf_001", "mlprec_005"])
+def test_shipped_weights_against_the_serialised_serving_graphs(name):
+    """CUDA path vs the outputs of the reference's own serialised `serving_default` functions (evaluated node by
+    node by oracle/savedmodel_graph.py; tests/golden/savedmodel_graph_vectors.json): 512 head rows + the
+    HttpClient pair.  A wiring mistake (concat order, kernel binding, activation) would be an O(0.1) difference."""
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "savedmodel_graph_vectors.json")) as f:
+        v = json.load(f)[name]
+    W = load_golden_weights(name)
+    feats = {"movieId": np.array(v["movieId"], np.int32), "userId": np.array(v["userId"], np.int32)}
+    spec = default_spec("twotowers", hidden=(10,), final_dense=False) if name == "mlprec_005" else default_spec("neuralcf")
+    with _model(spec, W) as m:
+        p = m.predict(feats)
+    np.testing.assert_allclose(p[:, 0], np.array(v["output"], np.float32), rtol=0, atol=5e-6)
+
+
 def test_httpclient_pair_through_tfrecmodel_surface():
     from tfrecmodel import neuralcf
     neuralcf.load(weights=load_golden_weights("neuralcf_002"))

@@ -88,3 +88,62 @@ def test_head_fixture_is_prefix_of_reference_file():
     with open(os.path.join(GOLDEN, "samples_head.csv"), "rb") as f:
         head = f.read()
     assert ref.startswith(head)
+
+
+# ---- the reference's own serialised graphs (tests/golden/make_savedmodel_graph_vectors.py) ----------------
+def _graph_vectors():
+    with open(os.path.join(GOLDEN, "savedmodel_graph_vectors.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["neuralcf_002", "neuralcf_001", "mlprec_005"])
+def test_oracle_matches_the_serialised_serving_graphs(name):
+    """The golden outputs come from evaluating `__inference__wrapped_model_*` of the shipped `saved_model.pb` - the
+    function TensorFlow serialised for `serving_default` - node by node (oracle/savedmodel_graph.py), not from a
+    reading of the Python scripts: concat order, kernel / bias binding, activations and the Dot tail are the
+    graph's.  The oracle must reproduce them on all 512 head rows and the HttpClient pair."""
+    v = _graph_vectors()[name]
+    W = load_golden_weights(name)
+    feats = {"movieId": np.array(v["movieId"], np.int32), "userId": np.array(v["userId"], np.int32)}
+    if name == "mlprec_005":
+        p, _ = O.twotowers_forward(default_spec("twotowers", hidden=(10,), final_dense=False), W, feats)
+    else:
+        p, _ = O.neuralcf_forward(default_spec("neuralcf"), W, feats)
+    np.testing.assert_allclose(p[:, 0], np.array(v["output"], np.float32), rtol=0, atol=5e-7)
+    assert len(v["output"]) == 514
+    # the first eight rows are the known answers SURVEY.md 8c recorded, now backed by the graph itself
+    np.testing.assert_allclose(v["output"][:8], KNOWN[name], rtol=0, atol=2e-7)
+
+
+def test_serialised_graph_structure_is_what_the_loaders_assume():
+    """Facts read off the graphs that `bundle.load_neuralcf` / `load_twotowers` and the kernels hard-code."""
+    v = _graph_vectors()
+    for name in ("neuralcf_002", "neuralcf_001"):
+        g = v[name]
+        assert g["placeholders"] == ["movieId", "userId"]
+        assert g["variables"] == {
+            "dense_features/movieId_embedding/embedding_weights": "layer_with_weights-0/movieId_embedding/embedding_weights",
+            "dense_features_1/userId_embedding/embedding_weights": "layer_with_weights-1/userId_embedding/embedding_weights",
+            "dense/kernel": "layer_with_weights-2/kernel", "dense/bias": "layer_with_weights-2/bias",
+            "dense_1/kernel": "layer_with_weights-3/kernel", "dense_1/bias": "layer_with_weights-3/bias",
+            "dense_2/kernel": "layer_with_weights-4/kernel", "dense_2/bias": "layer_with_weights-4/bias"}
+        ops = [op for _, op in g["trace"]]
+        # movie embedding first, user embedding second into ONE concat (NeuralCF.py:47), relu, relu, sigmoid
+        assert ops[0].startswith("DenseFeatures[movieId") and ops[1].startswith("DenseFeatures[userId")
+        assert ops[2:4] == ["Const", "ConcatV2"]
+        assert [o for o in ops if o in ("Relu", "Sigmoid")] == ["Relu", "Relu", "Sigmoid"]
+    t = v["mlprec_005"]
+    ops = [op for _, op in t["trace"]]
+    assert t["variables"]["dense/kernel"] == "layer_with_weights-2/kernel"          # item tower = `dense`
+    assert ops[0].startswith("DenseFeatures[movieId") and ops[1:6] == ["ReadVariableOp", "MatMul", "ReadVariableOp", "BiasAdd", "Relu"]
+    assert ops[-3:] == ["BatchMatMulV2", "Squeeze", "Identity"] and "Sigmoid" not in ops   # raw Dot(axes=1) output
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
+def test_graph_vectors_regenerate_from_the_reference_exports():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(GOLDEN, "make_savedmodel_graph_vectors.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    fresh = json.loads(json.dumps(mk.vectors()))
+    assert fresh == _graph_vectors()
