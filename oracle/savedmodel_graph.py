@@ -7,11 +7,13 @@ node_def.proto / attr_value.proto / tensor.proto), follows `serving_default` -> 
 `__inference__wrapped_model_*`, binds every resource argument of that function to its checkpoint tensor through the
 export's own `__inference__traced_restore_*` function, and evaluates the function node by node in float32.
 
-What is interpreted from the graph, not from the Python script: which placeholder and which table feed each
-DenseFeatures block, the order of the concatenation, which kernel / bias every MatMul / BiasAdd reads, the
-activations, the Dot / Squeeze tail, the output tensor.  What is restated: the body of a DenseFeatures block with one
-identity-categorical embedding column (`safe_embedding_lookup_sparse`, combiner "mean", over exactly one id per row)
-is taken as "row `id` of the table the block's ResourceGather reads" instead of executing its ~90 sparse ops.
+Everything is interpreted from the graph, not from the Python script: which placeholder and which table feed each
+DenseFeatures block, the ~90 sparse ops of its embedding column (`to_sparse_input` with ignore value -1,
+SparseReshape, SparseFillEmptyRows, Unique, ResourceGather, SparseSegmentMean, Select) and its range asserts, the
+order of the concatenation, which kernel / bias every MatMul / BiasAdd reads, the activations, the Dot / Squeeze
+tail, the output tensor.  What is restated is only the meaning of each TensorFlow op in numpy (`node_value`).
+`run(..., full=False)` replaces a single-column DenseFeatures block by "row id of the table its ResourceGather
+reads"; both give the same 3 x 514 outputs bit for bit.
 
 Used by `tests/golden/make_savedmodel_graph_vectors.py` (writes `tests/golden/savedmodel_graph_vectors.json`) and
 `tests/test_oracle_golden.py`; never imported by the product.
@@ -121,6 +123,13 @@ class Node:
         v = get(self.attr.get(key, []), 5)
         return bool(v[0]) if v else default
 
+    def i(self, key, default=0):
+        v = get(self.attr.get(key, []), 3)
+        return _signed(v[0]) if v else default
+
+    def dtype(self, key):
+        return {1: np.float32, 3: np.int32, 9: np.int64, 10: np.bool_}[get(self.attr[key], 6)[0]]
+
     def ints(self, key):
         lst = get(self.attr.get(key, []), 1)
         return [_signed(x) for v in get(fields(lst[0]), 3) for x in _packed_varints(v)] if lst else []
@@ -184,73 +193,169 @@ class ServingGraph:
         self.variable_names = {a: (v, strip(key_of_var[v])) for a, v in var_of_arg.items()}
         self.trace = []                                                  # (node, op) in evaluation order
 
-    # ---- evaluation -----------------------------------------------------------------------------------------
-    def _dense_features(self, scope, feeds):
-        """One DenseFeatures block with a single identity-categorical embedding column (see the module docstring):
-        the placeholder and the table are read off the graph."""
-        inside = [n for n in self.fn.nodes.values() if n.name.startswith(scope + "/")]
-        gathers = [n for n in inside if n.op == "ResourceGather"]
-        assert len(gathers) == 1, "%s: expected one embedding column, found %d" % (scope, len(gathers))
-        table = self.variables[gathers[0].data_inputs()[0]]
-        fed = {i for n in inside for i in n.data_inputs() if i in self.placeholders}
-        assert len(fed) == 1, "%s reads placeholders %s" % (scope, sorted(fed))
-        ph = self.placeholders[fed.pop()]
-        self.trace.append((scope, "DenseFeatures[%s -> %s]" % (ph, self.variable_names[gathers[0].data_inputs()[0]][0])))
-        ids = np.asarray(feeds[ph]).astype(np.int64).reshape(-1)
-        assert ids.min() >= 0 and ids.max() < table.shape[0]
-        return table[ids]
+    def dense_features_blocks(self):
+        """{scope: (placeholder, variable node name, number of nodes)} for every DenseFeatures block of the function."""
+        out = {}
+        for n in self.fn.nodes.values():
+            if n.op != "ResourceGather":
+                continue
+            scope = "/".join(n.name.split("/")[:2])
+            inside = [m for m in self.fn.nodes.values() if m.name.startswith(scope + "/")]
+            fed = sorted({self.placeholders[i] for m in inside for i in m.data_inputs() if i in self.placeholders})
+            assert len(fed) == 1 and scope not in out
+            out[scope] = (fed[0], self.variable_names[n.data_inputs()[0]][0], len(inside))
+        return out
 
-    def run(self, feeds):
-        """feeds: {placeholder name (e.g. "movieId"): 1-D array}.  Returns the function's output array."""
+    # ---- evaluation -----------------------------------------------------------------------------------------
+    def run(self, feeds, full=True):
+        """feeds: {placeholder name (e.g. "movieId"): 1-D array}.  Returns the function's output array.
+        full=True executes every node of the function, the ~90 sparse ops of each DenseFeatures block included
+        (`to_sparse_input` -> SparseReshape -> SparseFillEmptyRows -> Unique -> ResourceGather -> SparseSegmentMean
+        -> Select) and its range asserts; full=False takes a single-column block as "row id of the table its
+        ResourceGather reads" (the shortcut the first version of the golden vectors used - kept as a cross-check)."""
         memo = {}
         self.trace = []
 
-        def ev(ref):
-            if ref in memo:
-                return memo[ref]
-            name = ref.split(":")[0]
-            if name in self.placeholders:
-                out = np.asarray(feeds[self.placeholders[name]])
-            elif name in self.variables:
-                out = name                                               # a resource handle
-            else:
-                n = self.fn.nodes[name]
-                if name.endswith("/concat/concat") and name.split("/")[-3].startswith("dense_features"):   # DenseFeatures output
-                    out = self._dense_features(name[:-len("/concat/concat")], feeds)
-                else:
-                    x = [ev(i) for i in n.data_inputs()]
-                    if n.op == "Const":
-                        out = tensor_proto(get(n.attr["value"], 8)[0])
-                    elif n.op == "ReadVariableOp":
-                        out = self.variables[x[0]]
-                    elif n.op == "Identity":
-                        out = x[0]
-                    elif n.op == "ConcatV2":
-                        out = np.concatenate(x[:-1], axis=int(x[-1]))
-                    elif n.op == "MatMul":
-                        a = x[0].T if n.b("transpose_a") else x[0]
-                        b = x[1].T if n.b("transpose_b") else x[1]
-                        out = (a.astype(np.float32) @ b.astype(np.float32)).astype(np.float32)
-                    elif n.op == "BiasAdd":
-                        out = (x[0] + x[1]).astype(np.float32)
-                    elif n.op == "Relu":
-                        out = np.maximum(x[0], np.float32(0))
-                    elif n.op == "Sigmoid":
-                        out = (1.0 / (1.0 + np.exp(-x[0].astype(np.float64)))).astype(np.float32)
-                    elif n.op == "ExpandDims":
-                        out = np.expand_dims(x[0], int(x[1]))
-                    elif n.op == "BatchMatMulV2":
-                        a = np.swapaxes(x[0], -1, -2) if n.b("adj_x") else x[0]
-                        b = np.swapaxes(x[1], -1, -2) if n.b("adj_y") else x[1]
-                        out = np.matmul(a.astype(np.float32), b.astype(np.float32)).astype(np.float32)
-                    elif n.op == "Squeeze":
-                        dims = n.ints("squeeze_dims")
-                        out = np.squeeze(x[0], axis=tuple(dims)) if dims else np.squeeze(x[0])
+        def shortcut(scope):
+            inside = [n for n in self.fn.nodes.values() if n.name.startswith(scope + "/")]
+            gathers = [n for n in inside if n.op == "ResourceGather"]
+            assert len(gathers) == 1, "%s: expected one embedding column, found %d" % (scope, len(gathers))
+            table = self.variables[gathers[0].data_inputs()[0]]
+            fed = {i for n in inside for i in n.data_inputs() if i in self.placeholders}
+            assert len(fed) == 1, "%s reads placeholders %s" % (scope, sorted(fed))
+            ids = np.asarray(feeds[self.placeholders[fed.pop()]]).astype(np.int64).reshape(-1)
+            return table[ids]
+
+        def node_value(n):
+            x = [ev(i) for i in n.data_inputs()]
+            op = n.op
+            if op == "Const":
+                return tensor_proto(get(n.attr["value"], 8)[0])
+            if op == "ReadVariableOp":
+                return self.variables[x[0]]
+            if op in ("Identity", "StopGradient"):
+                return x[0]
+            if op == "ConcatV2":
+                return np.concatenate(x[:-1], axis=int(x[-1]))
+            if op == "MatMul":
+                a = x[0].T if n.b("transpose_a") else x[0]
+                b = x[1].T if n.b("transpose_b") else x[1]
+                return (a.astype(np.float32) @ b.astype(np.float32)).astype(np.float32)
+            if op == "BiasAdd":
+                return (x[0] + x[1]).astype(np.float32)
+            if op == "Relu":
+                return np.maximum(x[0], np.float32(0))
+            if op == "Sigmoid":
+                return (1.0 / (1.0 + np.exp(-x[0].astype(np.float64)))).astype(np.float32)
+            if op == "ExpandDims":
+                return np.expand_dims(x[0], int(x[1]))
+            if op == "BatchMatMulV2":
+                a = np.swapaxes(x[0], -1, -2) if n.b("adj_x") else x[0]
+                b = np.swapaxes(x[1], -1, -2) if n.b("adj_y") else x[1]
+                return np.matmul(a.astype(np.float32), b.astype(np.float32)).astype(np.float32)
+            if op == "Squeeze":
+                dims = n.ints("squeeze_dims")
+                return np.squeeze(x[0], axis=tuple(dims)) if dims else np.squeeze(x[0])
+            # ---- the sparse embedding lookup of a DenseFeatures block ------------------------------------
+            if op in ("NotEqual", "Less", "GreaterEqual"):
+                return {"NotEqual": np.not_equal, "Less": np.less, "GreaterEqual": np.greater_equal}[op](x[0], x[1])
+            if op == "Where":
+                return np.argwhere(x[0]).astype(np.int64)
+            if op == "GatherNd":
+                return x[0][tuple(np.asarray(x[1]).T)]
+            if op == "Shape":
+                return np.array(np.shape(x[0]), dtype=n.dtype("out_type") if "out_type" in n.attr else np.int32)
+            if op == "Cast":
+                return np.asarray(x[0]).astype(n.dtype("DstT"))
+            if op == "All":
+                return np.all(x[0])
+            if op == "If":                                   # the Assert guards of the identity column
+                if not bool(x[0]):
+                    raise ValueError("assertion of the graph failed: %s" % n.name)
+                return x[1]
+            if op == "Slice":
+                begin, size = [int(v) for v in x[1]], [int(v) for v in x[2]]
+                return x[0][tuple(slice(b, None if z < 0 else b + z) for b, z in zip(begin, size))]
+            if op == "Prod":
+                return np.prod(x[0], axis=tuple(np.atleast_1d(x[1]).tolist())).astype(x[0].dtype)
+            if op == "GatherV2":
+                return np.take(x[0], x[1], axis=int(x[2]))
+            if op == "Pack":
+                return np.stack([np.asarray(v) for v in x], axis=n.i("axis", 0))
+            if op == "Reshape":
+                return np.reshape(x[0], [int(v) for v in np.atleast_1d(x[1])])
+            if op == "SparseReshape":
+                idx, shape, new = x[0], [int(v) for v in x[1]], [int(v) for v in x[2]]
+                total = int(np.prod(shape))
+                if -1 in new:
+                    new[new.index(-1)] = total // int(-np.prod(new))
+                lin = np.ravel_multi_index(tuple(idx.T), shape) if len(idx) else np.zeros(0, np.int64)
+                out = np.stack(np.unravel_index(lin, new), axis=1).astype(np.int64) if len(idx) else np.zeros((0, len(new)), np.int64)
+                return {"output_indices": out, "output_shape": np.array(new, np.int64)}
+            if op == "SparseFillEmptyRows":
+                idx, vals, shape, default = x[0], x[1], [int(v) for v in x[2]], x[3]
+                rows = shape[0]
+                present = np.zeros(rows, bool)
+                present[idx[:, 0]] = True
+                add = np.flatnonzero(~present)
+                all_idx = np.concatenate([idx, np.stack([add, np.zeros_like(add)], axis=1)], axis=0)
+                all_val = np.concatenate([vals, np.full(len(add), default, dtype=vals.dtype)])
+                order = np.lexsort((all_idx[:, 1], all_idx[:, 0]))
+                return {"output_indices": all_idx[order].astype(np.int64), "output_values": all_val[order],
+                        "empty_row_indicator": ~present, "reverse_index_map": np.argsort(order)[:len(idx)].astype(np.int64)}
+            if op == "StridedSlice":
+                begin, end, stride = ([int(v) for v in np.atleast_1d(a)] for a in x[1:4])
+                bm, em, sm = n.i("begin_mask"), n.i("end_mask"), n.i("shrink_axis_mask")
+                assert n.i("ellipsis_mask") == 0 and n.i("new_axis_mask") == 0
+                key = []
+                for d in range(len(begin)):
+                    if sm >> d & 1:
+                        key.append(begin[d])
                     else:
-                        raise NotImplementedError("op %s (%s)" % (n.op, n.name))
-                    self.trace.append((n.name, n.op))
-            memo[ref] = out
-            return out
+                        key.append(slice(None if bm >> d & 1 else begin[d], None if em >> d & 1 else end[d], stride[d]))
+                return np.asarray(x[0])[tuple(key)]
+            if op == "Unique":
+                y, first, inv = np.unique(x[0], return_index=True, return_inverse=True)
+                order = np.argsort(first)                    # TF keeps first-occurrence order
+                rank = np.empty_like(order)
+                rank[order] = np.arange(len(order))
+                return {"y": y[order], "idx": rank[inv].astype(np.int32)}
+            if op == "ResourceGather":
+                return self.variables[x[0]][np.asarray(x[1]).astype(np.int64)]
+            if op == "SparseSegmentMean":
+                data, indices, seg = x[0], np.asarray(x[1]).astype(np.int64), np.asarray(x[2]).astype(np.int64)
+                out = np.zeros((int(seg.max()) + 1 if len(seg) else 0,) + data.shape[1:], np.float32)
+                cnt = np.zeros(out.shape[0], np.float32)
+                np.add.at(out, seg, data[indices])
+                np.add.at(cnt, seg, 1)
+                return (out / np.maximum(cnt, 1)[:, None]).astype(np.float32)
+            if op == "Tile":
+                return np.tile(x[0], [int(v) for v in x[1]])
+            if op == "ZerosLike":
+                return np.zeros_like(x[0])
+            if op in ("Select", "SelectV2"):
+                return np.where(x[0], x[1], x[2])
+            raise NotImplementedError("op %s (%s)" % (op, n.name))
+
+        def ev(ref):
+            parts = ref.split(":")
+            name = parts[0]
+            if name in self.placeholders:
+                return np.asarray(feeds[self.placeholders[name]])
+            if name in self.variables:
+                return name                                              # a resource handle
+            if name not in memo:
+                n = self.fn.nodes[name]
+                for c in n.inputs:                                       # control dependencies first: the range asserts
+                    if c.startswith("^") and c[1:] in self.fn.nodes and c[1:] not in memo:
+                        ev(c[1:])
+                if not full and name.endswith("/concat/concat") and name.split("/")[-3].startswith("dense_features"):
+                    memo[name] = shortcut(name[:-len("/concat/concat")])
+                else:
+                    memo[name] = node_value(n)
+                self.trace.append((name, n.op))
+            v = memo[name]
+            return v[parts[1]] if isinstance(v, dict) else v
 
         assert len(self.fn.outs) == 1
         return ev(self.fn.ret[self.fn.outs[0]])

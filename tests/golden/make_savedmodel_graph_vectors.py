@@ -39,7 +39,12 @@ def vectors():
         out[name] = {
             "export": rel, "function": g.fn.name, "placeholders": sorted(g.placeholders.values()),
             "variables": {v: k for (v, k) in g.variable_names.values()},
-            "trace": [[n, op] for n, op in g.trace],
+            "dense_features": {k: list(v) for k, v in g.dense_features_blocks().items()},
+            "nodes_evaluated": len(g.trace),
+            "wiring": {n.name: [i.split(":")[0] for i in n.data_inputs()] for n in g.fn.nodes.values()
+                       if "/dense_features" not in n.name and n.op in ("ConcatV2", "MatMul", "BiasAdd", "BatchMatMulV2",
+                                                                      "Relu", "Sigmoid", "Squeeze", "ExpandDims")},
+            "trace": [[n, op] for n, op in g.trace if "/dense_features" not in n or n.endswith("/concat/concat")],
             "movieId": movie.tolist(), "userId": user.tolist(),
             "output": [float(np.float32(v)) for v in y],
         }

@@ -127,16 +127,54 @@ def test_serialised_graph_structure_is_what_the_loaders_assume():
             "dense/kernel": "layer_with_weights-2/kernel", "dense/bias": "layer_with_weights-2/bias",
             "dense_1/kernel": "layer_with_weights-3/kernel", "dense_1/bias": "layer_with_weights-3/bias",
             "dense_2/kernel": "layer_with_weights-4/kernel", "dense_2/bias": "layer_with_weights-4/bias"}
-        ops = [op for _, op in g["trace"]]
-        # movie embedding first, user embedding second into ONE concat (NeuralCF.py:47), relu, relu, sigmoid
-        assert ops[0].startswith("DenseFeatures[movieId") and ops[1].startswith("DenseFeatures[userId")
-        assert ops[2:4] == ["Const", "ConcatV2"]
-        assert [o for o in ops if o in ("Relu", "Sigmoid")] == ["Relu", "Relu", "Sigmoid"]
+        assert g["dense_features"] == {
+            "model/dense_features": ["movieId", "dense_features/movieId_embedding/embedding_weights", 91],
+            "model/dense_features_1": ["userId", "dense_features_1/userId_embedding/embedding_weights", 91]}
+        w = g["wiring"]
+        # movie embedding first, user embedding second into ONE concat (NeuralCF.py:47), then relu, relu, sigmoid
+        assert w["model/concatenate/concat"] == ["model/dense_features/concat/concat", "model/dense_features_1/concat/concat",
+                                                 "model/concatenate/concat/axis"]
+        assert w["model/dense/MatMul"][0] == "model/concatenate/concat" and w["model/dense/Relu"] == ["model/dense/BiasAdd"]
+        assert w["model/dense_1/MatMul"][0] == "model/dense/Relu" and w["model/dense_2/MatMul"][0] == "model/dense_1/Relu"
+        assert w["model/dense_2/Sigmoid"] == ["model/dense_2/BiasAdd"]
+        assert [op for _, op in g["trace"]][-1] == "Identity" and g["trace"][-2] == ["model/dense_2/Sigmoid", "Sigmoid"]
+        assert g["nodes_evaluated"] == 196                       # the whole function, sparse lookups and asserts included
     t = v["mlprec_005"]
-    ops = [op for _, op in t["trace"]]
+    w = t["wiring"]
     assert t["variables"]["dense/kernel"] == "layer_with_weights-2/kernel"          # item tower = `dense`
-    assert ops[0].startswith("DenseFeatures[movieId") and ops[1:6] == ["ReadVariableOp", "MatMul", "ReadVariableOp", "BiasAdd", "Relu"]
-    assert ops[-3:] == ["BatchMatMulV2", "Squeeze", "Identity"] and "Sigmoid" not in ops   # raw Dot(axes=1) output
+    assert t["dense_features"]["model/dense_features_1"][:2] == ["movieId", "dense_features_1/movieId_embedding/embedding_weights"]
+    assert t["dense_features"]["model/dense_features_2"][:2] == ["userId", "dense_features_2/userId_embedding/embedding_weights"]
+    assert w["model/dense/MatMul"][0] == "model/dense_features_1/concat/concat"     # one relu Dense per tower
+    assert w["model/dense_1/MatMul"][0] == "model/dense_features_2/concat/concat"
+    assert w["model/dot/ExpandDims"][0] == "model/dense/Relu" and w["model/dot/ExpandDims_1"][0] == "model/dense_1/Relu"
+    assert w["model/dot/Squeeze"] == ["model/dot/MatMul"]
+    assert not any(k.endswith("Sigmoid") for k in w)                                # raw Dot(axes=1) output
+    assert t["trace"][-2:] == [["model/dot/Squeeze", "Squeeze"], ["Identity", "Identity"]]
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
+def test_identity_column_edge_cases_of_the_serialised_graph():
+    """What the reference's graph itself does with odd ids: an id >= num_buckets trips the graph's own assert (our
+    ValueError / SRS_ERR_RANGE), the last valid id works, and -1 is the column's "missing" value: its embedding is
+    the zero vector (we reject -1 instead: INTEGRATION.md, error table)."""
+    from oracle import savedmodel_graph as SG
+    from sparrowrecsys_b200 import bundle
+    g = SG.ServingGraph(REFERENCE_WEBROOT + "modeldata/neuralcf/002", bundle.read_variables)
+    with pytest.raises(ValueError):
+        g.run({"movieId": np.array([5, 1001]), "userId": np.array([7, 7])})
+    with pytest.raises(ValueError):
+        g.run({"movieId": np.array([5, 5]), "userId": np.array([7, 30001])})
+    ok = g.run({"movieId": np.array([5, 1000]), "userId": np.array([7, 30000])})
+    assert ok.shape == (2, 1)
+    W = bundle.load_neuralcf(REFERENCE_WEBROOT + "modeldata/neuralcf/002")
+    missing = g.run({"movieId": np.array([-1]), "userId": np.array([7])})
+    Wz = dict(W)
+    Wz["movieId_embedding"] = W["movieId_embedding"].copy()
+    Wz["movieId_embedding"][0] = 0                            # row 0 zeroed = what a zero vector does
+    p, _ = O.neuralcf_forward(default_spec("neuralcf"), Wz, {"movieId": np.array([0], np.int32), "userId": np.array([7], np.int32)})
+    np.testing.assert_allclose(missing[:, 0], p[:, 0], rtol=0, atol=5e-7)
+    assert np.array_equal(g.run({"movieId": np.array([3, 9]), "userId": np.array([7, 8])}),
+                          g.run({"movieId": np.array([3, 9]), "userId": np.array([7, 8])}, full=False))
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
