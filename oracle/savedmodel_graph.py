@@ -189,9 +189,39 @@ class ServingGraph:
         ckpt = read_variables(os.path.join(savedmodel_dir, "variables"))
         # checkpoint keys are object-graph paths: "<path>/.ATTRIBUTES/VARIABLE_VALUE", "/" inside a name escaped as ".S"
         strip = lambda k: (k[:-len("/.ATTRIBUTES/VARIABLE_VALUE")] if k.endswith("/.ATTRIBUTES/VARIABLE_VALUE") else k).replace(".S", "/")
+        self.other_resources = {a: v for a, v in var_of_arg.items() if v not in key_of_var}   # e.g. vocabulary hash tables
+        var_of_arg = {a: v for a, v in var_of_arg.items() if v in key_of_var}
         self.variables = {a: np.asarray(ckpt[strip(key_of_var[v])], dtype=np.float32) for a, v in var_of_arg.items()}
         self.variable_names = {a: (v, strip(key_of_var[v])) for a, v in var_of_arg.items()}
+        self.top_nodes = {n.name: n for n in top}
         self.trace = []                                                  # (node, op) in evaluation order
+
+    def vocabulary_tables(self):
+        """{column (lower case, from the argument name): (keys, values, default)} for every vocabulary-list column:
+        the keys / values the export's initialisers import into its hash tables and the lookup's default value."""
+        top = self.top_nodes
+        const = lambda name: tensor_proto(get(top[name].attr["value"], 8)[0])
+        imported = {}
+        for n in top.values():
+            if n.op in ("StatefulPartitionedCall", "PartitionedCall") and "f" in n.attr:
+                fn = self.funcs[n.func()]
+                if any(m.op == "LookupTableImportV2" for m in fn.nodes.values()):
+                    t, k, v = n.data_inputs()
+                    imported[t] = (const(k), const(v))
+        out = {}
+        for arg, node in self.other_resources.items():
+            col = arg.split("dense_features_")[1].split("_indicator")[0].split("_embedding")[0]
+            if arg.endswith("table_handle"):
+                out.setdefault(col, {})["keys"], out[col]["values"] = imported[node]
+            elif arg.endswith("default_value"):
+                out.setdefault(col, {})["default"] = const(node)
+        return out
+
+    def dense_features_order(self, scope_suffix="dense_features/concat"):
+        """Column names in the order a multi-column DenseFeatures block concatenates them."""
+        n = [m for m in self.fn.nodes.values() if m.op == "ConcatV2" and m.name.endswith(scope_suffix)]
+        assert len(n) == 1
+        return [i.split(":")[0].split("/")[-2] for i in n[0].data_inputs()[:-1]]
 
     def dense_features_blocks(self):
         """{scope: (placeholder, variable node name, number of nodes)} for every DenseFeatures block of the function."""

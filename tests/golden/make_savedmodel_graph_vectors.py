@@ -48,6 +48,32 @@ def vectors():
             "movieId": movie.tolist(), "userId": user.tolist(),
             "output": [float(np.float32(v)) for v in y],
         }
+    # the older MLPRec exports are Sequential(DenseFeatures(...), Dense...) models over numeric and vocabulary-list
+    # indicator columns: no oracle graph corresponds to them, but they show what DenseFeatures and
+    # categorical_column_with_vocabulary_list do - the semantics every other graph of the oracle rests on
+    for name, rel in (("mlprec_001", "modeldata/MLPRec/001"), ("mlprec_002", "modeldata/MLPRec/002"),
+                      ("mlprec_003", "modeldata/MLPRec/003"), ("mlprec_004", "modeldata/MLPRec/004")):
+        g = G.ServingGraph(REF + rel, bundle.read_variables)
+        voc = g.vocabulary_tables()
+        casts = sorted(n.name.split("/")[-2] for n in g.fn.nodes.values()
+                       if n.op == "Cast" and n.data_inputs()[0] in g.placeholders)
+        ignore = {}
+        for n in g.fn.nodes.values():
+            if n.op == "NotEqual" and "to_sparse_input" in n.name:
+                c = g.fn.nodes[n.data_inputs()[1].split(":")[0]]
+                v = G.tensor_proto(G.get(c.attr["value"], 8)[0]).reshape(-1)[0]
+                ignore[n.name.split("/")[-3]] = v if isinstance(v, str) else int(v)
+        out[name] = {
+            "export": rel, "function": g.fn.name,
+            "dense_features_order": g.dense_features_order(),
+            "first_dense_kernel_rows": int(next(v for a, v in g.variables.items() if v.ndim == 2 and "dense_matmul" in a).shape[0]),
+            "vocabularies": {c: ([str(k) for k in t["keys"]] if t["keys"].dtype == object else
+                                 {"int_keys": int(len(t["keys"])), "keys_are_0_to_n": bool((t["keys"] == np.arange(len(t["keys"]))).all())})
+                             for c, t in sorted(voc.items())},
+            "values_are_positions": all(bool((t["values"] == np.arange(len(t["values"]))).all()) for t in voc.values()),
+            "oov_default": sorted({int(t["default"]) for t in voc.values()}),
+            "ignore_value": ignore, "int_columns_cast_to_float": casts,
+        }
     return out
 
 

@@ -152,6 +152,41 @@ def test_serialised_graph_structure_is_what_the_loaders_assume():
     assert t["trace"][-2:] == [["model/dot/Squeeze", "Squeeze"], ["Identity", "Identity"]]
 
 
+def test_feature_column_semantics_read_off_the_older_exports():
+    """`modeldata/MLPRec/001-004` are Sequential(DenseFeatures, Dense...) exports over numeric and vocabulary-list
+    columns.  No oracle graph corresponds to them, but their serialised functions show the feature-column
+    semantics every oracle graph rests on: DenseFeatures concatenates its columns sorted by column
+    NAME (numeric and categorical interleaved, `<key>_indicator` / `<key>_embedding`), integer numerics are cast to
+    float32, a vocabulary list maps word -> list position with -1 for out-of-vocabulary words, "" (strings) and -1
+    (ints) mean "no value" and contribute nothing."""
+    from sparrowrecsys_b200.spec import GENRE_VOCAB
+    v = _graph_vectors()
+    for name, width in (("mlprec_001", 6158), ("mlprec_002", 8), ("mlprec_003", 6166), ("mlprec_004", 7)):
+        g = v[name]
+        assert g["dense_features_order"] == sorted(g["dense_features_order"]), name
+        assert g["first_dense_kernel_rows"] == width
+    mixed = v["mlprec_003"]["dense_features_order"]
+    assert mixed[:6] == ["movieAvgRating", "movieGenre1_indicator", "movieGenre2_indicator", "movieGenre3_indicator",
+                         "movieId_indicator", "movieRatingCount"]             # numerics and categoricals interleave
+    assert v["mlprec_004"]["dense_features_order"] == ["movieAvgRating", "movieRatingCount", "movieRatingStddev",
+                                                       "releaseYear", "userAvgRating", "userRatingCount",
+                                                       "userRatingStddev"]    # EmbeddingMLP.py's seven numerics
+    assert v["mlprec_004"]["int_columns_cast_to_float"] == ["movieRatingCount", "releaseYear", "userRatingCount"]
+    for name in ("mlprec_001", "mlprec_003"):
+        g = v[name]
+        genres = [c for c in g["vocabularies"] if "genre" in c]
+        assert len(genres) == 8
+        for c in genres:
+            assert g["vocabularies"][c] == list(GENRE_VOCAB), c                 # same words, same order
+        assert g["values_are_positions"] and g["oov_default"] == [-1]
+        assert all(val == ("" if "Genre" in col else -1) for col, val in g["ignore_value"].items())
+        # 8 genre columns x 19 + 6 movie-id columns x 1001 (+ 8 numerics) = the first Dense layer's fan-in
+        assert 8 * 19 + 6 * 1001 + (8 if name == "mlprec_003" else 0) == g["first_dense_kernel_rows"]
+    # ... and the oracle's conventions are those: position in the list, -1 for unknown / empty words
+    f = {"movieGenre1": np.array(["Film-Noir", "Musical", "", "no-such-genre", b"Action"], dtype=object)}
+    assert O.genre_index(f, "movieGenre1").tolist() == [0, 18, -1, -1, 1]
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
 def test_identity_column_edge_cases_of_the_serialised_graph():
     """What the reference's graph itself does with odd ids: an id >= num_buckets trips the graph's own assert (our
