@@ -71,7 +71,7 @@ def test_shipped_weights_against_the_serialised_serving_graphs(name):
     spec = default_spec("twotowers", hidden=(10,), final_dense=False) if name == "mlprec_005" else default_spec("neuralcf")
     with _model(spec, W) as m:
         p = m.predict(feats)
-    np.testing.assert_allclose(p[:, 0], np.array(v["output"], np.float32), rtol=0, atol=5e-6)
+    np.testing.assert_allclose(p[:, 0], np.array(v["output"], np.float32), rtol=0, atol=PROB_ATOL)
 
 
 def test_httpclient_pair_through_tfrecmodel_surface():
