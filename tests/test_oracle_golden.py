@@ -220,3 +220,30 @@ def test_graph_vectors_regenerate_from_the_reference_exports():
     spec.loader.exec_module(mk)
     fresh = json.loads(json.dumps(mk.vectors()))
     assert fresh == _graph_vectors()
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_WEBROOT), reason="reference checkout not present")
+def test_whole_test_file_through_the_serialised_graph():
+    """All 22 440 rows of the reference's testSamples.csv through the serialised neuralcf/002 graph: the oracle agrees
+    row by row, and the accuracy / ROC-AUC recorded in full_file_stats.json are the graph's."""
+    from oracle import savedmodel_graph as SG
+    from sparrowrecsys_b200 import bundle
+    from sparrowrecsys_b200.features import load_samples_csv
+    full = load_samples_csv(REFERENCE_WEBROOT + "sampledata/testSamples.csv")
+    g = SG.ServingGraph(REFERENCE_WEBROOT + "modeldata/neuralcf/002", bundle.read_variables)
+    pg = g.run({"movieId": np.asarray(full["movieId"]), "userId": np.asarray(full["userId"])})[:, 0]
+    W = bundle.load_neuralcf(REFERENCE_WEBROOT + "modeldata/neuralcf/002")
+    po = O.predict(default_spec("neuralcf"), W, full)[:, 0]
+    assert len(pg) == 22440 and np.abs(pg - po).max() <= 5e-7
+    lab = np.asarray(full["label"])
+    with open(os.path.join(GOLDEN, "full_file_stats.json")) as f:
+        s = json.load(f)
+    assert abs(float(((pg > 0.5) == (lab == 1)).mean()) - s["accuracy"]) < 1e-9
+    order = np.argsort(pg, kind="mergesort")
+    ranks = np.empty(len(pg))
+    ranks[order] = np.arange(1, len(pg) + 1)
+    _, inv, cnt = np.unique(pg, return_inverse=True, return_counts=True)
+    ranks = (np.bincount(inv, weights=ranks) / cnt)[inv]
+    npos = int((lab == 1).sum())
+    auc = (ranks[lab == 1].sum() - npos * (npos + 1) / 2) / (npos * (len(lab) - npos))
+    assert abs(auc - s["roc_auc"]) < 1e-6
