@@ -2,7 +2,7 @@
  * srs_ctr.h - C ABI of the B200-native SparrowRecSys CTR ranking forward path.
  *
  * The reference has no FFI: its hot path is `model.predict(feature_dict)` on a
- * Keras graph (TFRecModel/src/com/sparrowrecsys/offline/tensorflow/*.py) and, at
+ * Keras graph (TFRecModel/src/com/sparrowrecsys/offline/tensorflow/<Model>.py) and, at
  * serve time, the same graph behind TF-Serving's REST `:predict`
  * (src/main/java/com/sparrowrecsys/online/recprocess/RecForYouProcess.java:113-138).
  * This header is the boundary a maintainer binds instead (ctypes stub in

@@ -251,3 +251,31 @@ def test_row_tile_barrier_protocol_model():
     assert sim.check(False, runs=21) == []
     broken = sim.check(True, runs=21)
     assert broken and any("different tiles" in m or "Deadlock" in m or "meant completion" in m for _, _, m in broken)
+
+
+def test_c_example_builds_against_the_public_header(tmp_path, have_gpu):
+    """`include/srs_ctr.h` is a C header (C99, -pedantic clean) and `examples/rank_request.c` - the ranking request
+    of RecForYouProcess.java:40-59,113-138 as one call over the C ABI, the body a JNI shim would wrap - compiles,
+    links against the library and, without a GPU, fails loudly instead of computing on the CPU."""
+    import shutil
+    import subprocess
+    from sparrowrecsys_b200 import build as B
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    B.build()
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(inc, "srs_ctr.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / "rank_request")
+    libdir = os.path.dirname(B.LIB)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc,
+                        os.path.join(ROOT, "examples", "rank_request.c"), "-L", libdir, "-lsrs_ctr",
+                        "-Wl,--unresolved-symbols=ignore-in-shared-libs", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if have_gpu:
+        assert run.returncode == 0 and "top 10 of 800 candidates" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 1 and "no CPU path" in run.stderr
